@@ -1,0 +1,335 @@
+// extern "C" entry points of libdrnmf.so (declared in include/drnmf.h).
+#include "internal.h"
+#include "../../include/drnmf.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+using namespace drnmf;
+
+namespace drnmf {
+
+static size_t al(size_t x) { return round_up_sz(x, 256); }
+
+FwdWorkspace carve_forward_ws(const drnmf_handle* h, int B, int T, void* base) {
+  FwdWorkspace w;
+  const size_t BT = (size_t)B * T, BTp = round_up_sz(BT, 128);
+  const int Bp = round_up(B, 64);
+  w.Bp = Bp;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* q = p ? p + off : nullptr; off += al(bytes); return q; };
+  w.xp_hi = (float*)take(BTp * h->Fp * 4);
+  w.xp_lo = (float*)take(BTp * h->Fp * 4);
+  w.mvalid = (float*)take(BTp * 4);
+  w.XW = (float*)take(BT * (size_t)h->K * h->Rp * 4);
+  w.Hp_hi = (float*)take(BTp * h->Rp * 4);
+  w.Hp_lo = (float*)take(BTp * h->Rp * 4);
+  w.hb_hi = (float*)take(2 * (size_t)Bp * h->Rp * 4);
+  w.hb_lo = (float*)take(2 * (size_t)Bp * h->Rp * 4);
+  w.state = (float*)take((size_t)Bp * h->Rp * 4);
+  w.psum = (float*)take(2 * 256 * (size_t)Bp * 4);
+  w.leak = (float*)take((size_t)Bp * 4);
+  w.flags = (unsigned int*)take(16384 * 4);
+  w.bytes = off;
+  return w;
+}
+
+static int check_device(const drnmf_handle* h) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device: libdrnmf has no CPU fallback"); return DRNMF_ERR_NO_DEVICE; }
+  if (h && dev != h->device) { set_error("handle belongs to device %d but device %d is current", h->device, dev); return DRNMF_ERR_INVALID; }
+  return DRNMF_OK;
+}
+
+static int pick_impl(int flags) {
+  int impl = (flags & DRNMF_IMPL_SIMT) ? DRNMF_IMPL_SIMT : DRNMF_IMPL_TCGEN05;
+  const char* e = getenv("DRNMF_IMPL");
+  if (e && !strcmp(e, "simt")) impl = DRNMF_IMPL_SIMT;
+  if (e && !strcmp(e, "tc")) impl = DRNMF_IMPL_TCGEN05;
+  return impl;
+}
+
+static int run_gemm(const drnmf_handle* h, GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
+  return h->impl == DRNMF_IMPL_SIMT ? launch_gemm_simt(epi, a, st) : launch_gemm_tc(epi, a, st);
+}
+
+static int check_dev_error(drnmf_handle* h, cudaStream_t st, const char* what) {
+  int v = 0;
+  DRNMF_CUDA(cudaMemcpyAsync(&v, h->dev_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  DRNMF_CUDA(cudaStreamSynchronize(st));
+  int g = gemm_device_error(st);
+  if (v != 0 || g != 0) {
+    set_error("%s: device-side failure code %d (gemm %d): a kernel watchdog expired or a protocol check failed", what, v, g);
+    return DRNMF_ERR_DEVICE;
+  }
+  return DRNMF_OK;
+}
+
+}  // namespace drnmf
+
+extern "C" {
+
+int drnmf_version(void) { return 100; }
+const char* drnmf_last_error(void) { return drnmf::last_error(); }
+unsigned long long drnmf_launch_count(void) { return drnmf::launch_count(); }
+
+int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags) {
+  DRNMF_CHECK(out != nullptr, "drnmf_create: out is NULL");
+  *out = nullptr;
+  DRNMF_CHECK(F >= 1 && R >= 2 && (R % 2) == 0 && K_layers >= 1, "drnmf_create: need F>=1, even R>=2, K>=1 (got F=%d R=%d K=%d)", F, R, K_layers);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: libdrnmf has no CPU fallback");
+    return DRNMF_ERR_NO_DEVICE;
+  }
+  int dev = 0;
+  DRNMF_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DRNMF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libdrnmf is built for sm_100a only and has no fallback", dev, prop.major, prop.minor);
+    return DRNMF_ERR_NO_DEVICE;
+  }
+  drnmf_handle* h = new (std::nothrow) drnmf_handle();
+  DRNMF_CHECK(h != nullptr, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->F = F; h->R = R; h->K = K_layers; h->r = R / 2;
+  h->Rp = round_up(R, 128); h->Fp = round_up(F, 32); h->Fq = round_up(F, 128);
+  h->flags = flags; h->impl = pick_impl(flags); h->device = dev; h->num_sms = prop.multiProcessorCount;
+  const size_t K = K_layers, Rp = h->Rp, Fp = h->Fp, Fq = h->Fq;
+  const size_t nS = (K > 1 ? K - 1 : 1);
+  struct { float** p; size_t n; } allocs[] = {
+      {&h->Dt_hi, K * Rp * Fp}, {&h->Dt_lo, K * Rp * Fp}, {&h->Wt_hi, K * Rp * Fp}, {&h->Wt_lo, K * Rp * Fp},
+      {&h->bias, K * Rp}, {&h->ST_hi, nS * Rp * Rp}, {&h->ST_lo, nS * Rp * Rp},
+      {&h->EcT_hi, Fq * Rp}, {&h->EcT_lo, Fq * Rp}, {&h->EnT_hi, Fq * Rp}, {&h->EnT_lo, Fq * Rp},
+      {&h->h0, Rp}, {&h->inv_norm, K * Rp}};
+  for (auto& a : allocs) {
+    cudaError_t e = cudaMalloc(a.p, a.n * sizeof(float));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu bytes failed: %s", a.n * sizeof(float), cudaGetErrorString(e));
+      drnmf_destroy(h);
+      return DRNMF_ERR_CUDA;
+    }
+  }
+  if (cudaMalloc(&h->dev_error, sizeof(int)) != cudaSuccess || cudaMemset(h->dev_error, 0, sizeof(int)) != cudaSuccess) {
+    set_error("cudaMalloc(dev_error) failed");
+    drnmf_destroy(h);
+    return DRNMF_ERR_CUDA;
+  }
+  *out = h;
+  return DRNMF_OK;
+}
+
+int drnmf_destroy(drnmf_handle* h) {
+  if (!h) return DRNMF_OK;
+  float* ptrs[] = {h->Dt_hi, h->Dt_lo, h->Wt_hi, h->Wt_lo, h->bias, h->ST_hi, h->ST_lo, h->EcT_hi, h->EcT_lo,
+                   h->EnT_hi, h->EnT_lo, h->h0, h->inv_norm};
+  for (float* p : ptrs) if (p) cudaFree(p);
+  if (h->dev_error) cudaFree(h->dev_error);
+  delete h;
+  return DRNMF_OK;
+}
+
+int drnmf_padded_dims(const drnmf_handle* h, int* Rp, int* Fp) {
+  DRNMF_CHECK(h, "NULL handle");
+  if (Rp) *Rp = h->Rp;
+  if (Fp) *Fp = h->Fp;
+  return DRNMF_OK;
+}
+
+int drnmf_set_params(drnmf_handle* h, const float* log_D, int n_log_D, const float* log_alph, int n_log_alph,
+                     int alph_dim, const float* log_lam1, int n_log_lam1, const float* log_h0, const float* k_clean,
+                     const float* k_noise, float u0_diag, float u0_off, float uk_diag, float uk_off, void* stream) {
+  DRNMF_CHECK(h, "NULL handle");
+  int rc = check_device(h);
+  if (rc) return rc;
+  DRNMF_CHECK(log_D && log_alph && log_lam1 && log_h0 && k_clean && k_noise, "drnmf_set_params: NULL parameter pointer");
+  DRNMF_CHECK(n_log_D == 1 || n_log_D == h->K, "n_log_D must be 1 or K");
+  DRNMF_CHECK(n_log_alph == 1 || n_log_alph == h->K, "n_log_alph must be 1 or K");
+  DRNMF_CHECK(n_log_lam1 == 1 || n_log_lam1 == h->K, "n_log_lam1 must be 1 or K");
+  DRNMF_CHECK(alph_dim == 1 || alph_dim == h->R, "alph_dim must be 1 or R");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->u0_d = u0_diag; h->u0_o = u0_off; h->uk_d = uk_diag; h->uk_o = uk_off;
+  rc = launch_prep_params(h, log_D, n_log_D, log_alph, n_log_alph, alph_dim, log_lam1, n_log_lam1, log_h0, k_clean,
+                          k_noise, st);
+  if (rc) return rc;
+  const size_t Rp = h->Rp, Fp = h->Fp;
+  for (int k = 1; k < h->K; ++k) {      // Gram build: S_k^T = I - (D^_k/alph_k)^T-rows . D^_k-rows
+    GemmArgs a{};
+    a.A_hi = h->Wt_hi + k * Rp * Fp; a.A_lo = h->Wt_lo + k * Rp * Fp; a.lda = (int)Fp;
+    a.B_hi = h->Dt_hi + k * Rp * Fp; a.B_lo = h->Dt_lo + k * Rp * Fp; a.ldb = (int)Fp;
+    a.M = (int)Rp; a.N = (int)Rp; a.Kd = (int)Fp;
+    a.C = h->ST_hi + (size_t)(k - 1) * Rp * Rp; a.C_lo = h->ST_lo + (size_t)(k - 1) * Rp * Rp; a.ldc = (int)Rp;
+    a.R_valid = h->R; a.M_valid = (int)Rp; a.N_valid = (int)Rp;
+    rc = run_gemm(h, EPI_GRAM, a, st);
+    if (rc) return rc;
+  }
+  h->params_set = true;
+  return DRNMF_OK;
+}
+
+size_t drnmf_workspace_bytes(const drnmf_handle* h, int B, int T) {
+  if (!h || B < 1 || T < 1) return 0;
+  return carve_forward_ws(h, B, T, nullptr).bytes;
+}
+
+int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H, float* irm, void* ws,
+                  size_t ws_bytes, void* stream) {
+  DRNMF_CHECK(h, "NULL handle");
+  int rc = check_device(h);
+  if (rc) return rc;
+  DRNMF_CHECK(h->params_set, "drnmf_forward before drnmf_set_params");
+  DRNMF_CHECK(x && ws && B >= 1 && T >= 1, "drnmf_forward: bad arguments (x=%p ws=%p B=%d T=%d)", (const void*)x, ws, B, T);
+  DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  FwdWorkspace w = carve_forward_ws(h, B, T, ws);
+  if (ws_bytes < w.bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int BT = B * T;
+  if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st))) return rc;
+  {   // input projections for every layer: XW[bt][k*Rp + j] = x~[bt] . W_k[:, j]
+    GemmArgs a{};
+    a.A_hi = w.xp_hi; a.A_lo = w.xp_lo; a.lda = h->Fp;
+    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = h->Fp;
+    a.M = BT; a.N = h->K * h->Rp; a.Kd = h->Fp;
+    a.C = w.XW; a.ldc = h->K * h->Rp; a.M_valid = BT; a.N_valid = a.N;
+    if ((rc = run_gemm(h, EPI_STORE, a, st))) return rc;
+  }
+  rc = (h->impl == DRNMF_IMPL_SIMT) ? launch_recurrent_simt(h, w, B, T, H, st) : launch_recurrent_tc(h, w, B, T, H, st);
+  if (rc) return rc;
+  if (irm) {   // recon + mask: irm = exp(log(eps + H_c E_c) - log(eps + H_c E_c + H_n E_n))
+    GemmArgs a{};
+    a.A_hi = w.Hp_hi; a.A_lo = w.Hp_lo; a.lda = h->Rp;
+    a.B_hi = h->EcT_hi; a.B_lo = h->EcT_lo; a.B2_hi = h->EnT_hi; a.B2_lo = h->EnT_lo; a.ldb = h->Rp;
+    a.M = BT; a.N = h->F; a.Kd = h->Rp;
+    a.C = irm; a.ldc = h->F; a.M_valid = BT; a.N_valid = h->F;
+    a.square = (h->flags & DRNMF_FLAG_SQUARE_IRM) ? 1 : 0;
+    if ((rc = run_gemm(h, EPI_RECON, a, st))) return rc;
+  }
+  if (h->impl != DRNMF_IMPL_SIMT) return check_dev_error(h, st, "drnmf_forward");
+  return DRNMF_OK;
+}
+
+int drnmf_get_derived(const drnmf_handle* h, int which, int k, float* out, void* stream) {
+  DRNMF_CHECK(h && out, "NULL argument");
+  DRNMF_CHECK(h->params_set, "parameters not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Rp = h->Rp, Fp = h->Fp;
+  const float* src = nullptr; size_t n = 0;
+  switch (which) {
+    case 0: DRNMF_CHECK(k >= 1 && k < h->K, "S_k exists for 1 <= k < K"); src = h->ST_hi + (size_t)(k - 1) * Rp * Rp; n = Rp * Rp; break;
+    case 1: DRNMF_CHECK(k >= 0 && k < h->K, "bad k"); src = h->Wt_hi + (size_t)k * Rp * Fp; n = Rp * Fp; break;
+    case 2: DRNMF_CHECK(k >= 0 && k < h->K, "bad k"); src = h->bias + (size_t)k * Rp; n = Rp; break;
+    case 3: src = h->h0; n = Rp; break;
+    default: DRNMF_CHECK(false, "unknown derived tensor %d", which);
+  }
+  DRNMF_CUDA(cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DRNMF_OK;
+}
+
+int drnmf_stft_frames(int nsampl, int N, int hop) {
+  if (nsampl < 0 || N <= 0 || hop <= 0) return -1;
+  int nfram = (nsampl + hop - 1) / hop;
+  return 1 + (nfram * hop + N) / hop;       // 1 + (padded_len + 2N - N)//hop
+}
+
+int drnmf_stft_mag(const float* audio, const int64_t* offs, const int32_t* lens, const int64_t* fidx, int n_utt,
+                   int max_frames, int N, int hop, int64_t total_frames, float* stack, float* mag, void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  DRNMF_CHECK(audio && offs && lens && fidx && n_utt >= 0 && (stack || mag), "drnmf_stft_mag: bad arguments");
+  return launch_stft_mag(audio, offs, lens, fidx, n_utt, max_frames, N, hop, total_frames, stack, mag, (cudaStream_t)stream);
+}
+
+size_t drnmf_istft_workspace_bytes(int64_t total_frames, int N) {
+  if (total_frames < 0 || N <= 0) return 0;
+  return al((size_t)total_frames * N * sizeof(float));
+}
+
+int drnmf_mask_istft(const float* stack, const float* mask, const int64_t* fidx, const int64_t* out_offs, int n_utt,
+                     int max_frames, int N, int hop, int64_t total_frames, float* out_audio, void* ws, size_t ws_bytes,
+                     void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  DRNMF_CHECK(stack && fidx && out_offs && out_audio && ws, "drnmf_mask_istft: bad arguments");
+  if (ws_bytes < drnmf_istft_workspace_bytes(total_frames, N)) {
+    set_error("istft workspace too small: need %zu, got %zu", drnmf_istft_workspace_bytes(total_frames, N), ws_bytes);
+    return DRNMF_ERR_WORKSPACE;
+  }
+  return launch_mask_istft(stack, mask, fidx, out_offs, n_utt, max_frames, N, hop, total_frames, (float*)ws, out_audio,
+                           (cudaStream_t)stream);
+}
+
+// ---- end-to-end with host buffers ----------------------------------------------------------------
+struct EnhWs {
+  float *x, *stack, *irm, *frames_tmp, *audio;
+  int32_t* frames;
+  int64_t *fidx, *out_offs;
+  void* fwd;
+  size_t fwd_bytes, bytes;
+};
+static EnhWs carve_enh(const drnmf_handle* h, int B, int T, int N, int hop, void* base) {
+  EnhWs e;
+  uint8_t* p = (uint8_t*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* q = p ? p + off : nullptr; off += al(bytes); return q; };
+  const size_t BT = (size_t)B * T, F = h->F;
+  const size_t L = (size_t)((long long)hop * (T - 1) - N > 0 ? (long long)hop * (T - 1) - N : 0);
+  e.x = (float*)take(BT * F * 4);
+  e.stack = (float*)take(2 * F * BT * 4);
+  e.irm = (float*)take(BT * F * 4);
+  e.frames_tmp = (float*)take(BT * (size_t)N * 4);
+  e.audio = (float*)take((size_t)B * L * 4 + 4);
+  e.frames = (int32_t*)take((size_t)B * 4);
+  e.fidx = (int64_t*)take((size_t)B * 16);
+  e.out_offs = (int64_t*)take((size_t)B * 8);
+  e.fwd_bytes = carve_forward_ws(h, B, T, nullptr).bytes;
+  e.fwd = take(e.fwd_bytes);
+  e.bytes = off;
+  return e;
+}
+
+__global__ void k_enh_tables(const int32_t* frames, int B, int T, long long L, int64_t* fidx, int64_t* out_offs) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    int n = frames[b]; if (n < 0) n = 0; if (n > T) n = T;
+    fidx[2 * b] = (int64_t)b * T; fidx[2 * b + 1] = (int64_t)b * T + n; out_offs[b] = (int64_t)b * L;
+  }
+}
+
+size_t drnmf_enhance_workspace_bytes(const drnmf_handle* h, int B, int T, int N, int hop) {
+  if (!h || B < 1 || T < 1 || N < 1 || hop < 1) return 0;
+  return carve_enh(h, B, T, N, hop, nullptr).bytes;
+}
+
+int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const float* stack_host, const int32_t* frames_host, int B,
+                       int T, int N, int hop, float mask_value, float* audio_out_host, void* ws, size_t ws_bytes,
+                       void* stream) {
+  DRNMF_CHECK(h, "NULL handle");
+  int rc = check_device(h);
+  if (rc) return rc;
+  DRNMF_CHECK(x_host && stack_host && frames_host && audio_out_host && ws, "drnmf_enhance_host: NULL argument");
+  DRNMF_CHECK(N / 2 + 1 == h->F, "N=%d does not match the model's F=%d bins", N, h->F);
+  DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  EnhWs e = carve_enh(h, B, T, N, hop, ws);
+  if (ws_bytes < e.bytes) { set_error("workspace too small: need %zu bytes, got %zu", e.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t BT = (size_t)B * T, F = h->F;
+  const long long L = (long long)hop * (T - 1) - N;
+  DRNMF_CHECK(L > 0, "utterances too short for N=%d hop=%d", N, hop);
+  DRNMF_CUDA(cudaMemcpyAsync(e.x, x_host, BT * F * 4, cudaMemcpyHostToDevice, st));
+  DRNMF_CUDA(cudaMemcpyAsync(e.stack, stack_host, 2 * F * BT * 4, cudaMemcpyHostToDevice, st));
+  DRNMF_CUDA(cudaMemcpyAsync(e.frames, frames_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  k_enh_tables<<<(B + 127) / 128, 128, 0, st>>>(e.frames, B, T, L, e.fidx, e.out_offs);
+  count_launch();
+  DRNMF_CUDA(cudaMemsetAsync(e.audio, 0, (size_t)B * L * 4, st));
+  if ((rc = drnmf_forward(h, e.x, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream))) return rc;
+  if ((rc = launch_mask_istft(e.stack, e.irm, e.fidx, e.out_offs, B, T, N, hop, (int64_t)BT, e.frames_tmp, e.audio, st))) return rc;
+  DRNMF_CUDA(cudaMemcpyAsync(audio_out_host, e.audio, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
+  DRNMF_CUDA(cudaStreamSynchronize(st));
+  return DRNMF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// C = A . B^T with fused epilogues, in two implementations over identical layouts:
+//   k_gemm_tc   : tcgen05.mma kind::tf32 with TMEM accumulators, operands staged by TMA (128B swizzle), 3xTF32
+//                 error compensation (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi) so that results keep fp32 fidelity.
+//   k_gemm_simt : CUDA-core fp32 FMAs (semantics lock / debugging).
+// Used for: the Gram build S_k (enhance.py:172-181), the input projections x~.W_k (custom_layers.py:368 hoisted out
+// of the recurrence) and recon + mask (enhance.py:269-305, custom_layers.py:24,44).
+#include "internal.h"
+#include "gemm_simt.cuh"
+
+namespace drnmf {
+
+// ------------------------------------------------------------------------------------------------
+// SIMT
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
+  float acc[4][4], acc2[4][4];
+  const int m0 = blockIdx.y * SIMT_BM, n0 = blockIdx.x * SIMT_BN;
+  simt_tile_mainloop<EPI == EPI_RECON>(a.A_hi, a.lda, a.M, a.B_hi, a.B2_hi, a.ldb, a.N, a.Kd, m0, n0, acc, acc2);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M_valid) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.N_valid) continue;
+      if (EPI == EPI_STORE) {
+        a.C[(size_t)m * a.ldc + n] = acc[i][j];
+      } else if (EPI == EPI_GRAM) {
+        float v = epi_gram_value(m, n, a.R_valid, acc[i][j]);
+        a.C[(size_t)m * a.ldc + n] = v;
+        a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(v);
+      } else {
+        a.C[(size_t)m * a.ldc + n] = epi_irm_value(acc[i][j], acc2[i][j], a.square);
+      }
+    }
+  }
+}
+
+int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
+  dim3 grid((a.N + SIMT_BN - 1) / SIMT_BN, (a.M + SIMT_BM - 1) / SIMT_BM);
+  switch (epi) {
+    case EPI_STORE: k_gemm_simt<EPI_STORE><<<grid, SIMT_THREADS, 0, st>>>(a); break;
+    case EPI_GRAM:  k_gemm_simt<EPI_GRAM><<<grid, SIMT_THREADS, 0, st>>>(a); break;
+    case EPI_RECON: k_gemm_simt<EPI_RECON><<<grid, SIMT_THREADS, 0, st>>>(a); break;
+  }
+  count_launch();
+  DRNMF_CUDA(cudaGetLastError());
+  return DRNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;          // BK = one 128-byte swizzle atom of fp32
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;             // 16 KB per operand tile
+constexpr int TC_THREADS = 192;                              // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+template <int EPI> struct TcCfg {
+  static constexpr bool DUAL = (EPI == EPI_RECON);
+  static constexpr int TILES_PER_STAGE = DUAL ? 6 : 4;        // A_hi A_lo B_hi B_lo [B2_hi B2_lo]
+  static constexpr int STAGES = DUAL ? 2 : 3;
+  static constexpr int STAGE_BYTES = TILES_PER_STAGE * TC_TILE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = DUAL ? 256 : 128;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+          const __grid_constant__ CUtensorMap tmB2_hi, const __grid_constant__ CUtensorMap tmB2_lo, GemmArgs a,
+          int* dev_error) {
+  using Cfg = TcCfg<EPI>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + Cfg::STAGES;
+  uint64_t* acc_full = empty + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int num_kb = (a.Kd + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+    if (Cfg::DUAL) { tma_prefetch_desc(&tmB2_hi); tma_prefetch_desc(&tmB2_lo); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane_id() == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(dev_error, 101); break; }
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        const int kc = kb * TC_BK;
+        tma_load_2d(st + 0 * TC_TILE_BYTES, &tmA_hi, &full[s], kc, m0);
+        tma_load_2d(st + 1 * TC_TILE_BYTES, &tmA_lo, &full[s], kc, m0);
+        tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[s], kc, n0);
+        tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full[s], kc, n0);
+        if (Cfg::DUAL) {
+          tma_load_2d(st + 4 * TC_TILE_BYTES, &tmB2_hi, &full[s], kc, n0);
+          tma_load_2d(st + 5 * TC_TILE_BYTES, &tmB2_lo, &full[s], kc, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane_id() == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+      bool ok = true;
+      for (int kb = 0; kb < num_kb && ok; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        if (!mbar_wait(&full[s], ph)) { atomicExch(dev_error, 102); ok = false; break; }
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          const uint32_t koff = ks * 32;     // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+          const uint64_t a_hi = umma_desc_k128(st + 0 * TC_TILE_BYTES + koff);
+          const uint64_t a_lo = umma_desc_k128(st + 1 * TC_TILE_BYTES + koff);
+          const uint64_t b_hi = umma_desc_k128(st + 2 * TC_TILE_BYTES + koff);
+          const uint64_t b_lo = umma_desc_k128(st + 3 * TC_TILE_BYTES + koff);
+          const bool first = (kb == 0 && ks == 0);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, !first);
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, true);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, true);
+          if (Cfg::DUAL) {
+            const uint64_t c_hi = umma_desc_k128(st + 4 * TC_TILE_BYTES + koff);
+            const uint64_t c_lo = umma_desc_k128(st + 5 * TC_TILE_BYTES + koff);
+            umma_tf32(tmem_base + TC_BN, a_lo, c_hi, idesc, !first);
+            umma_tf32(tmem_base + TC_BN, a_hi, c_lo, idesc, true);
+            umma_tf32(tmem_base + TC_BN, a_hi, c_hi, idesc, true);
+          }
+        }
+        tc_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
+      }
+      tc_commit(acc_full);                    // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane_id();
+    bool ok = mbar_wait(acc_full, 0);
+    if (!ok && lane_id() == 0) atomicExch(dev_error, 103);
+    tc_fence_after();
+    if (ok) {
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < TC_BN; c += 16) {
+        float v[16], v2[16];
+        tmem_ld16(trow + c, v);
+        if (Cfg::DUAL) tmem_ld16(trow + TC_BN + c, v2);
+        tc_wait_ld();
+        const int n = n0 + c;
+        if (m < a.M_valid) {
+          if (EPI == EPI_STORE) {
+            if (n < a.N_valid) {
+              float4* dst = reinterpret_cast<float4*>(a.C + (size_t)m * a.ldc + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          } else if (EPI == EPI_GRAM) {
+            if (n < a.N_valid) {
+              float hi[16], lo[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { hi[i] = epi_gram_value(m, n + i, a.R_valid, v[i]); lo[i] = tf32_lo(hi[i]); }
+              float4* d1 = reinterpret_cast<float4*>(a.C + (size_t)m * a.ldc + n);
+              float4* d2 = reinterpret_cast<float4*>(a.C_lo + (size_t)m * a.ldc + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                d1[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                d2[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n + i < a.N_valid) a.C[(size_t)m * a.ldc + n + i] = epi_irm_value(v[i], v2[i], a.square);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+template <int EPI>
+static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
+  using Cfg = TcCfg<EPI>;
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo;
+  int rc;
+  if ((rc = make_tmap_2d(&tA_hi, a.A_hi, a.Kd, a.M, a.lda, TC_BK, TC_BM))) return rc;
+  if ((rc = make_tmap_2d(&tA_lo, a.A_lo, a.Kd, a.M, a.lda, TC_BK, TC_BM))) return rc;
+  if ((rc = make_tmap_2d(&tB_hi, a.B_hi, a.Kd, a.N, a.ldb, TC_BK, TC_BN))) return rc;
+  if ((rc = make_tmap_2d(&tB_lo, a.B_lo, a.Kd, a.N, a.ldb, TC_BK, TC_BN))) return rc;
+  tB2_hi = tB_hi; tB2_lo = tB_lo;
+  if (Cfg::DUAL) {
+    if ((rc = make_tmap_2d(&tB2_hi, a.B2_hi, a.Kd, a.N, a.ldb, TC_BK, TC_BN))) return rc;
+    if ((rc = make_tmap_2d(&tB2_lo, a.B2_lo, a.Kd, a.N, a.ldb, TC_BK, TC_BN))) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRNMF_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM);
+  k_gemm_tc<EPI><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo, a, dev_error);
+  count_launch();
+  DRNMF_CUDA(cudaGetLastError());
+  return DRNMF_OK;
+}
+
+static int* g_gemm_dev_error = nullptr;   // lazily allocated error word for handle-less GEMM users
+
+int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
+  DRNMF_CHECK(a.lda % 4 == 0 && a.ldb % 4 == 0, "tcgen05 GEMM needs row strides that are multiples of 4 floats");
+  if (epi != EPI_RECON) DRNMF_CHECK(a.ldc % 4 == 0 && a.N_valid % 16 == 0, "tcgen05 GEMM store needs ldc%%4==0, N%%16==0");
+  if (!g_gemm_dev_error) {
+    DRNMF_CUDA(cudaMalloc(&g_gemm_dev_error, sizeof(int)));
+    DRNMF_CUDA(cudaMemset(g_gemm_dev_error, 0, sizeof(int)));
+  }
+  switch (epi) {
+    case EPI_STORE: return launch_tc_impl<EPI_STORE>(a, st, g_gemm_dev_error);
+    case EPI_GRAM:  return launch_tc_impl<EPI_GRAM>(a, st, g_gemm_dev_error);
+    case EPI_RECON: return launch_tc_impl<EPI_RECON>(a, st, g_gemm_dev_error);
+  }
+  return DRNMF_ERR_INVALID;
+}
+
+int gemm_device_error(cudaStream_t st) {
+  if (!g_gemm_dev_error) return 0;
+  int v = 0;
+  if (cudaMemcpyAsync(&v, g_gemm_dev_error, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  return v;
+}
+
+}  // namespace drnmf

@@ -1,0 +1,79 @@
+// Internal declarations shared by the translation units of libdrnmf.so (not part of the C-ABI).
+#pragma once
+#include "common.cuh"
+
+struct drnmf_handle {
+  int F, R, K, r;      // bins, atoms (speech+noise), layers, atoms per source
+  int Rp, Fp, Fq;      // R padded to 128, F padded to 32 (GEMM K dim), F padded to 128 (GEMM N dim rows)
+  int flags, impl, device, num_sms;
+  bool params_set;
+  // derived from the parameters, owned by the handle (device memory)
+  float *Dt_hi, *Dt_lo;    // K x Rp x Fp   rows j: D^_k[:, j]            (hi = fp32 value, lo = value - tf32_trunc)
+  float *Wt_hi, *Wt_lo;    // K x Rp x Fp   rows j: D^_k[:, j] / alph_kj   = W_k^T      (enhance.py:183-195)
+  float *bias;             // K x Rp        b_k = -lam_k / alph_kj                      (enhance.py:197-204)
+  float *ST_hi, *ST_lo;    // (K-1) x Rp x Rp   S_k^T[j][i] = delta_ij - (1/alph_kj) d^_j . d^_i   (enhance.py:172-181)
+  float *EcT_hi, *EcT_lo;  // Fq x Rp       exp(k_clean)^T in columns [0,r), zero elsewhere   (custom_layers.py:24)
+  float *EnT_hi, *EnT_lo;  // Fq x Rp       exp(k_noise)^T in columns [r,R), zero elsewhere
+  float *h0;               // Rp            softplus(log_h0)                            (custom_layers.py:206)
+  float *inv_norm;         // K x Rp scratch
+  float u0_d, u0_o, uk_d, uk_o;
+  int* dev_error;          // device-side error word (watchdogs / protocol violations)
+};
+
+namespace drnmf {
+
+void count_launch(int n = 1);
+
+// ---- workspace carving for forward ------------------------------------------------------------
+struct FwdWorkspace {
+  float *xp_hi, *xp_lo;     // BT x Fp     masked, zero-padded input and its tf32 remainder
+  float* mvalid;            // BT          1.0 where the frame is valid (Keras Masking)
+  float* XW;                // BT x (K*Rp) input projections x~_t . W_k for every layer
+  float *Hp_hi, *Hp_lo;     // BT x Rp     padded output sequence (A operand of the recon GEMM)
+  float *hb_hi, *hb_lo;     // 2 x Bp x Rp ping-pong hidden state between layers
+  float* state;             // Bp x Rp     recurrent state (last layer of the previous valid frame)
+  float* psum;              // 2 x 256 x Bp partial row sums of the state (rank-1 leak)
+  float* leak;              // Bp          SIMT path: sum_j state[b][j]
+  unsigned int* flags;      // device flags for the persistent kernel
+  size_t bytes;
+  int Bp;
+};
+FwdWorkspace carve_forward_ws(const drnmf_handle* h, int B, int T, void* base);
+
+// ---- prep.cu -----------------------------------------------------------------------------------
+int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const float* log_alph, int n_log_alph,
+                       int alph_dim, const float* log_lam1, int n_log_lam1, const float* log_h0, const float* k_clean,
+                       const float* k_noise, cudaStream_t st);
+int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st);
+
+// ---- gemm: C = A (M x K, K-major) . B^T (N x K, K-major) with a fused epilogue --------------------
+enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2 };
+struct GemmArgs {
+  const float *A_hi, *A_lo; int lda;     // M x Kd
+  const float *B_hi, *B_lo; int ldb;     // N x Kd
+  const float *B2_hi, *B2_lo;            // second B (EPI_RECON: noise dictionary)
+  int M, N, Kd;                          // logical extents (tiles beyond are zero-filled)
+  float *C, *C_lo; int ldc;              // outputs
+  int R_valid, N_valid, M_valid;         // masks for the epilogues
+  int square;                            // EPI_RECON: transform_before_irm == 'square'
+};
+int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
+int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
+
+// ---- recurrent.cu ----------------------------------------------------------------------------------
+int launch_recurrent_simt(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
+int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
+
+// ---- stft.cu -------------------------------------------------------------------------------------
+// fidx: (n_utt, 2) int64 (start, end) frame indices per utterance, the reference's fidx (util.py:335-337)
+int launch_stft_mag(const float* audio, const int64_t* offs, const int32_t* lens, const int64_t* fidx, int n_utt,
+                    int max_frames, int N, int hop, int64_t total_frames, float* stack, float* mag, cudaStream_t st);
+int launch_mask_istft(const float* stack, const float* mask, const int64_t* fidx, const int64_t* out_offs, int n_utt,
+                      int max_frames, int N, int hop, int64_t total_frames, float* frames_tmp, float* out_audio,
+                      cudaStream_t st);
+int launch_init_state(const drnmf_handle* h, FwdWorkspace& w, cudaStream_t st);
+int gemm_device_error(cudaStream_t st);
+const char* last_error();
+unsigned long long launch_count();
+
+}  // namespace drnmf

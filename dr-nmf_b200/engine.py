@@ -1,0 +1,213 @@
+"""Thin torch-tensor wrapper of the libdrnmf C-ABI.
+
+PyTorch is plumbing here: device memory, the current CUDA stream and (for training) torch.distributed.  Every
+number is produced by the hand-written sm_100a kernels behind include/drnmf.h; nothing falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PARAM_KEYS = ("log_D", "log_alph", "log_lam1", "log_U1", "log_Uk", "log_h0", "k_clean", "k_noise")
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.DrnmfError(5, "no CUDA device visible: the DR-NMF path runs on B200 only (no CPU fallback)")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def structured_u(log_U, what="log_U"):
+    """(diag, off) of exp(log_U)^T, verifying the a*I + b*11^T structure build_alt creates (enhance.py:163-167)."""
+    U = torch.as_tensor(np.asarray(log_U) if not torch.is_tensor(log_U) else log_U).detach().float().cpu()
+    R = U.shape[0]
+    if U.ndim != 2 or U.shape[1] != R:
+        raise ValueError("%s must be square" % what)
+    d = torch.diagonal(U)
+    eye = torch.eye(R, dtype=torch.bool)
+    off = U[~eye]
+    if not (bool((d == d[0]).all()) and (off.numel() == 0 or bool((off == off[0]).all()))):
+        raise NotImplementedError(
+            "%s is not of the (a*I + b*11^T) form build_alt creates; a dense recurrent U is not supported by the "
+            "fixed kernel (custom_layers.py:362 multiplies by it densely)" % what)
+    dv = float(torch.exp(d[0]))
+    ov = float(torch.exp(off[0])) if off.numel() else 0.0
+    return dv, ov
+
+
+class DrnmfEngine:
+    """One DR-NMF model instance on the current CUDA device (drnmf_create .. drnmf_destroy)."""
+
+    def __init__(self, F, R, K_layers, square_irm=False, impl=None):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.F, self.R, self.K = int(F), int(R), int(K_layers)
+        flags = (_lib.FLAG_SQUARE_IRM if square_irm else 0)
+        if impl == "simt":
+            flags |= _lib.IMPL_SIMT
+        h = C.c_void_p()
+        _lib.check(self.lib.drnmf_create(C.byref(h), self.F, self.R, self.K, flags))
+        self.h = h
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self._ws = None
+        self._ews = None
+        self._keep = None
+        rp, fp = C.c_int(), C.c_int()
+        _lib.check(self.lib.drnmf_padded_dims(self.h, C.byref(rp), C.byref(fp)))
+        self.Rp, self.Fp = rp.value, fp.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.drnmf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def set_params(self, p):
+        """p: dict with PARAM_KEYS (numpy or torch).  log_D (K|1,F,R) or (F,R); log_alph (K|1,) / (K|1,R) / scalar;
+        log_lam1 (K|1,) or scalar; log_U1/log_Uk (R,R) or (diag, off) tuples; log_h0 (R,); k_clean/k_noise (R/2,F)."""
+        dev = self.device
+
+        def t(a):
+            if torch.is_tensor(a):
+                return a.detach().to(dev, torch.float32).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float32)), device=dev)
+
+        log_D = t(p["log_D"])
+        if log_D.ndim == 2:
+            log_D = log_D[None]
+        log_alph = t(p["log_alph"])
+        if log_alph.ndim == 0:
+            log_alph = log_alph.reshape(1, 1)
+        elif log_alph.ndim == 1:
+            # (K,) scalars per layer, or (R,) untied-alph vector of a tied model
+            if log_alph.shape[0] in (1, self.K):
+                log_alph = log_alph.reshape(-1, 1)
+            elif log_alph.shape[0] == self.R:
+                log_alph = log_alph.reshape(1, -1)
+            else:
+                raise ValueError("log_alph has %d entries; expected 1, K or R" % log_alph.shape[0])
+        log_lam1 = t(p["log_lam1"]).reshape(-1)
+        log_h0 = t(p["log_h0"]).reshape(-1)
+        k_clean, k_noise = t(p["k_clean"]), t(p["k_noise"])
+        if tuple(log_D.shape[1:]) != (self.F, self.R):
+            raise ValueError("log_D must be (K, F, R) = (*, %d, %d), got %s" % (self.F, self.R, tuple(log_D.shape)))
+        if tuple(k_clean.shape) != (self.R // 2, self.F) or tuple(k_noise.shape) != (self.R // 2, self.F):
+            raise ValueError("k_clean / k_noise must be (R/2, F) Keras Dense kernels")
+        if log_h0.numel() != self.R:
+            raise ValueError("log_h0 must have R entries")
+        u1 = p["log_U1"] if isinstance(p["log_U1"], tuple) else structured_u(p["log_U1"], "log_U1")
+        uk = p["log_Uk"] if isinstance(p["log_Uk"], tuple) else structured_u(p["log_Uk"], "log_Uk")
+        self._keep = (log_D, log_alph, log_lam1, log_h0, k_clean, k_noise)
+        _lib.check(self.lib.drnmf_set_params(
+            self.h, _ptr(log_D), log_D.shape[0], _ptr(log_alph), log_alph.shape[0], log_alph.shape[1], _ptr(log_lam1),
+            log_lam1.shape[0], _ptr(log_h0), _ptr(k_clean), _ptr(k_noise), u1[0], u1[1], uk[0], uk[1], _stream()))
+
+    # ---- inference ----------------------------------------------------------------------------
+    def _workspace(self, nbytes, which="_ws"):
+        ws = getattr(self, which)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            setattr(self, which, ws)
+        off = (-ws.data_ptr()) % 256
+        return C.c_void_p(ws.data_ptr() + off), ws.numel() - off
+
+    def forward(self, x, mask_value=-1.0, want_H=True, want_irm=True):
+        """x: (B,T,F) float32 CUDA tensor padded with mask_value -> (H (B,T,R) | None, irm (B,T,F) | None)."""
+        if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32):
+            raise TypeError("x must be a float32 CUDA tensor (the product path has no CPU implementation)")
+        x = x.contiguous()
+        B, T, F = x.shape
+        if F != self.F:
+            raise ValueError("x has %d features, model expects %d" % (F, self.F))
+        H = torch.empty((B, T, self.R), dtype=torch.float32, device=x.device) if want_H else None
+        irm = torch.empty((B, T, F), dtype=torch.float32, device=x.device) if want_irm else None
+        need = self.lib.drnmf_workspace_bytes(self.h, B, T)
+        ws, wsb = self._workspace(need)
+        _lib.check(self.lib.drnmf_forward(self.h, _ptr(x), B, T, float(mask_value), _ptr(H), _ptr(irm), ws, wsb,
+                                          _stream()))
+        return H, irm
+
+    def enhance_host(self, x_host, stack_host, frames_host, N, hop, mask_value=-1.0, out=None):
+        """End-to-end with HOST tensors (pinned recommended): magnitudes (B,T,F) + [Re;Im] stack (2F, B*T) ->
+        enhanced audio (B, hop*(T-1)-N) on the host.  H2D/D2H copies happen inside the call."""
+        B, T, F = x_host.shape
+        L = hop * (T - 1) - N
+        if out is None:
+            out = torch.empty((B, L), dtype=torch.float32).pin_memory()
+        need = self.lib.drnmf_enhance_workspace_bytes(self.h, B, T, N, hop)
+        ws, wsb = self._workspace(need, "_ews")
+        _lib.check(self.lib.drnmf_enhance_host(self.h, _ptr(x_host), _ptr(stack_host), _ptr(frames_host), B, T, N, hop,
+                                               float(mask_value), _ptr(out), ws, wsb, _stream()))
+        return out
+
+    def derived(self, which, k=0):
+        n = {0: self.Rp * self.Rp, 1: self.Rp * self.Fp, 2: self.Rp, 3: self.Rp}[which]
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.drnmf_get_derived(self.h, which, k, _ptr(out), _stream()))
+        return out.reshape({0: (self.Rp, self.Rp), 1: (self.Rp, self.Fp), 2: (self.Rp,), 3: (self.Rp,)}[which])
+
+
+# ---- STFT / iSTFT ------------------------------------------------------------------------------
+def stft_frames(nsampl, N, hop):
+    return _lib.load().drnmf_stft_frames(int(nsampl), int(N), int(hop))
+
+
+def stft_mag(audio, offs, lens, N, hop, want_stack=True, want_mag=True):
+    """audio: 1-D float32 CUDA tensor holding all utterances; offs/lens: per-utterance start/length (python lists).
+    Returns (stack (2F, total) | None, mag (total, F) | None, fidx (n_utt,2) int64 CUDA tensor)."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = audio.device
+    n_utt = len(lens)
+    frames = [lib.drnmf_stft_frames(int(n), N, hop) for n in lens]
+    starts = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+    total = int(starts[-1])
+    fidx = torch.as_tensor(np.stack([starts[:-1], starts[1:]], axis=1).copy(), device=dev)
+    F = N // 2 + 1
+    offs_t = torch.as_tensor(np.asarray(offs, dtype=np.int64), device=dev)
+    lens_t = torch.as_tensor(np.asarray(lens, dtype=np.int32), device=dev)
+    stack = torch.empty((2 * F, total), dtype=torch.float32, device=dev) if want_stack else None
+    mag = torch.empty((total, F), dtype=torch.float32, device=dev) if want_mag else None
+    _lib.check(lib.drnmf_stft_mag(_ptr(audio), _ptr(offs_t), _ptr(lens_t), _ptr(fidx), n_utt, max(frames) if frames else 0,
+                                  N, hop, total, _ptr(stack), _ptr(mag), _stream()))
+    return stack, mag, fidx
+
+
+def mask_istft(stack, mask, fidx, N, hop):
+    """stack (2F,total) CUDA, mask (total,F) CUDA or None, fidx (n_utt,2) int64 -> list of 1-D CUDA tensors."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = stack.device
+    fi = fidx.detach().cpu().numpy().astype(np.int64)
+    n_utt = fi.shape[0]
+    counts = (fi[:, 1] - fi[:, 0]).astype(np.int64)
+    out_lens = np.maximum(hop * (counts - 1) - N, 0)
+    out_offs = np.concatenate([[0], np.cumsum(out_lens)]).astype(np.int64)
+    out = torch.zeros(int(out_offs[-1]) + 1, dtype=torch.float32, device=dev)
+    total = stack.shape[1]
+    nb = lib.drnmf_istft_workspace_bytes(total, N)
+    ws = torch.empty(nb + 256, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    fidx_d = fidx.to(dev, torch.int64).contiguous()
+    offs_d = torch.as_tensor(out_offs[:-1].copy(), device=dev)
+    _lib.check(lib.drnmf_mask_istft(_ptr(stack), _ptr(mask), _ptr(fidx_d), _ptr(offs_d), n_utt,
+                                    int(counts.max()) if n_utt else 0, N, hop, total, _ptr(out),
+                                    C.c_void_p(ws.data_ptr() + off), nb, _stream()))
+    return [out[int(out_offs[u]):int(out_offs[u + 1])] for u in range(n_utt)]

@@ -1,0 +1,115 @@
+/* libdrnmf.so -- C-ABI of the B200-native DR-NMF hot path.
+ *
+ * The reference (stwisdom/dr-nmf) has no FFI: its hot path sits behind Python-level interfaces (Keras layers,
+ * a MATLAB subprocess, numpy/librosa helpers).  Each entry point below states the reference interface it
+ * replaces (file:line relative to the reference repo); INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - return 0 = ok, nonzero = error (drnmf_status); drnmf_last_error() gives the message of the last failure
+ *     on the calling thread.  Nothing is silently dropped (the reference constructs-and-drops its errors,
+ *     snmf.py:105-106).
+ *   - all `const float*` / `float*` arguments are DEVICE pointers unless the name ends in `_host`.
+ *   - the caller owns every input/output/workspace buffer; the library only owns what a handle derives from the
+ *     parameters (Gram matrices, normalised dictionaries).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  A handle is bound to the device that
+ *     was current at creation and is not thread-safe (one handle per GPU process).
+ *   - there is no CPU fallback: without an sm_100 device every compute call fails with DRNMF_ERR_NO_DEVICE.
+ *   - all arithmetic is fp32 storage; contractions run on tcgen05 tensor cores as 3xTF32 (error-compensated).
+ */
+#ifndef DRNMF_H_
+#define DRNMF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DRNMF_API __attribute__((visibility("default")))
+#else
+#define DRNMF_API
+#endif
+
+typedef struct drnmf_handle drnmf_handle;
+
+enum drnmf_status {
+  DRNMF_OK = 0,
+  DRNMF_ERR_INVALID = 1,
+  DRNMF_ERR_CUDA = 2,
+  DRNMF_ERR_WORKSPACE = 3,
+  DRNMF_ERR_DEVICE = 4,
+  DRNMF_ERR_NO_DEVICE = 5
+};
+
+/* drnmf_create flags */
+#define DRNMF_IMPL_TCGEN05 0      /* default: tcgen05/TMEM/TMA kernels                                        */
+#define DRNMF_IMPL_SIMT 1         /* plain CUDA-core fp32 kernels (semantics lock / debugging; same layouts)  */
+#define DRNMF_FLAG_SQUARE_IRM 16  /* transform_before_irm == 'square' (enhance.py:294-300)                    */
+
+DRNMF_API int drnmf_version(void);
+DRNMF_API const char* drnmf_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
+DRNMF_API unsigned long long drnmf_launch_count(void);
+
+/* ---- model handle: SimpleDeepRNN + recon + mask  (custom_layers.py:104-412, enhance.py:139-317) ---------- */
+DRNMF_API int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags);
+DRNMF_API int drnmf_destroy(drnmf_handle* h);
+
+/* Replaces SimpleDeepRNN.build + the build_alt maps (custom_layers.py:187-294, enhance.py:163-204): derives
+ * D^_k, W_k = D^_k/alph_k, S_k = (I - (D^_k/alph_k)^T D^_k)^T, b_k = -lam_k/alph_k, h0 = softplus(log_h0) and
+ * the recon kernels exp(k_clean), exp(k_noise) (custom_layers.py:24) on the device.
+ *   log_D     (n_log_D, F, R)            n_log_D    in {1 (tied), K}
+ *   log_alph  (n_log_alph, alph_dim)     n_log_alph in {1, K}, alph_dim in {1, R ('untie_alph', enhance.py:225)}
+ *   log_lam1  (n_log_lam1)               n_log_lam1 in {1, K}
+ *   log_h0 (R) ; k_clean, k_noise (R/2, F)  -- Keras kernel layout of DenseNonNegW (enhance.py:283,292)
+ *   u0_diag/u0_off, uk_diag/uk_off: diagonal / off-diagonal value of exp(log_U1)^T and exp(log_Uk)^T
+ *   (enhance.py:163-167); only that (a*I + b*11^T) structure is supported -- it is what build_alt creates. */
+DRNMF_API int drnmf_set_params(drnmf_handle* h, const float* log_D, int n_log_D, const float* log_alph, int n_log_alph,
+                     int alph_dim, const float* log_lam1, int n_log_lam1, const float* log_h0,
+                     const float* k_clean, const float* k_noise, float u0_diag, float u0_off, float uk_diag,
+                     float uk_off, void* stream);
+
+DRNMF_API size_t drnmf_workspace_bytes(const drnmf_handle* h, int B, int T);
+
+/* Replaces model_irm.predict_on_batch (enhance.py:1191-1193): Masking(mask_value) -> SimpleDeepRNN -> recon ->
+ * divide_A_by_AplusB.  x (B,T,F) padded with mask_value; H (B,T,R) and irm (B,T,F) outputs (either may be NULL). */
+DRNMF_API int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H, float* irm, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* Debug/inspection: copy a derived tensor to a caller device buffer.  which: 0 = S_k^T (Rp x Rp, k>=1),
+ * 1 = W_k^T (Rp x Fp), 2 = b_k (Rp), 3 = h0 (Rp).  Rp/Fp via drnmf_padded_dims. */
+DRNMF_API int drnmf_get_derived(const drnmf_handle* h, int which, int k, float* out, void* stream);
+DRNMF_API int drnmf_padded_dims(const drnmf_handle* h, int* Rp, int* Fp);
+
+/* ---- STFT analysis / masked synthesis (util.py:171-226, :48-169; audio_dataset.py:194,22-23,267-278) -------
+ * Utterance u occupies audio[offs[u] .. offs[u]+lens[u]) and frames [fidx[u][0], fidx[u][1]) of the stacks; fidx is
+ * the reference's (n_utt, 2) (start, end) table (util.py:335-337) as int64.  max_frames >= max_u frames_u.
+ * stft_frames(n, N, hop) = ceil(n/hop) + N/hop + 1 (util.py:184-190 + librosa center=False).
+ * stack is the reference's [Re; Im] layout (2F, total_frames) row-major (util.py:351); mag is (total_frames, F)
+ * row-major, i.e. already the (T,F) slices enhance.py feeds the network.  Either output may be NULL. */
+DRNMF_API int drnmf_stft_frames(int nsampl, int N, int hop);
+DRNMF_API int drnmf_stft_mag(const float* audio, const int64_t* offs, const int32_t* lens, const int64_t* fidx, int n_utt,
+                   int max_frames, int N, int hop, int64_t total_frames, float* stack, float* mag, void* stream);
+/* Replaces AudioDataset.reconstruct_x (audio_dataset.py:267-278): mask (total_frames, F) row-major (may be NULL),
+ * out_audio: utterance u written at out_offs[u], length hop*(frames_u-1) - N  (istft_mc trims N both ends). */
+DRNMF_API int drnmf_mask_istft(const float* stack, const float* mask, const int64_t* fidx, const int64_t* out_offs, int n_utt,
+                     int max_frames, int N, int hop, int64_t total_frames, float* out_audio, void* ws,
+                     size_t ws_bytes, void* stream);
+DRNMF_API size_t drnmf_istft_workspace_bytes(int64_t total_frames, int N);
+
+/* ---- end-to-end inference with HOST buffers (enhance.py:1186-1203 predict + reconstruct loop) -------------
+ * x_host (B,T,F) padded magnitudes, stack_host (2F, B*T) [Re;Im] of the same utterances laid out utterance-major
+ * with T frames each, frames_host[B] valid frame counts; audio_out_host (B, hop*(T-1)-N) zero beyond each
+ * utterance's length.  H2D and D2H copies happen inside (pinned memory recommended). */
+DRNMF_API int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const float* stack_host, const int32_t* frames_host,
+                       int B, int T, int N, int hop, float mask_value, float* audio_out_host, void* ws,
+                       size_t ws_bytes, void* stream);
+DRNMF_API size_t drnmf_enhance_workspace_bytes(const drnmf_handle* h, int B, int T, int N, int hop);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRNMF_H_ */

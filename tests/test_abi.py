@@ -1,0 +1,51 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/drnmf.h declares, and
+refuses to compute without a B200 (no fallback)."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from drnmf_b200 import _lib, engine
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _lib.header_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libdrnmf.so does not export %s" % n
+    assert lib.drnmf_version() >= 100
+
+
+def test_host_only_entry_points():
+    lib = _lib.load()
+    # stft_frames follows util.py:184-190 + librosa center=False
+    assert lib.drnmf_stft_frames(48000, 512, 128) == 380
+    assert lib.drnmf_stft_frames(48000, 1024, 256) == 193
+    assert lib.drnmf_stft_frames(48000, 2048, 512) == 99
+    assert lib.drnmf_stft_frames(333, 64, 16) == 26
+    assert lib.drnmf_istft_workspace_bytes(10, 64) >= 10 * 64 * 4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.drnmf_create(ctypes.byref(h), 33, 16, 3, 0)
+    assert rc == 5, "expected DRNMF_ERR_NO_DEVICE"
+    assert b"no CPU fallback" in lib.drnmf_last_error()
+    with pytest.raises(_lib.DrnmfError):
+        engine.DrnmfEngine(33, 16, 3)
+    with pytest.raises(TypeError):
+        engine.DrnmfEngine.forward(object.__new__(engine.DrnmfEngine), torch.zeros(1, 2, 3))
+
+
+def test_structured_u_detection():
+    import numpy as np
+    R = 6
+    e = np.float32(1e-7)
+    d, o = engine.structured_u(np.log(e + np.eye(R, dtype=np.float32)))
+    assert abs(d - 1.0) < 1e-6 and abs(o - 1e-7) < 1e-12
+    with pytest.raises(NotImplementedError):
+        engine.structured_u(np.random.default_rng(0).standard_normal((R, R)))
