@@ -129,6 +129,7 @@ int drnmf_destroy(drnmf_handle* h) {
                    h->EnT_hi, h->EnT_lo, h->h0, h->inv_norm};
   for (float* p : ptrs) if (p) cudaFree(p);
   if (h->dev_error) cudaFree(h->dev_error);
+  if (h->ev_ready) for (auto& e : h->ev) cudaEventDestroy(e);
   delete h;
   return DRNMF_OK;
 }
@@ -188,7 +189,14 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
   if (ws_bytes < w.bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   const int BT = B * T;
+  if (!h->ev_ready) {
+    for (auto& e : h->ev) DRNMF_CUDA(cudaEventCreate(&e));
+    h->ev_ready = true;
+  }
+  h->ev_valid = false;
+  DRNMF_CUDA(cudaEventRecord(h->ev[0], st));
   if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st))) return rc;
+  DRNMF_CUDA(cudaEventRecord(h->ev[1], st));
   {   // input projections for every layer: XW[bt][k*Rp + j] = x~[bt] . W_k[:, j]
     GemmArgs a{};
     a.A_hi = w.xp_hi; a.A_lo = w.xp_lo; a.lda = h->Fp;
@@ -197,8 +205,16 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
     a.C = w.XW; a.ldc = h->K * h->Rp; a.M_valid = BT; a.N_valid = a.N;
     if ((rc = run_gemm(h, EPI_STORE, a, st))) return rc;
   }
-  rc = (h->impl == DRNMF_IMPL_SIMT) ? launch_recurrent_simt(h, w, B, T, H, st) : launch_recurrent_tc(h, w, B, T, H, st);
+  DRNMF_CUDA(cudaEventRecord(h->ev[2], st));
+  {
+    bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
+    const char* e = getenv("DRNMF_RECURRENT");      // debugging aid: mix tcgen05 GEMMs with the SIMT recurrence
+    if (e && !strcmp(e, "simt")) rec_simt = true;
+    if (e && !strcmp(e, "tc")) rec_simt = false;
+    rc = rec_simt ? launch_recurrent_simt(h, w, B, T, H, st) : launch_recurrent_tc(h, w, B, T, H, st);
+  }
   if (rc) return rc;
+  DRNMF_CUDA(cudaEventRecord(h->ev[3], st));
   if (irm) {   // recon + mask: irm = exp(log(eps + H_c E_c) - log(eps + H_c E_c + H_n E_n))
     GemmArgs a{};
     a.A_hi = w.Hp_hi; a.A_lo = w.Hp_lo; a.lda = h->Rp;
@@ -208,7 +224,17 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
     a.square = (h->flags & DRNMF_FLAG_SQUARE_IRM) ? 1 : 0;
     if ((rc = run_gemm(h, EPI_RECON, a, st))) return rc;
   }
+  DRNMF_CUDA(cudaEventRecord(h->ev[4], st));
+  h->ev_valid = true;
   if (h->impl != DRNMF_IMPL_SIMT) return check_dev_error(h, st, "drnmf_forward");
+  return DRNMF_OK;
+}
+
+int drnmf_stage_times(drnmf_handle* h, float* ms4) {
+  DRNMF_CHECK(h && ms4, "NULL argument");
+  DRNMF_CHECK(h->ev_valid, "no completed drnmf_forward to report on");
+  DRNMF_CUDA(cudaEventSynchronize(h->ev[4]));
+  for (int i = 0; i < 4; ++i) DRNMF_CUDA(cudaEventElapsedTime(&ms4[i], h->ev[i], h->ev[i + 1]));
   return DRNMF_OK;
 }
 

@@ -18,6 +18,8 @@ struct drnmf_handle {
   float *inv_norm;         // K x Rp scratch
   float u0_d, u0_o, uk_d, uk_o;
   int* dev_error;          // device-side error word (watchdogs / protocol violations)
+  cudaEvent_t ev[5];       // stage boundaries of the last drnmf_forward (mask | projection | recurrence | recon)
+  bool ev_ready, ev_valid;
 };
 
 namespace drnmf {

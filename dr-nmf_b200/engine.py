@@ -157,6 +157,12 @@ class DrnmfEngine:
                                                float(mask_value), _ptr(out), ws, wsb, _stream()))
         return out
 
+    def stage_times(self):
+        """ms of (masking, projection GEMM, recurrence, recon+mask GEMM) of the last forward (CUDA events)."""
+        ms = (C.c_float * 4)()
+        _lib.check(self.lib.drnmf_stage_times(self.h, ms))
+        return [float(v) for v in ms]
+
     def derived(self, which, k=0):
         n = {0: self.Rp * self.Rp, 1: self.Rp * self.Fp, 2: self.Rp, 3: self.Rp}[which]
         out = torch.empty(n, dtype=torch.float32, device=self.device)

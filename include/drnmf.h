@@ -79,6 +79,10 @@ DRNMF_API size_t drnmf_workspace_bytes(const drnmf_handle* h, int B, int T);
 DRNMF_API int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H, float* irm, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* Device time (ms, CUDA events on the call's stream) of the four stages of the last drnmf_forward on this handle:
+ * [0] Masking + padding, [1] input-projection GEMM, [2] recurrence over (T x K_layers), [3] recon + mask GEMM. */
+DRNMF_API int drnmf_stage_times(drnmf_handle* h, float* ms4);
+
 /* Debug/inspection: copy a derived tensor to a caller device buffer.  which: 0 = S_k^T (Rp x Rp, k>=1),
  * 1 = W_k^T (Rp x Fp), 2 = b_k (Rp), 3 = h0 (Rp).  Rp/Fp via drnmf_padded_dims. */
 DRNMF_API int drnmf_get_derived(const drnmf_handle* h, int which, int k, float* out, void* stream);

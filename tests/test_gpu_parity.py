@@ -1,0 +1,211 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI, against the numpy oracle
+(float64 truth) on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances are the ones BASELINE.json's north_star states: relative error <= 1e-4 on H and on the mask
+(Frobenius AND max-abs/max), <= 0.01 dB on the SDR of the reconstructed audio.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from drnmf_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4           # north_star: relative error <= 1e-4 on H and on the mask
+IMPLS = ["simt", "tc"]
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    fro = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    mx = np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+    return fro, mx
+
+
+def _golden_params(g, tag):
+    return {k: g["%s_%s" % (tag, k)] for k in
+            ("log_D", "log_alph", "log_lam1", "log_U1", "log_Uk", "log_h0", "k_clean", "k_noise")}
+
+
+def _run(p, x, impl, square=False):
+    K, F, R = p["log_D"].shape
+    eng = engine.DrnmfEngine(F, R, K, square_irm=square, impl=impl)
+    eng.set_params(p)
+    H, irm = eng.forward(torch.as_tensor(x, device="cuda"))
+    torch.cuda.synchronize()
+    return eng, H.cpu().numpy(), irm.cpu().numpy()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_forward_golden(golden_dir, tag, impl):
+    """Fixtures produced by the reference's own step()/build_alt code (oracle/pin_reference.py)."""
+    g = np.load(os.path.join(golden_dir, "drnmf_forward.npz"))
+    p = _golden_params(g, tag)
+    _, H, irm = _run(p, g[tag + "_x"], impl)
+    for got, want in ((H, g[tag + "_H"]), (irm, g[tag + "_irm"])):
+        fro, mx = rel_err(got, want)
+        assert fro < TOL and mx < TOL, (impl, tag, fro, mx)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_derived_weights(impl):
+    F, R, K = 70, 48, 3
+    p = synth.model_params(F, R, K, alph=20.0)
+    p["log_alph"] = (p["log_alph"] + np.array([0.0, 0.1, -0.2], np.float32)).astype(np.float32)
+    eng = engine.DrnmfEngine(F, R, K, impl=impl)
+    eng.set_params(p)
+    for k in range(K):
+        Wk, Sk, bk = O.layer_weights(p, k)
+        WT = eng.derived(1, k).cpu().numpy()
+        assert rel_err(WT[:R, :F], Wk.T)[1] < 1e-5
+        assert np.all(WT[R:] == 0) and np.all(WT[:, F:] == 0)
+        assert rel_err(eng.derived(2, k).cpu().numpy()[:R], bk)[1] < 1e-6
+        if k > 0:
+            ST = eng.derived(0, k).cpu().numpy()
+            assert rel_err(ST[:R, :R], Sk.T)[1] < 2e-6, (impl, k, rel_err(ST[:R, :R], Sk.T))
+            assert np.all(ST[R:] == 0) and np.all(ST[:, R:] == 0)
+    h0 = np.logaddexp(p["log_h0"].astype(np.float64), 0)
+    assert rel_err(eng.derived(3).cpu().numpy()[:R], h0)[1] < 1e-6
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", [
+    dict(F=65, R=40, K=4, B=5, T=12, alph=30.0),            # ragged lengths, R not a multiple of 8
+    dict(F=129, R=200, K=5, B=3, T=9, alph=50.0),           # reference-like r=100 (Rp=256)
+    dict(F=257, R=200, K=2, B=70, T=6, alph=50.0),          # B above one batch tile
+    dict(F=33, R=16, K=1, B=2, T=5, alph=10.0),             # single layer: no Gram term at all
+])
+def test_forward_vs_oracle(shape, impl):
+    F, R, K, B, T = (shape[k] for k in "FRKBT")
+    rng = np.random.default_rng(1234 + F + R)
+    p = synth.model_params(F, R, K, alph=shape["alph"], lam1=0.5)
+    p["log_alph"] = (p["log_alph"] + 0.05 * rng.standard_normal(K)).astype(np.float32)
+    x = (np.abs(rng.standard_normal((B, T, F))) * 3.0).astype(np.float32)
+    lens = rng.integers(1, T + 1, size=B)
+    lens[0] = T
+    for b in range(B):
+        x[b, lens[b]:] = -1.0
+    Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+    _, H, irm = _run(p, x, impl)
+    fro, mx = rel_err(H, Ho)
+    assert fro < TOL and mx < TOL, ("H", impl, shape, fro, mx)
+    fro, mx = rel_err(irm, irmo)
+    assert fro < TOL and mx < TOL, ("irm", impl, shape, fro, mx)
+    # masked frames carry the state; mask in (0,1)
+    for b in range(B):
+        for t in range(lens[b], T):
+            np.testing.assert_array_equal(H[b, t], H[b, lens[b] - 1])
+    assert np.all(irm > 0) and np.all(irm <= 1)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_untie_alph_and_square_irm(impl):
+    F, R, K, B, T = 40, 24, 3, 2, 7
+    rng = np.random.default_rng(77)
+    p = synth.model_params(F, R, K, alph=15.0)
+    p["log_alph"] = (np.log(15.0) + 0.1 * rng.standard_normal((K, R))).astype(np.float32)     # enhance.py:225-226
+    x = (np.abs(rng.standard_normal((B, T, F))) * 2.0).astype(np.float32)
+    Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64, transform_before_irm="square")
+    _, H, irm = _run(p, x, impl, square=True)
+    assert max(rel_err(H, Ho)) < TOL and max(rel_err(irm, irmo)) < TOL
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_leading_masked_frame(impl):
+    F, R, K = 20, 16, 3
+    rng = np.random.default_rng(5)
+    p = synth.model_params(F, R, K, alph=10.0)
+    x = np.abs(rng.standard_normal((2, 5, F))).astype(np.float32)
+    x[0, 0] = -1.0
+    Ho = O.rnn_forward(x, p)
+    _, H, _ = _run(p, x, impl)
+    assert np.all(H[0, 0] == 0.0)
+    assert max(rel_err(H, Ho)) < TOL
+
+
+def test_tc_matches_simt_bitwise_stable():
+    """Two runs of the tensor-core path give identical bits (deterministic reductions, no atomics)."""
+    F, R, K, B, T = 65, 40, 4, 6, 8
+    rng = np.random.default_rng(9)
+    p = synth.model_params(F, R, K, alph=30.0)
+    x = np.abs(rng.standard_normal((B, T, F))).astype(np.float32)
+    eng, H1, irm1 = _run(p, x, "tc")
+    H2, irm2 = eng.forward(torch.as_tensor(x, device="cuda"))
+    assert np.array_equal(H1, H2.cpu().numpy()) and np.array_equal(irm1, irm2.cpu().numpy())
+
+
+# ---- STFT / iSTFT ------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_stft_istft_golden(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "stft_istft.npz"))
+    N, hop, x = int(g[tag + "_N"]), int(g[tag + "_hop"]), g[tag + "_x"]
+    audio = torch.as_tensor(x, device="cuda")
+    stack, mag, fidx = engine.stft_mag(audio, [0], [len(x)], N, hop)
+    ref = g[tag + "_stack"]
+    assert stack.shape == ref.shape
+    assert np.max(np.abs(stack.cpu().numpy() - ref)) < 2e-5 * max(1.0, np.abs(ref).max())
+    F = N // 2 + 1
+    np.testing.assert_allclose(mag.cpu().numpy().T, np.sqrt(ref[:F] ** 2 + ref[F:] ** 2), atol=3e-5)
+    ref_stack = torch.as_tensor(ref, device="cuda")
+    for mask, want in ((None, g[tag + "_xr"]), (g[tag + "_mask"], g[tag + "_xr_masked"])):
+        m = None if mask is None else torch.as_tensor(np.ascontiguousarray(mask.T), device="cuda")
+        (y,) = engine.mask_istft(ref_stack, m, fidx, N, hop)
+        assert y.numel() == want.shape[1]
+        np.testing.assert_allclose(y.cpu().numpy(), want[0], atol=2e-6)
+
+
+def test_stft_roundtrip_full_size():
+    """BASELINE-sized property: STFT -> iSTFT reconstructs the signal (test_audio_dataset.py:78-89), ragged batch."""
+    N, hop = 1024, 256
+    lens = [48000, 32000, 40123, 300, 700]
+    sigs = [synth.utterance(i, seconds=n / 16000.0)[0][:n] for i, n in enumerate(lens)]
+    offs = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    audio = torch.as_tensor(np.concatenate(sigs), device="cuda")
+    stack, mag, fidx = engine.stft_mag(audio, list(offs), lens, N, hop)
+    ys = engine.mask_istft(stack, None, fidx, N, hop)
+    for s, y, n in zip(sigs, ys, lens):
+        y = y.cpu().numpy()[:n]
+        assert np.mean((s - y) ** 2) / max(np.mean(s ** 2), 1e-30) < 1e-10
+    # linearity of the masked synthesis: mask 0.5 halves the output
+    half = torch.full_like(mag, 0.5)
+    yh = engine.mask_istft(stack, half, fidx, N, hop)
+    np.testing.assert_allclose(yh[0].cpu().numpy(), 0.5 * ys[0].cpu().numpy(), atol=1e-6)
+
+
+# ---- end to end: SDR parity ---------------------------------------------------------------------
+@pytest.mark.parametrize("impl", IMPLS)
+def test_enhance_sdr_parity(impl):
+    """north_star: <= 0.01 dB on the SDR of the reconstructed audio (float audio and after wav int16 quantisation)."""
+    N, hop, R, K, B = 256, 64, 64, 4, 3
+    F = N // 2 + 1
+    secs = [0.5, 0.4, 0.3]
+    pairs = [synth.utterance(i, seconds=s) for i, s in enumerate(secs)]
+    win = O.sqrt_hann(N)
+    frames = [synth.stft_frames(len(n), N, hop) for n, _ in pairs]
+    T = max(frames)
+    p = synth.model_params(F, R, K, alph=25.0)
+    x = np.full((B, T, F), -1.0, np.float32)
+    stack = np.zeros((2 * F, B * T), np.float32)
+    for b, (noisy, _) in enumerate(pairs):
+        Y = O.stack_reim(O.stft_mc(noisy, N, hop, win))
+        x[b, :frames[b]] = O.magnitude(Y).T
+        stack[:, b * T:b * T + frames[b]] = Y
+    _, irm = O.drnmf_forward(x, p, dtype=np.float64)
+    eng = engine.DrnmfEngine(F, R, K, impl=impl)
+    eng.set_params(p)
+    out = eng.enhance_host(torch.as_tensor(x).pin_memory(), torch.as_tensor(stack).pin_memory(),
+                           torch.as_tensor(np.asarray(frames, np.int32)), N, hop).numpy()
+    for b, (noisy, clean) in enumerate(pairs):
+        ref = O.reconstruct_x(stack[:, b * T:b * T + frames[b]].astype(np.float64), hop, win.astype(np.float64),
+                              mask=irm[b, :frames[b]].T, dtype=np.float64)[0]
+        got = out[b, :ref.size]
+        n = len(clean)
+        d = abs(O.sdr_db(got[:n], clean) - O.sdr_db(ref[:n], clean))
+        dq = abs(O.sdr_db(O.wav_quantize(got[:n]), clean) - O.sdr_db(O.wav_quantize(ref[:n].astype(np.float32)), clean))
+        assert d < 0.01 and dq < 0.01, (impl, b, d, dq)
+        assert np.all(out[b, ref.size:] == 0)
