@@ -238,6 +238,13 @@ int drnmf_stage_times(drnmf_handle* h, float* ms4) {
   return DRNMF_OK;
 }
 
+int drnmf_recurrent_config(const drnmf_handle* h, int* cfg9) {
+  DRNMF_CHECK(h && cfg9, "NULL argument");
+  cfg9[0] = h->last_rec_impl;
+  for (int i = 0; i < 8; ++i) cfg9[1 + i] = h->rec_cfg[i];
+  return DRNMF_OK;
+}
+
 int drnmf_get_derived(const drnmf_handle* h, int which, int k, float* out, void* stream) {
   DRNMF_CHECK(h && out, "NULL argument");
   DRNMF_CHECK(h->params_set, "parameters not set");

@@ -114,6 +114,7 @@ int launch_init_state(const drnmf_handle* h, FwdWorkspace& w, cudaStream_t st) {
 }
 
 int launch_recurrent_simt(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
+  h->last_rec_impl = 1;
   int rc = launch_init_state(h, w, st);
   if (rc) return rc;
   const int Rp = h->Rp, K = h->K;

@@ -19,6 +19,9 @@
 //                           4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue + publish).
 #include "internal.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace drnmf {
 
 constexpr int RT_THREADS = 384;
@@ -46,6 +49,15 @@ struct RecBars {   // all mbarriers, laid out at off_bar
   uint32_t tmem_slot;
   int abort;
 };
+
+// named-barrier AND-reduction over the 128 owner threads (barrier id 1): uniform agreement on a predicate
+__device__ __forceinline__ bool owners_all(bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.and.pred p, 1, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(r) : "r"((uint32_t)pred) : "memory");
+  return r != 0;
+}
 
 __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int target, volatile int* err) {
   if (flag_ld_acquire(f) >= target) return true;
@@ -262,7 +274,8 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmS_hi, const __grid_constant
             // ---- wait for the KS partial tiles, sum them in rank order ----
             const int rs = it % a.RST;
             if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
-            if (!mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 210); ok = false; break; }
+            const bool got = mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG);
+            if (!owners_all(got)) { atomicCAS(a.dev_error, 0, 210); ok = false; break; }
             const float* red = reinterpret_cast<const float*>(smem + a.off_red + rs * a.red_slot_bytes);
 #pragma unroll
             for (int c = 0; c < MAXE; ++c) {
@@ -342,15 +355,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmS_hi, const __grid_constant
 // ---------------------------------------------------------------------------------------------------
 struct RecPlan { int NB, KS, MT, RO, ATOMS, KSLICE, n_tiles, WST, HST, RST; size_t smem; RecArgs a; bool ok; const char* why; };
 
-static RecPlan plan_recurrent(const drnmf_handle* h, int B, int Bp) {
+static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
   RecPlan p{};
   p.ok = false;
   const int Rp = h->Rp;
   p.MT = Rp / 128;
-  p.NB = (B <= 16) ? 16 : 32;
+  p.NB = NB;
   p.n_tiles = (B + p.NB - 1) / p.NB;
-  int KS = 16;
-  while (KS > 1 && (Rp % (KS * 32) != 0 || p.MT * KS > h->num_sms)) KS >>= 1;
   if (Rp % (KS * 32) != 0 || p.MT * KS > h->num_sms) { p.why = "no (M-tile x K-split) grid fits the device"; return p; }
   p.KS = KS; p.RO = 128 / KS; p.KSLICE = Rp / KS; p.ATOMS = p.KSLICE / 32;
   if (p.RO * p.NB > 128 * 8) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
@@ -380,9 +391,28 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int Bp) {
   p.a.h_stage_bytes = h_stage; p.a.red_slot_bytes = red_slot;
   p.a.MT = p.MT; p.a.KS = p.KS; p.a.RO = p.RO; p.a.ATOMS = p.ATOMS; p.a.KSLICE = p.KSLICE; p.a.n_tiles = p.n_tiles;
   p.a.WST = p.WST; p.a.HST = p.HST; p.a.RST = p.RST;
-  (void)Bp;
   p.ok = true;
   return p;
+}
+
+// co-resident clusters the device offers for this plan (the kernel spins on peers: all CTAs must be resident)
+template <int NB>
+static int rec_max_clusters(const RecPlan& p, int* out) {
+  auto kern = k_recurrent_tc<NB>;
+  DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.KS, p.MT, 1);
+  cfg.blockDim = dim3(RT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = p.smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.KS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  *out = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(out, kern, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); *out = 0; }
+  return DRNMF_OK;
 }
 
 template <int NB>
@@ -390,7 +420,7 @@ static int launch_rec(const RecPlan& p, const CUtensorMap& tS_hi, const CUtensor
                       const CUtensorMap& tH_lo, cudaStream_t st) {
   auto kern = k_recurrent_tc<NB>;
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  if (p.KS > 8) DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.KS, p.MT, 1);
   cfg.blockDim = dim3(RT_THREADS, 1, 1);
@@ -400,12 +430,6 @@ static int launch_rec(const RecPlan& p, const CUtensorMap& tS_hi, const CUtensor
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.KS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  int max_clusters = 0;
-  DRNMF_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-  if (max_clusters < p.MT) {
-    set_error("persistent recurrence needs %d co-resident clusters of %d CTAs, device offers %d", p.MT, p.KS, max_clusters);
-    return DRNMF_ERR_INVALID;
-  }
   DRNMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tS_hi, tS_lo, tH_hi, tH_lo, p.a));
   count_launch();
   return DRNMF_OK;
@@ -413,13 +437,34 @@ static int launch_rec(const RecPlan& p, const CUtensorMap& tS_hi, const CUtensor
 
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
   const int K = h->K, Rp = h->Rp;
-  RecPlan p = plan_recurrent(h, B, w.Bp);
+  // Candidate tilings, preferred first: more K-splits = more SMs streaming the weights; the cluster (= the K-splits of
+  // one M-tile) must be co-resident MT times, which depends on the board's GPC layout -> ask the occupancy API.
+  RecPlan p{};
+  p.ok = false; p.why = "no candidate tiling";
+  const char* env_ks = getenv("DRNMF_REC_KS");
+  const char* env_nb = getenv("DRNMF_REC_NB");
+  for (int KS = 16; KS >= 1 && !p.ok; KS >>= 1) {
+    if (env_ks && atoi(env_ks) != KS) continue;
+    for (int NB = 32; NB >= 16 && !p.ok; NB >>= 1) {
+      if (env_nb && atoi(env_nb) != NB) continue;
+      if (NB == 32 && B <= 16) continue;
+      RecPlan c = plan_recurrent(h, B, KS, NB);
+      if (!c.ok) { if (!p.why || !p.ok) p.why = c.why; continue; }
+      int mc = 0;
+      if (NB == 16) rec_max_clusters<16>(c, &mc); else rec_max_clusters<32>(c, &mc);
+      if (mc < c.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
+      p = c;
+    }
+  }
   if (!p.ok || p.n_tiles * p.MT > 16384) {
     // Shapes the persistent kernel does not cover yet run on the CUDA-core recurrence (still on the GPU).
     static bool warned = false;
     if (!warned) { fprintf(stderr, "[libdrnmf] persistent tcgen05 recurrence unavailable (%s); using the SIMT recurrence\n", p.ok ? "too many tiles" : p.why); warned = true; }
+    h->last_rec_impl = 1;
     return launch_recurrent_simt(h, w, B, T, H_user, st);
   }
+  h->last_rec_impl = 0;
+  { int c[8] = {p.NB, p.KS, p.MT, p.ATOMS, p.n_tiles, p.WST, p.HST, p.RST}; for (int i = 0; i < 8; ++i) h->rec_cfg[i] = c[i]; }
   RecArgs& a = p.a;
   a.XW = w.XW; a.bias = h->bias; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.state = w.state; a.psum = w.psum; a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;

@@ -128,7 +128,7 @@ class DrnmfEngine:
         off = (-ws.data_ptr()) % 256
         return C.c_void_p(ws.data_ptr() + off), ws.numel() - off
 
-    def forward(self, x, mask_value=-1.0, want_H=True, want_irm=True):
+    def forward(self, x, mask_value=-1.0, want_H=True, want_irm=True, H_out=None, irm_out=None):
         """x: (B,T,F) float32 CUDA tensor padded with mask_value -> (H (B,T,R) | None, irm (B,T,F) | None)."""
         if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32):
             raise TypeError("x must be a float32 CUDA tensor (the product path has no CPU implementation)")
@@ -136,8 +136,10 @@ class DrnmfEngine:
         B, T, F = x.shape
         if F != self.F:
             raise ValueError("x has %d features, model expects %d" % (F, self.F))
-        H = torch.empty((B, T, self.R), dtype=torch.float32, device=x.device) if want_H else None
-        irm = torch.empty((B, T, F), dtype=torch.float32, device=x.device) if want_irm else None
+        H = H_out if H_out is not None else (
+            torch.empty((B, T, self.R), dtype=torch.float32, device=x.device) if want_H else None)
+        irm = irm_out if irm_out is not None else (
+            torch.empty((B, T, F), dtype=torch.float32, device=x.device) if want_irm else None)
         need = self.lib.drnmf_workspace_bytes(self.h, B, T)
         ws, wsb = self._workspace(need)
         _lib.check(self.lib.drnmf_forward(self.h, _ptr(x), B, T, float(mask_value), _ptr(H), _ptr(irm), ws, wsb,
@@ -163,11 +165,49 @@ class DrnmfEngine:
         _lib.check(self.lib.drnmf_stage_times(self.h, ms))
         return [float(v) for v in ms]
 
+    def recurrent_config(self):
+        """dict describing how the last forward's recurrence ran (impl 'tcgen05' | 'simt' + tiling)."""
+        c = (C.c_int * 9)()
+        _lib.check(self.lib.drnmf_recurrent_config(self.h, c))
+        keys = ("NB", "KS", "MT", "ATOMS", "n_tiles", "WST", "HST", "RST")
+        d = {"impl": "tcgen05" if c[0] == 0 else "simt"}
+        d.update({k: int(c[1 + i]) for i, k in enumerate(keys)})
+        return d
+
     def derived(self, which, k=0):
         n = {0: self.Rp * self.Rp, 1: self.Rp * self.Fp, 2: self.Rp, 3: self.Rp}[which]
         out = torch.empty(n, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.drnmf_get_derived(self.h, which, k, _ptr(out), _stream()))
         return out.reshape({0: (self.Rp, self.Rp), 1: (self.Rp, self.Fp), 2: (self.Rp,), 3: (self.Rp,)}[which])
+
+
+class EnhancePlan:
+    """Preallocated device-resident enhancement step: forward -> mask -> iSTFT with inputs already in HBM
+    (enhance.py:1186-1203 without the host copies).  frames[b] = valid frames of utterance b (default T)."""
+
+    def __init__(self, eng, B, T, N, hop, frames=None):
+        self.eng, self.B, self.T, self.N, self.hop = eng, B, T, N, hop
+        dev = eng.device
+        F = eng.F
+        fr = np.full((B,), T, np.int64) if frames is None else np.asarray(frames, np.int64)
+        self.L = hop * (T - 1) - N
+        starts = np.arange(B, dtype=np.int64) * T
+        self.fidx = torch.as_tensor(np.stack([starts, starts + fr], axis=1).copy(), device=dev)
+        self.out_offs = torch.as_tensor(np.arange(B, dtype=np.int64) * self.L, device=dev)
+        self.irm = torch.empty((B, T, F), dtype=torch.float32, device=dev)
+        self.audio = torch.zeros((B, self.L), dtype=torch.float32, device=dev)
+        self.nb = eng.lib.drnmf_istft_workspace_bytes(B * T, N)
+        self.ws = torch.empty(self.nb + 256, dtype=torch.uint8, device=dev)
+        self.ws_ptr = C.c_void_p(self.ws.data_ptr() + ((-self.ws.data_ptr()) % 256))
+        self.max_frames = int(fr.max())
+
+    def run(self, x, stack, mask_value=-1.0):
+        eng = self.eng
+        eng.forward(x, mask_value, want_H=False, irm_out=self.irm)
+        _lib.check(eng.lib.drnmf_mask_istft(_ptr(stack), _ptr(self.irm), _ptr(self.fidx), _ptr(self.out_offs), self.B,
+                                            self.max_frames, self.N, self.hop, self.B * self.T, _ptr(self.audio),
+                                            self.ws_ptr, self.nb, _stream()))
+        return self.audio
 
 
 # ---- STFT / iSTFT ------------------------------------------------------------------------------

@@ -83,6 +83,11 @@ DRNMF_API int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float
  * [0] Masking + padding, [1] input-projection GEMM, [2] recurrence over (T x K_layers), [3] recon + mask GEMM. */
 DRNMF_API int drnmf_stage_times(drnmf_handle* h, float* ms4);
 
+/* How the recurrence of the last drnmf_forward ran: cfg9[0] = 0 persistent tcgen05 kernel / 1 SIMT per-step kernels;
+ * cfg9[1..8] = batch tile NB, K-splits (cluster size) KS, M-tiles MT, weight atoms per slice, batch tiles,
+ * weight / hidden / reduction ring depths of the persistent kernel. */
+DRNMF_API int drnmf_recurrent_config(const drnmf_handle* h, int* cfg9);
+
 /* Debug/inspection: copy a derived tensor to a caller device buffer.  which: 0 = S_k^T (Rp x Rp, k>=1),
  * 1 = W_k^T (Rp x Fp), 2 = b_k (Rp), 3 = h0 (Rp).  Rp/Fp via drnmf_padded_dims. */
 DRNMF_API int drnmf_get_derived(const drnmf_handle* h, int which, int k, float* out, void* stream);

@@ -37,6 +37,9 @@ def _run(p, x, impl, square=False):
     eng.set_params(p)
     H, irm = eng.forward(torch.as_tensor(x, device="cuda"))
     torch.cuda.synchronize()
+    if impl == "tc" and os.environ.get("DRNMF_RECURRENT") != "simt":
+        # the product path must really be the persistent tcgen05 kernel, not the CUDA-core lock path
+        assert eng.recurrent_config()["impl"] == "tcgen05", eng.recurrent_config()
     return eng, H.cpu().numpy(), irm.cpu().numpy()
 
 
@@ -101,6 +104,23 @@ def test_forward_vs_oracle(shape, impl):
         for t in range(lens[b], T):
             np.testing.assert_array_equal(H[b, t], H[b, lens[b] - 1])
     assert np.all(irm > 0) and np.all(irm <= 1)
+
+
+def test_north_star_shape():
+    """F=513, R=1000 (r=500), K=25 as in BASELINE.json, short utterances so that the float64 oracle stays fast."""
+    F, R, K, B, T = 513, 1000, 25, 6, 12
+    rng = np.random.default_rng(2017)
+    p = synth.model_params(F, R, K)
+    x = (np.abs(rng.standard_normal((B, T, F))) * 4.0).astype(np.float32)
+    x[1, 9:] = -1.0
+    Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+    eng, H, irm = _run(p, x, "tc")
+    cfg = eng.recurrent_config()
+    assert cfg["impl"] == "tcgen05" and cfg["MT"] == 8, cfg
+    fro, mx = rel_err(H, Ho)
+    assert fro < TOL and mx < TOL, ("H", fro, mx, cfg)
+    fro, mx = rel_err(irm, irmo)
+    assert fro < TOL and mx < TOL, ("irm", fro, mx, cfg)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
