@@ -197,12 +197,13 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
   DRNMF_CUDA(cudaEventRecord(h->ev[0], st));
   if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st))) return rc;
   DRNMF_CUDA(cudaEventRecord(h->ev[1], st));
-  {   // input projections for every layer: XW[bt][k*Rp + j] = x~[bt] . W_k[:, j]
+  {   // input projections for every layer: XW[bt][k*Rp + j] = x~[bt] . W_k[:, j] + b_k[j]
     GemmArgs a{};
     a.A_hi = w.xp_hi; a.A_lo = w.xp_lo; a.lda = h->Fp;
     a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = h->Fp;
     a.M = BT; a.N = h->K * h->Rp; a.Kd = h->Fp;
     a.C = w.XW; a.ldc = h->K * h->Rp; a.M_valid = BT; a.N_valid = a.N;
+    a.bias = h->bias;            // XW[bt][k*Rp + j] = x~ . W_k[:, j] + b_k[j]
     if ((rc = run_gemm(h, EPI_STORE, a, st))) return rc;
   }
   DRNMF_CUDA(cudaEventRecord(h->ev[2], st));

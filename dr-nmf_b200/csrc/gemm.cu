@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.N_valid) continue;
       if (EPI == EPI_STORE) {
-        a.C[(size_t)m * a.ldc + n] = acc[i][j];
+        a.C[(size_t)m * a.ldc + n] = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
       } else if (EPI == EPI_GRAM) {
         float v = epi_gram_value(m, n, a.R_valid, acc[i][j]);
         a.C[(size_t)m * a.ldc + n] = v;
@@ -74,14 +74,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const __grid_constant__ CUtensorMap tmB2_hi, const __grid_constant__ CUtensorMap tmB2_lo, GemmArgs a,
           int* dev_error) {
   using Cfg = TcCfg<EPI>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];      // no static smem: the dynamic window is 1024-aligned
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* acc_full = empty + Cfg::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5;
+  if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(dev_error, 199); return; }
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int num_kb = (a.Kd + TC_BK - 1) / TC_BK;
 
@@ -172,6 +172,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           if (EPI == EPI_STORE) {
             if (n < a.N_valid) {
               float4* dst = reinterpret_cast<float4*>(a.C + (size_t)m * a.ldc + n);
+              if (a.bias) {
+                const float4* bb = reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 t4 = __ldg(bb + i);
+                  v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w;
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }

@@ -32,7 +32,7 @@ void count_launch(int n = 1);
 struct FwdWorkspace {
   float *xp_hi, *xp_lo;     // BT x Fp     masked, zero-padded input and its tf32 remainder
   float* mvalid;            // BT          1.0 where the frame is valid (Keras Masking)
-  float* XW;                // BT x (K*Rp) input projections x~_t . W_k for every layer
+  float* XW;                // BT x (K*Rp) input projections x~_t . W_k + b_k for every layer
   float *Hp_hi, *Hp_lo;     // BT x Rp     padded output sequence (A operand of the recon GEMM)
   float *hb_hi, *hb_lo;     // 2 x Bp x Rp ping-pong hidden state between layers
   float* state;             // Bp x Rp     recurrent state (last layer of the previous valid frame)
@@ -60,6 +60,7 @@ struct GemmArgs {
   float *C, *C_lo; int ldc;              // outputs
   int R_valid, N_valid, M_valid;         // masks for the epilogues
   int square;                            // EPI_RECON: transform_before_irm == 'square'
+  const float* bias;                     // EPI_STORE: optional per-column bias added in the epilogue (length N)
 };
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);

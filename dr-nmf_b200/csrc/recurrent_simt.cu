@@ -7,7 +7,7 @@
 namespace drnmf {
 
 struct StepArgs {
-  const float* XW;        // BT x (K*Rp)
+  const float* XW;        // BT x (K*Rp)  input projections INCLUDING the bias b_k
   const float* bias;      // K x Rp
   const float* mvalid;    // BT
   float* state;           // Bp x Rp
@@ -57,7 +57,7 @@ __global__ void k_frame_begin(StepArgs a) {
   const float* xw = a.XW + ((size_t)b * a.T + a.t) * ((size_t)a.K * a.Rp);
   for (int j = threadIdx.x; j < a.Rp; j += blockDim.x) {
     float g = 0.f;
-    if (j < a.R) g = fmaxf(st[j] * a.dmo + a.off * leak + xw[j] + a.bias[j], 0.f);
+    if (j < a.R) g = fmaxf(st[j] * a.dmo + a.off * leak + xw[j], 0.f);
     if (a.K == 1) {
       finish_frame(a, b, j, g);
     } else {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_step_simt(StepArgs a) {
       if (j >= a.Rp) continue;
       float g = 0.f;
       if (j < a.R) {
-        float pre = a.off * leak + acc[i][jj] + xw[j] + a.bias[(size_t)a.k * a.Rp + j];
+        float pre = a.off * leak + acc[i][jj] + xw[j];
         if (a.dmo != 0.f) pre += a.dmo * a.state[(size_t)b * a.Rp + j];
         g = fmaxf(pre, 0.f);
       }

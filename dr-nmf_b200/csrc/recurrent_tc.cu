@@ -4,19 +4,23 @@
 // last layer of frame t); per step the work is  g^k = relu(g^{k-1} . S_k + x~W_k + b_k + leak),  a (B x R).(R x R)
 // product with a SKINNY batch dimension.  S_k (4 MB at R=1000) must be re-streamed every step, so every SM has to pull
 // its share of the weights each step: the step is tiled as
-//       M-tile m (128 output atoms)  x  K-split s (a slice of the input atoms),   grid = (KS, MT), cluster = the KS
-// K-splits of one M-tile.  Each CTA multiplies its 128 x Kslice block of S_k^T (A operand, TMA -> smem, 128B swizzle)
-// by the Kslice x NB block of the hidden state (B operand) on the tensor cores (tcgen05.mma kind::tf32, 3xTF32
-// compensation, fp32 accumulators in TMEM).  The split-K partial sums are reduced INSIDE the cluster through
-// distributed shared memory (st.async + mbarrier complete_tx): CTA o of the cluster owns rows [o*RO, (o+1)*RO) of the
-// M-tile, sums the KS partials in a fixed order (deterministic), applies the fused epilogue (input projection, bias,
-// rank-1 leak, relu, Keras mask carry) and publishes hi/lo fp32 of the new hidden rows to a ping-pong global buffer
-// (L2 resident) + a release flag.  Consumers acquire the flag and TMA the slice they need.  Utterances are cut into
-// independent batch tiles of NB columns that are software-pipelined through the same weights, which hides the
-// exchange latency when B is large and reuses every weight tile n_tiles times.
+//       M-tile m (128 output atoms)  x  K-split s (a slice of <=128 input atoms),   grid = (KS, MT), cluster = the KS
+// K-splits of one M-tile.
+//   * weights: a warpgroup loads the CTA's 128 x KSLICE block of S_k^T straight from L2 into registers, splits it into
+//     tf32 hi + remainder lo and writes both into TENSOR MEMORY (tcgen05.st).  The MMA takes its A operand from TMEM,
+//     which removes the per-instruction shared-memory read of A that dominates skinny-N tcgen05 products (measured:
+//     ~114 cycles per MMA with A in smem regardless of N) and frees 160 KB of smem.
+//   * hidden state: B operand, Kslice x NB tile (hi and lo) TMA-loaded with 128B swizzle from a ping-pong global buffer.
+//   * product: tcgen05.mma kind::tf32, 3xTF32 compensation (W_lo.h_hi + W_hi.h_lo + W_hi.h_hi), fp32 accumulators in TMEM.
+//   * split-K reduction INSIDE the cluster over distributed shared memory (st.async + mbarrier complete_tx): CTA o owns
+//     rows [o*RO, (o+1)*RO) of the M-tile, sums the KS partials in a fixed order (deterministic), applies the fused
+//     epilogue (input projection, bias, rank-1 leak, relu, Keras mask carry) and writes hi/lo of the new hidden rows;
+//     a publisher thread issues one gpu-scope release per (step, tile); consumers acquire the flag and TMA their slice.
+//   * utterances are cut into independent batch tiles of NB columns that are software-pipelined through the same
+//     TMEM-resident weights (hides the exchange latency when B is large, reuses every weight n_tiles times).
 //
-// Warp roles (384 threads): 0 weight TMA | 1 hidden-state TMA (+flag acquire) | 2 MMA issuer / TMEM owner | 3 idle |
-//                           4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue + publish).
+// Warp roles (512 threads): 1 hidden-state TMA (+flag acquire) | 2 MMA issuer / TMEM owner | 3 publisher |
+//     4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue) | 12-15 weight loaders (L2 -> regs -> TMEM).
 #include "internal.h"
 
 #include <cstdio>
@@ -24,28 +28,33 @@
 
 namespace drnmf {
 
-constexpr int RT_THREADS = 384;
+constexpr int RT_THREADS = 512;
 constexpr int RT_AST = 2;                    // TMEM accumulator stages
+constexpr int RT_PST = 4;                    // owner -> publisher hand-off slots
 constexpr long long RT_WATCHDOG = 3000000000LL;
 
 struct RecArgs {
   // tensors
-  const float* XW; const float* bias; const float* mvalid; const float* h0;
+  const float* XW; const float* mvalid; const float* h0;   // XW includes the bias b_k
   float *state, *psum, *Hp_hi, *Hp_lo, *H_user, *hb_hi, *hb_lo;
   unsigned int* flags;
   int* dev_error;
+  long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
   // shapes
   int B, Bp, T, K, R, Rp;
   int MT, KS, RO, ATOMS, KSLICE, n_tiles;
-  int WST, HST, RST;                         // ring depths: weight atoms, hidden tiles, reduction slots
+  int WST, HST, RST;                         // WST unused (weights live in TMEM); hidden-tile / reduction-slot ring depths
+  const float* ST;                           // (K-1) x Rp x Rp  S_k^T
   float u0_dmo, u0_off, uk_dmo, uk_off;
   // smem offsets (bytes from the 1024-aligned base)
-  int off_w, off_h, off_red, off_leak, off_out, off_bar;
+  int off_w, off_h, off_red, off_push, off_leak, off_out, off_bar;
   int h_stage_bytes, red_slot_bytes;
 };
 
 struct RecBars {   // all mbarriers, laid out at off_bar
-  uint64_t w_full[8], w_empty[8], h_full[4], h_empty[4], t_full[RT_AST], t_empty[RT_AST], red_full[4], red_free[4];
+  uint64_t h_full[4], h_empty[4], t_full[RT_AST], t_empty[RT_AST], red_full[4], red_free[4];
+  uint64_t pub_full[RT_PST], pub_empty[RT_PST];
+  uint64_t wt_full, wt_empty;                // weights of the current step are in TMEM / may be overwritten
   uint32_t tmem_slot;
   int abort;
 };
@@ -72,32 +81,46 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int ta
   return true;
 }
 
+// accumulate the cycles spent in `stmt` into debug slot `slot` (only CTA (0,0), only when a.dbg is set)
+#define RT_TIMED(slot, stmt)                                   \
+  do {                                                         \
+    if (dbg_on) { long long _t0 = clock64(); stmt; dbg_acc[slot] += clock64() - _t0; } \
+    else { stmt; }                                             \
+  } while (0)
+
 template <int NB>
 __global__ void __launch_bounds__(RT_THREADS, 1)
-k_recurrent_tc(const __grid_constant__ CUtensorMap tmS_hi, const __grid_constant__ CUtensorMap tmS_lo,
-               const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo, RecArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo, RecArgs a) {
+  // No static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below).  Keeping `smem`
+  // a plain __shared__ array (no integer round-trip) lets the compiler emit LDS/STS instead of generic LD/ST.
+  extern __shared__ __align__(1024) uint8_t smem[];
   RecBars* bars = reinterpret_cast<RecBars*>(smem + a.off_bar);
   float* leak_s = reinterpret_cast<float*>(smem + a.off_leak);       // n_tiles x NB : sum_j state[b][j] of this frame
   float* out_s = reinterpret_cast<float*>(smem + a.off_out);         // NB x (RO+1) staging of the new state rows
   volatile int* err = a.dev_error;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0) {               // uniform across the grid: everybody leaves
+    if (threadIdx.x == 0) atomicCAS(a.dev_error, 0, 299);
+    return;
+  }
+  const bool dbg_on = (a.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
+  long long dbg_acc[6] = {0, 0, 0, 0, 0, 0};
+  const long long dbg_t0 = clock64();
   const int s = blockIdx.x;            // K-split == rank in cluster
   const int m = blockIdx.y;            // M-tile
   const int K = a.K, T = a.T, Rp = a.Rp, n_tiles = a.n_tiles, ATOMS = a.ATOMS;
-  constexpr int RSTRIDE = NB + 4;      // padded row of a reduction slot (bank-conflict-free transposed reads)
-  constexpr uint32_t TMEM_COLS = (RT_AST * NB < 32) ? 32 : RT_AST * NB;
-  const uint32_t W_ATOM_BYTES = 128 * 128;                           // 128 rows x 32 fp32
+  constexpr uint32_t TMEM_COLS = 512;    // [0,KSLICE) W hi | [KSLICE,2 KSLICE) W lo | [256, 256 + AST*NB) accumulators
+  constexpr uint32_t ACC_COL0 = 256;
   const uint32_t H_ATOM_BYTES = NB * 128;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmS_hi); tma_prefetch_desc(&tmS_lo); tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo);
-    for (int i = 0; i < 8; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo);
+    mbar_init(&bars->wt_full, 128); mbar_init(&bars->wt_empty, 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&bars->h_full[i], 1); mbar_init(&bars->h_empty[i], 1); }
     for (int i = 0; i < RT_AST; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&bars->red_full[i], 1); mbar_init(&bars->red_free[i], a.KS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars->red_full[i], 1); mbar_init(&bars->red_free[i], 4 * a.KS); }
+    for (int i = 0; i < RT_PST; ++i) { mbar_init(&bars->pub_full[i], 4); mbar_init(&bars->pub_empty[i], 1); }
     bars->abort = 0;
     fence_mbar_init();
   }
@@ -109,24 +132,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmS_hi, const __grid_constant
   const uint32_t tmem_base = bars->tmem_slot;
   const int n_mma_steps = T * (K - 1);
 
-  if (warp == 0) {
-    // ================= weight producer: S_k^T[m*128.., s*KSLICE + a*32..] hi/lo, one atom per stage =================
-    if (lane == 0) {
-      int wl = 0;
-      for (int t = 0; t < T && !*err; ++t)
-        for (int k = 1; k < K; ++k)
-          for (int at = 0; at < ATOMS; ++at, ++wl) {
-            const int ws = wl % a.WST;
-            if (!mbar_wait(&bars->w_empty[ws], ((wl / a.WST) & 1) ^ 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 201); goto w_done; }
-            uint8_t* dst = smem + a.off_w + ws * (2 * W_ATOM_BYTES);
-            mbar_expect_tx(&bars->w_full[ws], 2 * W_ATOM_BYTES);
-            const int c0 = s * a.KSLICE + at * 32, c1 = (k - 1) * Rp + m * 128;
-            tma_load_2d(dst, &tmS_hi, &bars->w_full[ws], c0, c1);
-            tma_load_2d(dst + W_ATOM_BYTES, &tmS_lo, &bars->w_full[ws], c0, c1);
-          }
-    }
-  w_done:;
-  } else if (warp == 1) {
+  if (warp == 1) {
     // ================= hidden-state loader: acquire the producers' flag, then TMA the K-slice of tile i =================
     if (lane == 0) {
       const int m_lo = (s * a.KSLICE) / 128, m_hi = ((s + 1) * a.KSLICE - 1) / 128;
@@ -137,10 +143,14 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmS_hi, const __grid_constant
           const int slot = (k - 1) & 1;
           for (int i = 0; i < n_tiles; ++i, ++it) {
             const int hs = it % a.HST;
-            if (!mbar_wait(&bars->h_empty[hs], ((it / a.HST) & 1) ^ 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 202); goto h_done; }
-            for (int mm = m_lo; mm <= m_hi; ++mm)
-              if (!poll_flag(a.flags + i * a.MT + mm, target, err)) { atomicCAS(a.dev_error, 0, 203); goto h_done; }
-            fence_proxy_async();                       // generic-proxy writes of the owners -> async-proxy (TMA) reads
+            bool okh;
+            RT_TIMED(0, okh = mbar_wait(&bars->h_empty[hs], ((it / a.HST) & 1) ^ 1, err, RT_WATCHDOG));
+            if (!okh) { atomicCAS(a.dev_error, 0, 202); goto h_done; }
+            for (int mm = m_lo; mm <= m_hi; ++mm) {
+              RT_TIMED(1, okh = poll_flag(a.flags + i * a.MT + mm, target, err));
+              if (!okh) { atomicCAS(a.dev_error, 0, 203); goto h_done; }
+            }
+            RT_TIMED(2, fence_proxy_async());          // generic-proxy writes of the owners -> async-proxy (TMA) reads
             uint8_t* dst = smem + a.off_h + hs * a.h_stage_bytes;
             mbar_expect_tx(&bars->h_full[hs], 2 * ATOMS * H_ATOM_BYTES);
             for (int at = 0; at < ATOMS; ++at) {
@@ -154,196 +164,371 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmS_hi, const __grid_constant
   h_done:;
   } else if (warp == 2) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The whole warp runs the loop convergently (descriptor arithmetic stays in the uniform datapath); one elected
+    // lane issues the tcgen05 instructions.
+    {
       const uint32_t idesc = umma_idesc_tf32(128, NB);
       int it = 0;
-      for (int ms = 0; ms < n_mma_steps; ++ms) {
+      bool okm = true;
+      for (int ms = 0; ms < n_mma_steps && okm; ++ms) {
         for (int i = 0; i < n_tiles; ++i, ++it) {
           const int as = it % RT_AST, hs = it % a.HST;
-          if (!mbar_wait(&bars->t_empty[as], ((it / RT_AST) & 1) ^ 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 204); goto m_done; }
-          if (!mbar_wait(&bars->h_full[hs], (it / a.HST) & 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 205); goto m_done; }
-          const uint32_t d_tmem = tmem_base + as * NB;
-          const uint32_t hbase = smem_u32(smem + a.off_h + hs * a.h_stage_bytes);
-          for (int at = 0; at < ATOMS; ++at) {
-            const int wl = ms * ATOMS + at, ws = wl % a.WST;
-            if (i == 0 && !mbar_wait(&bars->w_full[ws], (wl / a.WST) & 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 206); goto m_done; }
-            tc_fence_after();
-            const uint32_t wbase = smem_u32(smem + a.off_w + ws * (2 * W_ATOM_BYTES));
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t w_hi = umma_desc_k128(wbase + ks * 32);
-              const uint64_t w_lo = umma_desc_k128(wbase + W_ATOM_BYTES + ks * 32);
-              const uint64_t h_hi = umma_desc_k128(hbase + (2 * at) * H_ATOM_BYTES + ks * 32);
-              const uint64_t h_lo = umma_desc_k128(hbase + (2 * at + 1) * H_ATOM_BYTES + ks * 32);
-              umma_tf32(d_tmem, w_lo, h_hi, idesc, !(at == 0 && ks == 0));
-              umma_tf32(d_tmem, w_hi, h_lo, idesc, true);
-              umma_tf32(d_tmem, w_hi, h_hi, idesc, true);
-            }
-            if (i == n_tiles - 1) tc_commit(&bars->w_empty[ws]);     // weights of this step fully consumed
+          RT_TIMED(0, okm = mbar_wait(&bars->t_empty[as], ((it / RT_AST) & 1) ^ 1, err, RT_WATCHDOG));
+          if (!okm) { atomicCAS(a.dev_error, 0, 204); break; }
+          RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs], (it / a.HST) & 1, err, RT_WATCHDOG));
+          if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
+          if (i == 0) {      // this step's S_k^T block (hi | lo) has been written to TMEM by the loader warpgroup
+            RT_TIMED(2, okm = mbar_wait(&bars->wt_full, (uint32_t)(ms & 1), err, RT_WATCHDOG));
+            if (!okm) { atomicCAS(a.dev_error, 0, 206); break; }
           }
-          tc_commit(&bars->h_empty[hs]);
-          tc_commit(&bars->t_full[as]);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ACC_COL0 + as * NB;
+          const uint32_t hbase = smem_u32(smem + a.off_h + hs * a.h_stage_bytes);
+          const int nks = a.KSLICE / 8;
+          const bool leader = elect_one();
+#pragma unroll 4
+          for (int ks = 0; ks < nks; ++ks) {
+            const int at = ks >> 2, kk = ks & 3;
+            const uint32_t w_hi = tmem_base + ks * 8, w_lo = tmem_base + a.KSLICE + ks * 8;
+            const uint64_t h_hi = umma_desc_k128(hbase + (2 * at) * H_ATOM_BYTES + kk * 32);
+            const uint64_t h_lo = umma_desc_k128(hbase + (2 * at + 1) * H_ATOM_BYTES + kk * 32);
+            if (leader) {
+              umma_tf32_ts(d_tmem, w_lo, h_hi, idesc, ks != 0);
+              umma_tf32_ts(d_tmem, w_hi, h_lo, idesc, true);
+              umma_tf32_ts(d_tmem, w_hi, h_hi, idesc, true);
+            }
+          }
+          if (leader) {
+            if (i == n_tiles - 1) tc_commit(&bars->wt_empty);          // TMEM weights of this step fully consumed
+            tc_commit(&bars->h_empty[hs]);
+            tc_commit(&bars->t_full[as]);
+          }
+          __syncwarp();
         }
       }
     }
   m_done:;
   } else if (warp >= 4 && warp < 8) {
-    // ================= pushers: TMEM accumulator rows -> owner CTA's reduction slot over DSMEM =================
+    // ================= pushers: TMEM accumulator -> staging smem -> bulk DSMEM copy into every owner's slot =========
+    // Thread rho holds accumulator row rho.  Rows are staged row-major with the 16-byte chunks of a row XOR-swizzled
+    // by (row & 7) (conflict-free STS.128 here and LDS.128 in the owner); rows [o*RO, (o+1)*RO) are one contiguous
+    // block that a single cp.async.bulk moves into owner o's reduction slot (block index = this CTA's rank).
     const int q = warp - 4;
     const int rho = q * 32 + lane;                   // accumulator row (TMEM lane) within the M-tile
-    const int o = rho / a.RO, r = rho % a.RO;        // owner CTA in the cluster, row within the owner
-    const uint32_t rem_red = mapa_u32(smem_u32(smem + a.off_red), (uint32_t)o);
-    const uint32_t rem_bar = mapa_u32(smem_u32(&bars->red_full[0]), (uint32_t)o);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stage0 = smem_u32(smem + a.off_push);
+    const uint32_t blk_bytes = (uint32_t)(a.RO * NB * 4);
+    constexpr int CHUNKS = NB / 4;                   // 16-byte chunks per row
+    constexpr int SWZ = (CHUNKS >= 8) ? 7 : CHUNKS - 1;
     int it = 0;
-    bool ok = true;
-    for (int ms = 0; ms < n_mma_steps && ok; ++ms) {
-      for (int i = 0; i < n_tiles; ++i, ++it) {
+    for (int ms = 0; ms < n_mma_steps; ++ms) {      // on a watchdog error the loop keeps running (waits return at once)
+      for (int i = 0; i < n_tiles; ++i, ++it) {     // so that the named barrier below always sees all 128 threads
         const int as = it % RT_AST, rs = it % a.RST;
-        if (!mbar_wait(&bars->t_full[as], (it / RT_AST) & 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 207); ok = false; break; }
+        bool okp;
+        RT_TIMED(0, okp = mbar_wait(&bars->t_full[as], (it / RT_AST) & 1, err, RT_WATCHDOG));
+        if (!okp) atomicCAS(a.dev_error, 0, 207);
         tc_fence_after();
         float v[NB];
 #pragma unroll
-        for (int c = 0; c < NB; c += 16) tmem_ld16(trow + as * NB + c, v + c);
+        for (int c = 0; c < NB; c += 16) tmem_ld16(trow + ACC_COL0 + as * NB + c, v + c);
         tc_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->t_empty[as]);
-        if (!mbar_wait_cluster(&bars->red_free[rs], ((it / a.RST) & 1) ^ 1, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 208); ok = false; break; }
-        const uint32_t dst = rem_red + rs * a.red_slot_bytes + ((s * a.RO + r) * RSTRIDE) * 4;
-        const uint32_t bar = rem_bar + rs * 8;
+        // slot rs (staging here, reduction slot in the owners) is free once every owner has consumed its previous use
+        RT_TIMED(1, okp = mbar_wait_cluster(&bars->red_free[rs], ((it / a.RST) & 1) ^ 1, err, RT_WATCHDOG));
+        if (!okp) atomicCAS(a.dev_error, 0, 208);
+        const uint32_t srow = stage0 + rs * a.red_slot_bytes + rho * (NB * 4);
 #pragma unroll
-        for (int c = 0; c < NB; c += 4) st_async_v4(dst + c * 4, bar, v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int c = 0; c < CHUNKS; ++c) {
+          const uint32_t addr = srow + (uint32_t)(((c & ~SWZ) | ((c ^ rho) & SWZ)) * 16);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                       "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+        }
+        fence_proxy_async_smem();                     // generic-proxy STS -> async-proxy bulk copy reads
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 4 && lane < a.KS) {               // lane o copies this CTA's block for owner o
+          const uint32_t src = stage0 + rs * a.red_slot_bytes + (uint32_t)lane * blk_bytes;
+          const uint32_t dst = mapa_u32(smem_u32(smem + a.off_red) + rs * a.red_slot_bytes + (uint32_t)s * blk_bytes, (uint32_t)lane);
+          const uint32_t bar = mapa_u32(smem_u32(&bars->red_full[rs]), (uint32_t)lane);
+          dsmem_bulk_copy(dst, src, blk_bytes, bar);
+        }
       }
     }
-  } else if (warp >= 8) {
-    // ================= owners: reduce the KS partials of rows [o*RO, (o+1)*RO), epilogue, publish =================
+  } else if (warp == 3) {
+    // ================= publisher: one gpu-scope release per (step, tile) after the owners' stores =================
+    // The owner threads only arrive on pub_full (release.cta); this thread acquires it, issues the single cumulative
+    // gpu-scope fence and bumps flag[tile][m], so the owners never stall on a memory fence.
+    if (lane == 0) {
+      const long long n_items = (long long)T * K * n_tiles;
+      long long j = 0;
+      while (j < n_items) {
+        bool okb;
+        RT_TIMED(0, okb = mbar_wait(&bars->pub_full[(int)(j % RT_PST)], (uint32_t)((j / RT_PST) & 1), err, RT_WATCHDOG));
+        if (!okb) { atomicCAS(a.dev_error, 0, 211); break; }
+        // batch every further item that is already complete behind ONE gpu-scope fence (throughput mode)
+        long long jend = j + 1;
+        while (jend < n_items && jend - j < RT_PST &&
+               mbar_try_wait(&bars->pub_full[(int)(jend % RT_PST)], (uint32_t)((jend / RT_PST) & 1))) ++jend;
+        // fence.acq_rel.gpu is cumulative over the owners' stores observed through the mbarriers (release/acquire.cta)
+        RT_TIMED(1, asm volatile("fence.acq_rel.gpu;" ::: "memory"));
+        for (long long q2 = j; q2 < jend; ++q2) {
+          const int i = (int)(q2 % n_tiles);
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(a.flags + i * a.MT + m), "r"(1u) : "memory");
+          mbar_arrive(&bars->pub_empty[(int)(q2 % RT_PST)]);
+        }
+        j = jend;
+      }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ================= owners: reduce the KS partials of rows [o*RO, (o+1)*RO), epilogue, hand off to the publisher ====
     const int otid = threadIdx.x - 256;              // 0..127
     const int RO = a.RO;
     const int row0 = m * 128 + s * RO;               // first global output row this CTA owns
     const int n_out = RO * NB;                       // outputs per tile
     const int cta_lin = m * a.KS + s, n_cta = a.MT * a.KS;
     const size_t KRp = (size_t)K * Rp;
+    // Each active thread owns 4x4 blocks of outputs: rows 4*rq..+3 of this owner x batch columns 4*bq..+3 of the tile.
+    // Partials are read as LDS.128 over the batch columns, results leave as float4 over the rows (K-major state).
+    constexpr int MAXB = 1;                          // blocks per thread (RO*NB <= 2048*MAXB)
+    constexpr int BQ = NB / 4;
+    constexpr int SWZ = (BQ >= 8) ? 7 : BQ - 1;
+    const int n_blk = (RO / 4) * BQ;
     // sum_j h0[j]: leak of frame 0 (state = h0 for every utterance), same fixed order in every CTA
     float h0sum = 0.f;
     for (int j = 0; j < a.R; ++j) h0sum += a.h0[j];
+    int blk_bq[MAXB], blk_rq[MAXB];
+    bool blk_v[MAXB];
+#pragma unroll
+    for (int c = 0; c < MAXB; ++c) {
+      const int u = otid + 128 * c;
+      blk_v[c] = u < n_blk;
+      blk_bq[c] = blk_v[c] ? u % BQ : 0;
+      blk_rq[c] = blk_v[c] ? u / BQ : 0;
+    }
+    // x~W_k + b_k of an item does not depend on the recurrence: fetched one item ahead, unconditionally from clamped
+    // addresses, and only consumed an iteration later, so the in-order warp never waits on a load it just issued.
+    auto fetch_xw = [&](int t, int k, int i, float4 (&xa)[MAXB][4]) {
+      const int tc = t < T ? t : T - 1;
+#pragma unroll
+      for (int c = 0; c < MAXB; ++c)
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi) {
+          int b = i * NB + 4 * blk_bq[c] + bi; b = b < a.B ? b : a.B - 1;
+          xa[c][bi] = __ldg(reinterpret_cast<const float4*>(a.XW + ((size_t)b * T + tc) * KRp + (size_t)k * Rp + row0 + 4 * blk_rq[c]));
+        }
+    };
+    float4 xa_next[MAXB][4];
+    fetch_xw(0, 0, 0, xa_next);
     int it = 0;
-    bool ok = true;
-    for (int t = 0; t < T && ok; ++t) {
-      for (int k = 0; k < K && ok; ++k) {
-        const bool last = (k == K - 1);
-        const float dmo = (k == 0) ? a.u0_dmo : a.uk_dmo, off = (k == 0) ? a.u0_off : a.uk_off;
-        for (int i = 0; i < n_tiles; ++i) {
-          // ---- prefetch what does not depend on the exchange: x~W_k, bias, validity ----
-          constexpr int MAXE = 8;                    // outputs per thread (RO*NB/128 <= 8 for the supported configs)
-          float xw[MAXE], acc[MAXE];
+    long long j = 0;
+    for (int t = 0; t < T; ++t)
+    for (int k = 0; k < K; ++k)
+    for (int i = 0; i < n_tiles; ++i, ++j) {
+      const bool last = (k == K - 1);
+      const float dmo = (k == 0) ? a.u0_dmo : a.uk_dmo, off = (k == 0) ? a.u0_off : a.uk_off;
+      float4 xw[MAXB][4];
+      float acc[MAXB][4][4];                           // [block][row e][batch bi]
+      long long _ts = dbg_on ? clock64() : 0;
 #pragma unroll
-          for (int c = 0; c < MAXE; ++c) {
-            const int e = otid + 128 * c;
-            xw[c] = 0.f; acc[c] = 0.f;
-            if (e < n_out) {
-              const int b = i * NB + e / RO, row = row0 + e % RO;
-              if (b < a.B && row < a.R)
-                xw[c] = __ldg(a.XW + ((size_t)b * T + t) * KRp + (size_t)k * Rp + row) + __ldg(a.bias + (size_t)k * Rp + row);
-            }
-          }
-          if (k == 0) {
-            // ---- frame start: leak[b] = sum_j state[b][j] from the published partial sums of the previous frame ----
-            if (t > 0) {
-              const unsigned int target = (unsigned int)a.KS * (unsigned int)(t * K);
-              if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) { atomicCAS(a.dev_error, 0, 209); bars->abort = 1; }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              if (bars->abort) { ok = false; break; }
-              const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
-              float sacc = 0.f;
-              const float* ps = a.psum + (size_t)((t - 1) & 1) * 256 * a.Bp + i * NB + b;
-              for (int c = part; c < n_cta; c += nparts) sacc += __ldcg(ps + (size_t)c * a.Bp);
-              out_s[part * NB + b] = sacc;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              if (otid < NB) {
-                float tot = 0.f;
-                for (int p = 0; p < nparts; ++p) tot += out_s[p * NB + otid];
-                leak_s[i * NB + otid] = tot;
-              }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-            } else if (otid < NB) {
-              leak_s[i * NB + otid] = h0sum;
-            }
-            if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          } else {
-            // ---- wait for the KS partial tiles, sum them in rank order ----
-            const int rs = it % a.RST;
-            if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
-            const bool got = mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG);
-            if (!owners_all(got)) { atomicCAS(a.dev_error, 0, 210); ok = false; break; }
-            const float* red = reinterpret_cast<const float*>(smem + a.off_red + rs * a.red_slot_bytes);
+      for (int c = 0; c < MAXB; ++c)
 #pragma unroll
-            for (int c = 0; c < MAXE; ++c) {
-              const int e = otid + 128 * c;
-              if (e < n_out) {
-                const int bl = e / RO, r = e % RO;
-                float sum = 0.f;
-                for (int src = 0; src < a.KS; ++src) sum += red[(src * RO + r) * RSTRIDE + bl];
-                acc[c] = sum;
-              }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");            // every owner thread is done reading the slot
-            if (otid < a.KS) mbar_arrive_remote(&bars->red_free[rs], (uint32_t)otid);
-            ++it;
-          }
-          // ---- fused epilogue ----
-#pragma unroll
-          for (int c = 0; c < MAXE; ++c) {
-            const int e = otid + 128 * c;
-            if (e < n_out) {
-              const int bl = e / RO, r = e % RO, b = i * NB + bl, row = row0 + r;
-              float g = 0.f, st_new = 0.f;
-              const bool valid = (b < a.B && row < a.R);
-              float st_old = 0.f;
-              const bool need_state = valid && (k == 0 || dmo != 0.f);
-              if (need_state) st_old = (t == 0) ? __ldg(a.h0 + row) : __ldcg(a.state + (size_t)b * Rp + row);
-              if (valid) g = fmaxf(acc[c] + xw[c] + off * leak_s[i * NB + bl] + (need_state ? dmo * st_old : 0.f), 0.f);
-              if (!last) {
-                if (b < a.Bp) {
-                  const size_t o2 = ((size_t)(k & 1) * a.Bp + b) * Rp + row;
-                  __stcg(a.hb_hi + o2, g);
-                  __stcg(a.hb_lo + o2, tf32_lo(g));
-                }
-              } else if (b < a.B) {
-                // Keras masked scan: out_t = m ? g : out_{t-1} (zeros before the first step); state = m ? g : state
-                const size_t bt = (size_t)b * T + t;
-                const bool mv = __ldg(a.mvalid + bt) != 0.f;
-                float outv;
-                if (mv) { outv = g; st_new = g; }
-                else {
-                  outv = (t > 0) ? __ldcg(a.Hp_hi + (bt - 1) * Rp + row) : 0.f;
-                  st_new = (row < a.R) ? ((t == 0) ? __ldg(a.h0 + row) : __ldcg(a.state + (size_t)b * Rp + row)) : 0.f;
-                }
-                __stcg(a.Hp_hi + bt * Rp + row, outv);
-                __stcg(a.Hp_lo + bt * Rp + row, tf32_lo(outv));
-                if (a.H_user && row < a.R) a.H_user[bt * a.R + row] = outv;
-                __stcg(a.state + (size_t)b * Rp + row, st_new);
-              }
-              if (last) out_s[bl * (RO + 1) + r] = st_new;
-            }
-          }
-          if (last) {
-            // partial row sums of the new state over this CTA's RO rows (rank-1 leak of the next frame)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (otid < NB) {
-              float ps = 0.f;
-              for (int r = 0; r < RO; ++r) ps += out_s[otid * (RO + 1) + r];
-              __stcg(a.psum + (size_t)(t & 1) * 256 * a.Bp + (size_t)cta_lin * a.Bp + i * NB + otid, ps);
-            }
-          }
-          // ---- publish: all owner threads' global writes -> one release increment of flag[tile][m] ----
-          fence_proxy_async();
-          __threadfence();
+        for (int e = 0; e < 4; ++e) {
+          xw[c][e] = xa_next[c][e];
+          acc[c][e][0] = acc[c][e][1] = acc[c][e][2] = acc[c][e][3] = 0.f;
+        }
+      {
+        int i2 = i + 1, k2 = k, t2 = t;
+        if (i2 == n_tiles) { i2 = 0; if (++k2 == K) { k2 = 0; ++t2; } }
+        fetch_xw(t2, k2, i2, xa_next);
+      }
+      if (dbg_on) { long long _n = clock64(); dbg_acc[2] += _n - _ts; _ts = _n; }
+      if (k == 0) {
+        // ---- frame start: leak[b] = sum_j state[b][j] from the published partial sums of the previous frame ----
+        if (t > 0) {
+          const unsigned int target = (unsigned int)a.KS * (unsigned int)(t * K);
+          if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) atomicCAS(a.dev_error, 0, 209);
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (otid == 0) flag_add_release(a.flags + i * a.MT + m, 1u);
+          const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
+          float sacc = 0.f;
+          const float* ps = a.psum + (size_t)((t - 1) & 1) * 256 * a.Bp + i * NB + b;
+          for (int c = part; c < n_cta; c += nparts) sacc += __ldcg(ps + (size_t)c * a.Bp);
+          out_s[part * NB + b] = sacc;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (otid < NB) {
+            float tot = 0.f;
+            for (int p = 0; p < nparts; ++p) tot += out_s[p * NB + otid];
+            leak_s[i * NB + otid] = tot;
+          }
+        } else if (otid < NB) {
+          leak_s[i * NB + otid] = h0sum;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else {
+        // ---- wait for the KS partial tiles, sum them in rank order ----
+        const int rs = it % a.RST;
+        if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
+        bool oko;
+        RT_TIMED(0, oko = mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG));
+        if (!oko) atomicCAS(a.dev_error, 0, 210);
+        const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
+        if (dbg_on) _ts = clock64();
+        // address of (row r, 16-byte chunk bq) inside a source block: row-major, chunk index swizzled by (row & 7);
+        // the pusher's row index rho = o*RO + r has the same low 3 bits as r because RO is a multiple of 8.
+        uint32_t qaddr[MAXB][4];
+#pragma unroll
+        for (int c = 0; c < MAXB; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r = 4 * blk_rq[c] + e, ch = blk_bq[c];
+            qaddr[c][e] = red + (uint32_t)(r * (NB * 4) + ((ch & ~SWZ) | ((ch ^ r) & SWZ)) * 16);
+          }
+        const uint32_t src_stride = (uint32_t)(RO * NB * 4);
+#pragma unroll 2
+        for (int src = 0; src < a.KS; ++src) {
+          float4 ld[MAXB][4];
+#pragma unroll
+          for (int c = 0; c < MAXB; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ld[c][e].x), "=f"(ld[c][e].y), "=f"(ld[c][e].z),
+                           "=f"(ld[c][e].w) : "r"(qaddr[c][e] + src * src_stride));
+#pragma unroll
+          for (int c = 0; c < MAXB; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[c][e][0] += ld[c][e].x; acc[c][e][1] += ld[c][e].y; acc[c][e][2] += ld[c][e].z; acc[c][e][3] += ld[c][e].w;
+            }
+        }
+        if (dbg_on) { long long _n = clock64(); dbg_acc[3] += _n - _ts; _ts = _n; }
+        __syncwarp();                                  // this warp has consumed the slot (values are in registers):
+        if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);   // 4 warps x KS owners arrivals
+        if (dbg_on) { long long _n = clock64(); dbg_acc[4] += _n - _ts; _ts = _n; }
+        ++it;
+      }
+      // ---- fused epilogue: relu(acc + x~W_k + b_k + leak terms), Keras mask carry on the last layer ----
+#pragma unroll
+      for (int c = 0; c < MAXB; ++c) {
+        if (blk_v[c]) {
+          const int rowq = row0 + 4 * blk_rq[c];
+          const float4 lk4 = *reinterpret_cast<const float4*>(leak_s + i * NB + 4 * blk_bq[c]);
+          const float lkv[4] = {off * lk4.x, off * lk4.y, off * lk4.z, off * lk4.w};
+#pragma unroll
+          for (int bi = 0; bi < 4; ++bi) {
+            const int bl = 4 * blk_bq[c] + bi, b = i * NB + bl;
+            const float xv[4] = {xw[c][bi].x, xw[c][bi].y, xw[c][bi].z, xw[c][bi].w};
+            float g[4], stn[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool need_state = (b < a.B) && (k == 0 || dmo != 0.f);
+            float4 so = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (need_state)
+              so = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
+                            : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)b * Rp + rowq));
+            const float sv[4] = {so.x, so.y, so.z, so.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool valid = (b < a.B) && (rowq + e < a.R);
+              g[e] = valid ? fmaxf(acc[c][e][bi] + xv[e] + lkv[bi] + (need_state ? dmo * sv[e] : 0.f), 0.f) : 0.f;
+            }
+            if (!last) {
+              const size_t o2 = ((size_t)(k & 1) * a.Bp + b) * Rp + rowq;
+              __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(g[0], g[1], g[2], g[3]));
+              __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(g[0]), tf32_lo(g[1]), tf32_lo(g[2]), tf32_lo(g[3])));
+            } else if (b < a.B) {
+              // Keras masked scan: out_t = m ? g : out_{t-1} (zeros before the first step); state = m ? g : state
+              const size_t bt = (size_t)b * T + t;
+              const bool mv = __ldg(a.mvalid + bt) != 0.f;
+              float outv[4];
+              if (mv) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { outv[e] = g[e]; stn[e] = g[e]; }
+              } else {
+                float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t > 0) po = __ldcg(reinterpret_cast<const float4*>(a.Hp_hi + (bt - 1) * Rp + rowq));
+                const float4 ss = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
+                                           : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)b * Rp + rowq));
+                outv[0] = po.x; outv[1] = po.y; outv[2] = po.z; outv[3] = po.w;
+                stn[0] = ss.x; stn[1] = ss.y; stn[2] = ss.z; stn[3] = ss.w;
+              }
+              __stcg(reinterpret_cast<float4*>(a.Hp_hi + bt * Rp + rowq), make_float4(outv[0], outv[1], outv[2], outv[3]));
+              __stcg(reinterpret_cast<float4*>(a.Hp_lo + bt * Rp + rowq),
+                     make_float4(tf32_lo(outv[0]), tf32_lo(outv[1]), tf32_lo(outv[2]), tf32_lo(outv[3])));
+              if (a.H_user) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (rowq + e < a.R) a.H_user[bt * a.R + rowq + e] = outv[e];
+              }
+              __stcg(reinterpret_cast<float4*>(a.state + (size_t)b * Rp + rowq), make_float4(stn[0], stn[1], stn[2], stn[3]));
+            }
+            if (last) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) out_s[bl * (RO + 1) + 4 * blk_rq[c] + e] = stn[e];
+            }
+          }
         }
       }
+      if (last) {
+        // partial row sums of the new state over this CTA's RO rows (rank-1 leak of the next frame)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (otid < NB) {
+          float ps = 0.f;
+          for (int r = 0; r < RO; ++r) ps += out_s[otid * (RO + 1) + r];
+          __stcg(a.psum + (size_t)(t & 1) * 256 * a.Bp + (size_t)cta_lin * a.Bp + i * NB + otid, ps);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // out_s may be rewritten by the next item
+      }
+      if (dbg_on) { long long _n = clock64(); dbg_acc[5] += _n - _ts; _ts = _n; }
+      // ---- hand the item to the publisher (release.cta arrive; the publisher's fence makes it gpu-visible) ----
+      const int ps_ = (int)(j % RT_PST);
+      bool okq;
+      RT_TIMED(1, okq = mbar_wait(&bars->pub_empty[ps_], (uint32_t)(((j / RT_PST) & 1) ^ 1), err, RT_WATCHDOG));
+      if (!okq) atomicCAS(a.dev_error, 0, 212);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->pub_full[ps_]);   // release.cta, cumulative over the warp's stores (after __syncwarp)
     }
+  }
+  if (warp >= 12) {
+    // ================= weight loaders: S_k^T[m*128 + row][s*KSLICE ..] -> registers -> (hi | lo) in TMEM =================
+    const int q = warp - 12;                          // TMEM lane quarter (warp % 4)
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nchunk = a.KSLICE / 32;
+    for (int ms = 0; ms < n_mma_steps; ++ms) {
+      const int k = ms % (K - 1) + 1;
+      const float* src = a.ST + ((size_t)(k - 1) * Rp + (size_t)m * 128 + row) * Rp + (size_t)s * a.KSLICE;
+      float v[32];
+      // first chunk is fetched before waiting for the buffer (latency of L2 overlaps the previous step's tail)
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src) + c4);
+        v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
+      }
+      bool okl;
+      RT_TIMED(0, okl = mbar_wait(&bars->wt_empty, (uint32_t)((ms & 1) ^ 1), err, RT_WATCHDOG));
+      if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
+      tc_fence_after();
+      for (int ch = 0; ch < nchunk; ++ch) {
+        float lo[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(v[e]);
+        tmem_st32(trow + ch * 32, v);
+        tmem_st32(trow + a.KSLICE + ch * 32, lo);
+        if (ch + 1 < nchunk) {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(src + (ch + 1) * 32) + c4);
+            v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
+          }
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->wt_full);
+    }
+  }
+  if (dbg_on && (lane == 0 || warp >= 4) && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64 ||
+                                              threadIdx.x == 96 || threadIdx.x == 128 || threadIdx.x == 256 || threadIdx.x == 384)) {
+    long long* d = a.dbg + (threadIdx.x / 32) * 8;        // slot per warp: [total, acc0..acc5]
+    d[0] = clock64() - dbg_t0;
+    for (int q2 = 0; q2 < 6; ++q2) d[1 + q2] = dbg_acc[q2];
   }
   // ---- teardown: nobody leaves while a peer may still touch its shared memory ----
   tc_fence_before();
@@ -364,26 +549,26 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
   p.n_tiles = (B + p.NB - 1) / p.NB;
   if (Rp % (KS * 32) != 0 || p.MT * KS > h->num_sms) { p.why = "no (M-tile x K-split) grid fits the device"; return p; }
   p.KS = KS; p.RO = 128 / KS; p.KSLICE = Rp / KS; p.ATOMS = p.KSLICE / 32;
-  if (p.RO * p.NB > 128 * 8) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
-  const int w_atom = 2 * 128 * 128, h_stage = 2 * p.ATOMS * p.NB * 128, red_slot = 128 * (p.NB + 4) * 4;
+  if (p.KSLICE > 128) { p.why = "K-slice wider than 128 atoms: weights (hi|lo) do not fit the 256 TMEM columns reserved for them"; return p; }
+  if (p.RO * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
+  const int h_stage = 2 * p.ATOMS * p.NB * 128, red_slot = 128 * p.NB * 4;   // slot = KS blocks of RO x NB fp32
   const int leak_b = round_up(p.n_tiles * p.NB * 4, 128), out_b = round_up(max(p.NB * (p.RO + 1), 128) * 4, 128);
   const int fixed = leak_b + out_b + (int)sizeof(RecBars) + 256;
   const int budget = 232448 - 1024 - fixed;
-  p.HST = 2; p.RST = 2;
-  int wst = (budget - p.HST * h_stage - p.RST * red_slot) / w_atom;
-  if (wst > 8) wst = 8;
-  if (wst > 2 * p.ATOMS) wst = 2 * p.ATOMS;
-  if (wst < p.ATOMS + 1 && wst < 2 * p.ATOMS) {
-    if (wst < p.ATOMS) { p.why = "K-slice of the weights does not fit in shared memory (needs the streaming variant)"; return p; }
+  // every reduction slot has a twin staging slot on the pusher side (same index), hence 2 * red_slot per depth
+  p.WST = 0; p.HST = 2; p.RST = 1;
+  int rem = budget - p.HST * h_stage - p.RST * 2 * red_slot;
+  if (rem < 0) { p.why = "hidden-state and reduction rings do not fit in shared memory"; return p; }
+  if (rem >= 2 * red_slot) { ++p.RST; rem -= 2 * red_slot; }
+  if (p.n_tiles > 1) {
+    while (p.HST < 4 && rem >= h_stage) { ++p.HST; rem -= h_stage; }
+    while (p.RST < 4 && rem >= 2 * red_slot) { ++p.RST; rem -= 2 * red_slot; }
   }
-  p.WST = wst;
-  int rem = budget - p.WST * w_atom - p.HST * h_stage - p.RST * red_slot;
-  while (p.HST < 4 && rem >= h_stage) { ++p.HST; rem -= h_stage; if (p.HST >= 3) break; }
-  while (p.RST < 4 && rem >= red_slot) { ++p.RST; rem -= red_slot; if (p.RST >= 3) break; }
   int off = 0;
-  p.a.off_w = off; off += p.WST * w_atom;
+  p.a.off_w = 0;
   p.a.off_h = off; off += p.HST * h_stage;
   p.a.off_red = off; off += p.RST * red_slot;
+  p.a.off_push = off; off += p.RST * red_slot;
   p.a.off_leak = off; off += leak_b;
   p.a.off_out = off; off += out_b;
   p.a.off_bar = off; off += (int)sizeof(RecBars);
@@ -416,8 +601,7 @@ static int rec_max_clusters(const RecPlan& p, int* out) {
 }
 
 template <int NB>
-static int launch_rec(const RecPlan& p, const CUtensorMap& tS_hi, const CUtensorMap& tS_lo, const CUtensorMap& tH_hi,
-                      const CUtensorMap& tH_lo, cudaStream_t st) {
+static int launch_rec(const RecPlan& p, const CUtensorMap& tH_hi, const CUtensorMap& tH_lo, cudaStream_t st) {
   auto kern = k_recurrent_tc<NB>;
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
@@ -430,7 +614,7 @@ static int launch_rec(const RecPlan& p, const CUtensorMap& tS_hi, const CUtensor
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.KS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  DRNMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tS_hi, tS_lo, tH_hi, tH_lo, p.a));
+  DRNMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tH_hi, tH_lo, p.a));
   count_launch();
   return DRNMF_OK;
 }
@@ -445,13 +629,13 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   const char* env_nb = getenv("DRNMF_REC_NB");
   for (int KS = 16; KS >= 1 && !p.ok; KS >>= 1) {
     if (env_ks && atoi(env_ks) != KS) continue;
-    for (int NB = 32; NB >= 16 && !p.ok; NB >>= 1) {
+    for (int NB = 64; NB >= 16 && !p.ok; NB >>= 1) {
       if (env_nb && atoi(env_nb) != NB) continue;
-      if (NB == 32 && B <= 16) continue;
+      if (!env_nb && ((NB == 64 && B <= 32) || (NB == 32 && B <= 16))) continue;
       RecPlan c = plan_recurrent(h, B, KS, NB);
       if (!c.ok) { if (!p.why || !p.ok) p.why = c.why; continue; }
       int mc = 0;
-      if (NB == 16) rec_max_clusters<16>(c, &mc); else rec_max_clusters<32>(c, &mc);
+      if (NB == 16) rec_max_clusters<16>(c, &mc); else if (NB == 32) rec_max_clusters<32>(c, &mc); else rec_max_clusters<64>(c, &mc);
       if (mc < c.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
       p = c;
     }
@@ -466,21 +650,40 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   h->last_rec_impl = 0;
   { int c[8] = {p.NB, p.KS, p.MT, p.ATOMS, p.n_tiles, p.WST, p.HST, p.RST}; for (int i = 0; i < 8; ++i) h->rec_cfg[i] = c[i]; }
   RecArgs& a = p.a;
-  a.XW = w.XW; a.bias = h->bias; a.mvalid = w.mvalid; a.h0 = h->h0;
+  a.XW = w.XW; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.state = w.state; a.psum = w.psum; a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;
   a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
+  static long long* dbg_dev = nullptr;
+  const bool want_dbg = getenv("DRNMF_REC_DEBUG") != nullptr;
+  if (want_dbg && !dbg_dev) DRNMF_CUDA(cudaMalloc(&dbg_dev, 16 * 8 * sizeof(long long)));
+  a.dbg = want_dbg ? dbg_dev : nullptr;
+  if (want_dbg) DRNMF_CUDA(cudaMemsetAsync(dbg_dev, 0, 16 * 8 * sizeof(long long), st));
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = h->u0_d - h->u0_o; a.u0_off = h->u0_o; a.uk_dmo = h->uk_d - h->uk_o; a.uk_off = h->uk_o;
   DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles * p.MT, st));
-  CUtensorMap tS_hi, tS_lo, tH_hi, tH_lo;
+  a.ST = h->ST_hi;
+  CUtensorMap tH_hi, tH_lo;
   int rc;
-  const uint64_t s_rows = (uint64_t)(K > 1 ? K - 1 : 1) * Rp;
-  if ((rc = make_tmap_2d(&tS_hi, h->ST_hi, Rp, s_rows, Rp, 32, 128))) return rc;
-  if ((rc = make_tmap_2d(&tS_lo, h->ST_lo, Rp, s_rows, Rp, 32, 128))) return rc;
   if ((rc = make_tmap_2d(&tH_hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
   if ((rc = make_tmap_2d(&tH_lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
-  if (p.NB == 16) return launch_rec<16>(p, tS_hi, tS_lo, tH_hi, tH_lo, st);
-  return launch_rec<32>(p, tS_hi, tS_lo, tH_hi, tH_lo, st);
+  rc = (p.NB == 16) ? launch_rec<16>(p, tH_hi, tH_lo, st)
+     : (p.NB == 32) ? launch_rec<32>(p, tH_hi, tH_lo, st) : launch_rec<64>(p, tH_hi, tH_lo, st);
+  if (rc == DRNMF_OK && want_dbg) {
+    long long d[16 * 8];
+    DRNMF_CUDA(cudaMemcpyAsync(d, dbg_dev, sizeof(d), cudaMemcpyDeviceToHost, st));
+    DRNMF_CUDA(cudaStreamSynchronize(st));
+    const char* names[16] = {"", "h-loader", "mma", "publisher", "pusher", "", "", "", "owner", "", "", "", "w-loader", "", "", ""};
+    const long long items = (long long)T * (K - 1) * p.n_tiles;
+    fprintf(stderr, "[libdrnmf] recurrence debug (CTA 0,0; cycles per MMA item, %lld items): NB=%d KS=%d tiles=%d\n", items, p.NB, p.KS, p.n_tiles);
+    for (int wv = 0; wv < 16; ++wv) {
+      if (!names[wv][0]) continue;
+      const long long* q = d + wv * 8;
+      fprintf(stderr, "  %-10s total %8.0f | acc0 %8.0f acc1 %8.0f acc2 %8.0f acc3 %8.0f acc4 %8.0f acc5 %8.0f\n", names[wv],
+              (double)q[0] / items, (double)q[1] / items, (double)q[2] / items, (double)q[3] / items, (double)q[4] / items,
+              (double)q[5] / items, (double)q[6] / items);
+    }
+  }
+  return rc;
 }
 
 }  // namespace drnmf

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export DRNMF_REC_DEBUG=1
+( timeout 300 python scripts/rec_debug.py 64 40
+  timeout 300 python scripts/rec_debug.py 512 10 ) 2>&1 | grep -v "^\[libdrnmf\] recurrence debug" | awk '/h-loader/{c++} { if (c%2==0 || /^B=/) print }' > gpurun_out/trip8.log 2>&1
+tail -40 gpurun_out/trip8.log
