@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--R", type=int, default=1000)
     ap.add_argument("--layers", type=int, default=25)
     ap.add_argument("--cpu-utts", type=int, default=64, help="utterances in the CPU-baseline sample")
-    ap.add_argument("--ref-utts", type=int, default=16, help="utterances per step of --impl reference")
+    ap.add_argument("--ref-utts", type=int, default=64, help="utterances per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--throughput-batch", type=int, default=0,
                     help="also time a large device-resident batch (reported under config.throughput_mode)")

@@ -82,7 +82,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(dev_error, 199); return; }
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  // M-tiles are the fast grid dimension: the CTAs resident at any time share a few B (weight) tiles and sweep A,
+  // which is the smaller operand and fits L2 -> each weight tile is fetched from HBM once.
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
   const int num_kb = (a.Kd + TC_BK - 1) / TC_BK;
 
   if (warp == 0 && lane_id() == 0) {
@@ -229,7 +231,7 @@ static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
     DRNMF_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.M + TC_BM - 1) / TC_BM);
+  dim3 grid((a.M + TC_BM - 1) / TC_BM, (a.N + TC_BN - 1) / TC_BN);
   k_gemm_tc<EPI><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo, a, dev_error);
   count_launch();
   DRNMF_CUDA(cudaGetLastError());

@@ -229,3 +229,63 @@ def test_enhance_sdr_parity(impl):
         dq = abs(O.sdr_db(O.wav_quantize(got[:n]), clean) - O.sdr_db(O.wav_quantize(ref[:n].astype(np.float32)), clean))
         assert d < 0.01 and dq < 0.01, (impl, b, d, dq)
         assert np.all(out[b, ref.size:] == 0)
+
+
+# ---- the reference-facing interfaces (custom_layers / enhance / util / audio_dataset mirrors) ---------------
+def _build_params(F, r, K, T, W, **extra):
+    p = {"input_dim": F, "hidden_dim": 2 * r, "output_dim": F, "mask_value": -1.0, "maxseq": T, "K_layers": K, "W": W,
+         "alph": 20.0, "lam1": 0.5, "params_untied": ["log_D", "log_alph"], "params_trainable": ["log_D", "log_alph"]}
+    p.update(extra)
+    return p
+
+
+@pytest.mark.parametrize("untie_alph", [False, True])
+def test_build_unfolded_snmf_predict_on_batch(untie_alph):
+    from drnmf_b200 import enhance
+    F, r, K, B, T = 65, 12, 3, 4, 9
+    rng = np.random.default_rng(31)
+    W = synth.dictionary(F, 2 * r)
+    model = enhance.build_unfolded_snmf(_build_params(F, r, K, T, W, untie_alph=untie_alph))
+    x = (np.abs(rng.standard_normal((B, T, F))) * 2).astype(np.float32)
+    x[2, 5:] = -1.0
+    irm, H = model.predict_on_batch(x, return_hidden=True)
+    # oracle with the SAME initial parameters (log_h0 is drawn by the layer -> read it back)
+    p = O.alt_params_init(W, 20.0, 0.5, K, untie_alph=untie_alph)
+    p["log_h0"] = model.rnn.log_h0.cpu().numpy()
+    Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+    assert max(rel_err(H, Ho)) < TOL and max(rel_err(irm, irmo)) < TOL
+    # Keras-like weight surface: names, round trip through save/load
+    names = model.weight_names()
+    assert names[0].endswith("_log_h0") and any(n.endswith("_log_D_2") for n in names) and len(names) == len(model.get_weights())
+    w = model.get_weights()
+    model2 = enhance.build_unfolded_snmf(_build_params(F, r, K, T, np.ones_like(W), untie_alph=untie_alph))
+    model2.set_weights(w)
+    np.testing.assert_array_equal(model2.predict_on_batch(x), irm)
+
+
+def test_util_and_audio_dataset_mirrors(golden_dir):
+    from drnmf_b200 import audio_dataset, util
+    g = np.load(os.path.join(golden_dir, "stft_istft.npz"))
+    N, hop, x = int(g["b_N"]), int(g["b_hop"]), g["b_x"]
+    win = util.sqrt_hann(N)
+    X = util.stft_mc(x.reshape(1, -1), N, hop, win)
+    F = N // 2 + 1
+    np.testing.assert_allclose(np.concatenate([X[:, :, 0].real, X[:, :, 0].imag]), g["b_stack"], atol=3e-5)
+    xr, n_out = util.istft_mc(X, hop, flag_noDiv=1, window=win)
+    assert n_out == N
+    np.testing.assert_allclose(xr, g["b_xr"], atol=3e-6)
+    ds = audio_dataset.AudioDataset([x], params_stft={"N": N, "hop": hop, "nch": 1})
+    np.testing.assert_allclose(ds.reconstruct_x(0, mask=g["b_mask"]), g["b_xr_masked"], atol=3e-6)
+    with pytest.raises(NotImplementedError):
+        util.stft_mc(x, N, hop, np.ones(N, np.float32))
+
+
+def test_enhance_main_synthetic(tmp_path, capsys):
+    from drnmf_b200 import enhance
+    cfg = tmp_path / "params_unfolded_snmf_test.yaml"
+    cfg.write_text("K_layers: 2\nalph: 50.0\nlam1: 1.0\nr: 20\nparams_trainable: [log_D, log_alph]\n"
+                   "params_untied: [log_D, log_alph]\n")
+    dat = tmp_path / "params_data.yaml"
+    dat.write_text("maxlen: 500\nparams_stft: {N: 256, hop: 64, nch: 1}\n")
+    assert enhance.main(["-c", str(cfg), "-d", str(dat), "--synthetic", "3", "--seconds", "0.4"]) == 0
+    assert "mean SDR" in capsys.readouterr().out

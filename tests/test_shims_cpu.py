@@ -1,0 +1,58 @@
+"""CPU tests of the host-side mirrors of the reference interfaces (no GPU work)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from drnmf_b200 import custom_layers, enhance, synth
+
+
+def _const(W, alph, lam1, R, untie=False):
+    p = {"W": np.float32(W), "U1": np.eye(R).astype(np.float32), "Uk": np.zeros((R, R)).astype(np.float32),
+         "alph": np.float32(alph), "lam1": np.float32(lam1)}
+    if untie:
+        p["alph"] = p["alph"] * np.ones((R,), dtype=np.float32)
+    return p
+
+
+def test_build_alt_matches_reference_parameterisation():
+    """oracle.alt_params_init is pinned bit-for-bit against the reference's build_alt (oracle/pin_reference.py);
+    the shim must produce the same arrays under the reference's key names."""
+    F, R, K = 12, 6, 3
+    W = synth.dictionary(F, R)
+    alt, maps = enhance.build_alt(R, K, _const(W, 50., 1., R), params_untied=["log_D", "log_alph"])
+    ref = O.alt_params_init(W, 50., 1., K)
+    assert sorted(alt) == sorted(["log_D_%d" % k for k in range(K)] + ["log_alph_%d" % k for k in range(K)]
+                                 + ["log_lam1", "log_U1", "log_Uk"])
+    for k in range(K):
+        np.testing.assert_array_equal(alt["log_D_%d" % k], ref["log_D"][k])
+        np.testing.assert_array_equal(alt["log_alph_%d" % k], ref["log_alph"][k])
+    np.testing.assert_array_equal(alt["log_lam1"], ref["log_lam1"][0])
+    np.testing.assert_array_equal(alt["log_U1"], ref["log_U1"])
+    np.testing.assert_array_equal(alt["log_Uk"], ref["log_Uk"])
+    assert maps.labels_per_k["log_lam1"] == ["log_lam1"] * K and isinstance(maps, custom_layers.BuildAltMaps)
+    # tied: one shared array
+    alt_t, maps_t = enhance.build_alt(R, K, _const(W, 50., 1., R), params_untied=[])
+    assert sorted(alt_t) == ["log_D", "log_U1", "log_Uk", "log_alph", "log_lam1"]
+    assert maps_t.labels_per_k["log_D"] == ["log_D"] * K
+
+
+def test_trainable_weight_count_identity():
+    """notebook :121-126: K*F*2r + K + 2r counts log_D_k, log_alph_k and log_h0."""
+    F, r, K = 257, 100, 2
+    alt, _ = enhance.build_alt(2 * r, K, _const(np.ones((F, 2 * r)), 50., 1., 2 * r), ["log_D", "log_alph"])
+    n = sum(int(np.size(alt["log_D_%d" % k])) + int(np.size(alt["log_alph_%d" % k])) for k in range(K)) + 2 * r
+    assert n == 103002 == O.param_count_notebook(F, r, K)
+
+
+def test_layer_rejects_what_the_kernel_cannot_do():
+    with pytest.raises(NotImplementedError):
+        custom_layers.SimpleDeepRNN(8, activation="relu", K_layers=2, alt_params={}, maps_from_alt={"U": [lambda a: a]},
+                                    flag_connect_input_to_layers=True, flag_nonnegative=True, return_sequences=True)
+    _, maps = enhance.build_alt(4, 2, _const(np.ones((3, 4)), 5., 1., 4), [])
+    with pytest.raises(NotImplementedError):
+        custom_layers.SimpleDeepRNN(4, activation="tanh", K_layers=2, alt_params={}, maps_from_alt=maps,
+                                    flag_connect_input_to_layers=True, flag_nonnegative=True, return_sequences=True)
+    with pytest.raises(NotImplementedError):
+        custom_layers.DenseNonNegW(5, use_bias=True)
+    with pytest.raises(ValueError):
+        custom_layers.divide_A_by_AplusB([1, 2, 3])
