@@ -16,8 +16,15 @@ template <int EPI>
 __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
   float acc[4][4], acc2[4][4];
   const int m0 = blockIdx.y * SIMT_BM, n0 = blockIdx.x * SIMT_BN;
-  simt_tile_mainloop<EPI == EPI_RECON>(a.A_hi, a.lda, a.M, a.B_hi, a.B2_hi, a.ldb, a.N, a.Kd, m0, n0, acc, acc2);
+  const int nsplit = a.splits > 1 ? a.splits : 1;
+  const int kchunk = ((a.Kd + nsplit - 1) / nsplit + SIMT_BK - 1) / SIMT_BK * SIMT_BK;
+  const int kbeg = blockIdx.z * kchunk;
+  int klen = a.Kd - kbeg; if (klen > kchunk) klen = kchunk; if (klen < 0) klen = 0;
+  simt_tile_mainloop<EPI == EPI_RECON>(a.A_hi + kbeg, a.lda, a.M, a.B_hi + kbeg, EPI == EPI_RECON ? a.B2_hi + kbeg : nullptr,
+                                       a.ldb, a.N, klen, m0, n0, acc, acc2);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float* Cz = a.C + (size_t)blockIdx.z * a.split_stride;
+  float dsum = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -27,24 +34,42 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.N_valid) continue;
       if (EPI == EPI_STORE) {
-        a.C[(size_t)m * a.ldc + n] = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+        Cz[(size_t)m * a.ldc + n] = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
       } else if (EPI == EPI_GRAM) {
         float v = epi_gram_value(m, n, a.R_valid, acc[i][j]);
         a.C[(size_t)m * a.ldc + n] = v;
         a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(v);
-      } else {
+      } else if (EPI == EPI_RECON) {
         a.C[(size_t)m * a.ldc + n] = epi_irm_value(acc[i][j], acc2[i][j], a.square);
+      } else {
+        const float v = fmaxf(acc[i][j], a.flr);
+        a.C[(size_t)m * a.ldc + n] = v; a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(v);
+        a.CT[(size_t)n * a.ldct + m] = v; a.CT_lo[(size_t)n * a.ldct + m] = tf32_lo(v);
+        const float d = a.Vref[(size_t)m * a.ldv + n] - v;
+        dsum = fmaf(d, d, dsum);
       }
+    }
+  }
+  if (EPI == EPI_LAMBDA) {
+    __shared__ float red[SIMT_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < SIMT_THREADS / 32; ++w) t += (double)red[w];
+      a.div_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
   }
 }
 
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
-  dim3 grid((a.N + SIMT_BN - 1) / SIMT_BN, (a.M + SIMT_BM - 1) / SIMT_BM);
+  dim3 grid((a.N + SIMT_BN - 1) / SIMT_BN, (a.M + SIMT_BM - 1) / SIMT_BM, a.splits > 1 ? a.splits : 1);
   switch (epi) {
     case EPI_STORE: k_gemm_simt<EPI_STORE><<<grid, SIMT_THREADS, 0, st>>>(a); break;
     case EPI_GRAM:  k_gemm_simt<EPI_GRAM><<<grid, SIMT_THREADS, 0, st>>>(a); break;
     case EPI_RECON: k_gemm_simt<EPI_RECON><<<grid, SIMT_THREADS, 0, st>>>(a); break;
+    case EPI_LAMBDA: k_gemm_simt<EPI_LAMBDA><<<grid, SIMT_THREADS, 0, st>>>(a); break;
   }
   count_launch();
   DRNMF_CUDA(cudaGetLastError());
@@ -85,7 +110,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   // M-tiles are the fast grid dimension: the CTAs resident at any time share a few B (weight) tiles and sweep A,
   // which is the smaller operand and fits L2 -> each weight tile is fetched from HBM once.
   const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
-  const int num_kb = (a.Kd + TC_BK - 1) / TC_BK;
+  const int total_kb = (a.Kd + TC_BK - 1) / TC_BK;
+  const int nsplit = a.splits > 1 ? a.splits : 1;
+  const int kb_chunk = (total_kb + nsplit - 1) / nsplit;
+  const int kb0 = blockIdx.z * kb_chunk;
+  int num_kb = total_kb - kb0; if (num_kb > kb_chunk) num_kb = kb_chunk; if (num_kb < 0) num_kb = 0;
 
   if (warp == 0 && lane_id() == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
@@ -109,7 +138,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(dev_error, 101); break; }
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        const int kc = kb * TC_BK;
+        const int kc = (kb0 + kb) * TC_BK;
         tma_load_2d(st + 0 * TC_TILE_BYTES, &tmA_hi, &full[s], kc, m0);
         tma_load_2d(st + 1 * TC_TILE_BYTES, &tmA_lo, &full[s], kc, m0);
         tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[s], kc, n0);
@@ -121,9 +150,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane_id() == 0) {
+    // ===== MMA issuer: the warp runs the loop convergently (uniform datapath), one elected lane issues =====
+    {
       const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+      const bool leader = elect_one();
       bool ok = true;
       for (int kb = 0; kb < num_kb && ok; ++kb) {
         const int s = kb % Cfg::STAGES;
@@ -139,25 +169,32 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const uint64_t b_hi = umma_desc_k128(st + 2 * TC_TILE_BYTES + koff);
           const uint64_t b_lo = umma_desc_k128(st + 3 * TC_TILE_BYTES + koff);
           const bool first = (kb == 0 && ks == 0);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc, !first);
-          umma_tf32(tmem_base, a_hi, b_lo, idesc, true);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, true);
+          if (leader) {
+            umma_tf32(tmem_base, a_lo, b_hi, idesc, !first);
+            umma_tf32(tmem_base, a_hi, b_lo, idesc, true);
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, true);
+          }
           if (Cfg::DUAL) {
             const uint64_t c_hi = umma_desc_k128(st + 4 * TC_TILE_BYTES + koff);
             const uint64_t c_lo = umma_desc_k128(st + 5 * TC_TILE_BYTES + koff);
-            umma_tf32(tmem_base + TC_BN, a_lo, c_hi, idesc, !first);
-            umma_tf32(tmem_base + TC_BN, a_hi, c_lo, idesc, true);
-            umma_tf32(tmem_base + TC_BN, a_hi, c_hi, idesc, true);
+            if (leader) {
+              umma_tf32(tmem_base + TC_BN, a_lo, c_hi, idesc, !first);
+              umma_tf32(tmem_base + TC_BN, a_hi, c_lo, idesc, true);
+              umma_tf32(tmem_base + TC_BN, a_hi, c_hi, idesc, true);
+            }
           }
         }
-        tc_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
+        if (leader) tc_commit(&empty[s]);     // frees the smem stage when these MMAs retire
+        __syncwarp();
       }
-      tc_commit(acc_full);                    // accumulator complete
+      if (leader) tc_commit(acc_full);        // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int m = m0 + q * 32 + lane_id();
+    float dsum = 0.f;
     bool ok = mbar_wait(acc_full, 0);
     if (!ok && lane_id() == 0) atomicExch(dev_error, 103);
     tc_fence_after();
@@ -173,7 +210,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         if (m < a.M_valid) {
           if (EPI == EPI_STORE) {
             if (n < a.N_valid) {
-              float4* dst = reinterpret_cast<float4*>(a.C + (size_t)m * a.ldc + n);
+              float4* dst = reinterpret_cast<float4*>(a.C + (size_t)blockIdx.z * a.split_stride + (size_t)m * a.ldc + n);
               if (a.bias) {
                 const float4* bb = reinterpret_cast<const float4*>(a.bias + n);
 #pragma unroll
@@ -198,13 +235,47 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                 d2[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
               }
             }
-          } else {
+          } else if (EPI == EPI_RECON) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (n + i < a.N_valid) a.C[(size_t)m * a.ldc + n + i] = epi_irm_value(v[i], v2[i], a.square);
+          } else {
+            // sparse-NMF reconstruction: Lambda = max(W H, flr) in both layouts (+ tf32 remainders) and the squared
+            // error against V.  Row-major: 64 contiguous bytes per thread; transposed: lanes = consecutive rows.
+            if (n < a.N_valid) {
+              float hi[16], lo[16], vr[16];
+              const float4* vp = reinterpret_cast<const float4*>(a.Vref + (size_t)m * a.ldv + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { const float4 t4 = __ldg(vp + i); vr[4 * i] = t4.x; vr[4 * i + 1] = t4.y; vr[4 * i + 2] = t4.z; vr[4 * i + 3] = t4.w; }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool in = (n + i < a.N_valid);
+                hi[i] = in ? fmaxf(v[i], a.flr) : 0.f;
+                lo[i] = tf32_lo(hi[i]);
+                if (in) { const float d = vr[i] - hi[i]; dsum = fmaf(d, d, dsum); }
+              }
+              float4* d1 = reinterpret_cast<float4*>(a.C + (size_t)m * a.ldc + n);
+              float4* d2 = reinterpret_cast<float4*>(a.C_lo + (size_t)m * a.ldc + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                d1[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                d2[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n + i < a.N_valid) { a.CT[(size_t)(n + i) * a.ldct + m] = hi[i]; a.CT_lo[(size_t)(n + i) * a.ldct + m] = lo[i]; }
+            }
           }
         }
       }
+    }
+    if (EPI == EPI_LAMBDA) {
+      float* red = reinterpret_cast<float*>(tmem_slot + 2);
+      for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+      if (lane_id() == 0) red[q] = dsum;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane_id() == 0)
+        a.div_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = (double)red[0] + (double)red[1] + (double)red[2] + (double)red[3];
     }
     tc_fence_before();
   }
@@ -231,7 +302,7 @@ static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
     DRNMF_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((a.M + TC_BM - 1) / TC_BM, (a.N + TC_BN - 1) / TC_BN);
+  dim3 grid((a.M + TC_BM - 1) / TC_BM, (a.N + TC_BN - 1) / TC_BN, a.splits > 1 ? a.splits : 1);
   k_gemm_tc<EPI><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo, a, dev_error);
   count_launch();
   DRNMF_CUDA(cudaGetLastError());
@@ -242,7 +313,8 @@ static int* g_gemm_dev_error = nullptr;   // lazily allocated error word for han
 
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
   DRNMF_CHECK(a.lda % 4 == 0 && a.ldb % 4 == 0, "tcgen05 GEMM needs row strides that are multiples of 4 floats");
-  if (epi != EPI_RECON) DRNMF_CHECK(a.ldc % 4 == 0 && a.N_valid % 16 == 0, "tcgen05 GEMM store needs ldc%%4==0, N%%16==0");
+  if (epi == EPI_STORE || epi == EPI_GRAM) DRNMF_CHECK(a.ldc % 4 == 0 && a.N_valid % 16 == 0, "tcgen05 GEMM store needs ldc%%4==0, N%%16==0");
+  if (epi == EPI_LAMBDA) DRNMF_CHECK(a.ldc % 4 == 0 && a.ldv % 4 == 0, "EPI_LAMBDA needs ldc%%4==0 and ldv%%4==0");
   if (!g_gemm_dev_error) {
     DRNMF_CUDA(cudaMalloc(&g_gemm_dev_error, sizeof(int)));
     DRNMF_CUDA(cudaMemset(g_gemm_dev_error, 0, sizeof(int)));
@@ -251,6 +323,7 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
     case EPI_STORE: return launch_tc_impl<EPI_STORE>(a, st, g_gemm_dev_error);
     case EPI_GRAM:  return launch_tc_impl<EPI_GRAM>(a, st, g_gemm_dev_error);
     case EPI_RECON: return launch_tc_impl<EPI_RECON>(a, st, g_gemm_dev_error);
+    case EPI_LAMBDA: return launch_tc_impl<EPI_LAMBDA>(a, st, g_gemm_dev_error);
   }
   return DRNMF_ERR_INVALID;
 }

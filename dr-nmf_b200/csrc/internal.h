@@ -51,7 +51,7 @@ int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const f
 int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st);
 
 // ---- gemm: C = A (M x K, K-major) . B^T (N x K, K-major) with a fused epilogue --------------------
-enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2 };
+enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2, EPI_LAMBDA = 3 };
 struct GemmArgs {
   const float *A_hi, *A_lo; int lda;     // M x Kd
   const float *B_hi, *B_lo; int ldb;     // N x Kd
@@ -61,6 +61,14 @@ struct GemmArgs {
   int R_valid, N_valid, M_valid;         // masks for the epilogues
   int square;                            // EPI_RECON: transform_before_irm == 'square'
   const float* bias;                     // EPI_STORE: optional per-column bias added in the epilogue (length N)
+  int splits;                            // split-K: grid.z partial products, split z written at C + z*split_stride (0/1 = off)
+  size_t split_stride;
+  // EPI_LAMBDA (sparse NMF): C/C_lo = max(acc, flr) (M x ldc), CT/CT_lo = its transpose (N x ldct), and the squared
+  // error against Vref (M x ldv) summed per CTA into div_partials[blockIdx.y * gridDim.x + blockIdx.x]
+  float *CT, *CT_lo; int ldct;
+  const float* Vref; int ldv;
+  double* div_partials;
+  float flr;
 };
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
@@ -76,6 +84,11 @@ int launch_stft_mag(const float* audio, const int64_t* offs, const int32_t* lens
 int launch_mask_istft(const float* stack, const float* mask, const int64_t* fidx, const int64_t* out_offs, int n_utt,
                       int max_frames, int N, int hop, int64_t total_frames, float* frames_tmp, float* out_audio,
                       cudaStream_t st);
+// ---- snmf.cu ---------------------------------------------------------------------------------------
+size_t snmf_workspace_bytes(int F, int n, int R);
+int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
+               int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
+               double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st);
 int launch_init_state(const drnmf_handle* h, FwdWorkspace& w, cudaStream_t st);
 int gemm_device_error(cudaStream_t st);
 const char* last_error();

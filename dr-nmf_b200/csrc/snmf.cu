@@ -1,0 +1,341 @@
+// "Well-done" sparse NMF, Euclidean branch (sparseNMF/sparse_nmf_gpu.m:163-298, beta = 2) as fused GEMM + elementwise
+// kernels.  Per iteration:
+//   H <- H .* (W^T V) ./ max(W^T L + mu, flr)          (:217-221)      two (n x F).(F x R) GEMMs + k_mu_h
+//   L <- max(W H, flr)                                  (:228)          GEMM with the EPI_LAMBDA epilogue
+//   W <- W .* (V H^T + W .* colsum(L H^T .* W)) ./ max(L H^T + W .* colsum(V H^T .* W), flr)   (:243-249)
+//                                                                       two split-K (F x n).(n x R) GEMMs + k_mu_w
+//   W <- W ./ colnorm(W) ; L <- max(W H, flr)           (:262-263)
+//   div = |V - L|_F^2 (no 1/2) ; cost = div + mu * sum(H)   (:271,278) ; stop when |d cost| / cost_prev < conv_eps (:288-296)
+// Both operand layouts of every matrix are kept (frame-major for the contractions over F and R, feature-major for the
+// contractions over frames) together with their tf32 remainders; the epilogues write all of them.
+#include "internal.h"
+
+#include <cmath>
+#include <cstdio>
+
+namespace drnmf {
+
+struct SnmfWs {
+  // K-major operands (hi, lo).  Fk = ceil32(F), Rk = ceil32(R), nk = ceil128(n)
+  float *Wm_hi, *Wm_lo;   // F x Rk      W          (B operand of L = H W^T)
+  float *WT_hi, *WT_lo;   // R x Fk      W^T        (B operand of W^T L, W^T V)
+  float *Ht_hi, *Ht_lo;   // nk x Rk     H^T        (A operand of L)
+  float *Hm_hi, *Hm_lo;   // R x nk      H          (B operand of V H^T, L H^T)
+  float *Vt_hi, *Vt_lo;   // nk x Fk     V^T
+  float *Vm_hi, *Vm_lo;   // F x nk      V
+  float *Lt_hi, *Lt_lo;   // nk x Fk     L^T
+  float *Lm_hi, *Lm_lo;   // F x nk      L
+  float *dph, *dmh;       // nk x Rk     (W^T L)^T , (W^T V)^T
+  float *VHp, *LHp;       // splits x F x Rk   split-K partials of V H^T, L H^T
+  double *div_part, *hsum_part, *scal;   // per-CTA partial sums; scal[0] = div, scal[1] = mu * sum(H)
+  float* wnorm;           // Rk
+  size_t bytes;
+  int Fk, Rk, nk, splits, n_div_part, n_h_part;
+};
+
+static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+static SnmfWs carve_snmf(int F, int n, int R, void* base) {
+  SnmfWs w;
+  w.Fk = round_up(F, 32); w.Rk = round_up(R, 32); w.nk = round_up(n, 128);
+  int total_kb = w.nk / 32;
+  w.splits = total_kb >= 64 ? 16 : (total_kb >= 8 ? 4 : 1);
+  uint8_t* p = (uint8_t*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* q = p ? p + off : nullptr; off += al256(bytes); return q; };
+  const size_t F_ = F, R_ = R, Fk = w.Fk, Rk = w.Rk, nk = w.nk;
+  w.Wm_hi = (float*)take(F_ * Rk * 4); w.Wm_lo = (float*)take(F_ * Rk * 4);
+  w.WT_hi = (float*)take(R_ * Fk * 4); w.WT_lo = (float*)take(R_ * Fk * 4);
+  w.Ht_hi = (float*)take(nk * Rk * 4); w.Ht_lo = (float*)take(nk * Rk * 4);
+  w.Hm_hi = (float*)take(R_ * nk * 4); w.Hm_lo = (float*)take(R_ * nk * 4);
+  w.Vt_hi = (float*)take(nk * Fk * 4); w.Vt_lo = (float*)take(nk * Fk * 4);
+  w.Vm_hi = (float*)take(F_ * nk * 4); w.Vm_lo = (float*)take(F_ * nk * 4);
+  w.Lt_hi = (float*)take(nk * Fk * 4); w.Lt_lo = (float*)take(nk * Fk * 4);
+  w.Lm_hi = (float*)take(F_ * nk * 4); w.Lm_lo = (float*)take(F_ * nk * 4);
+  w.dph = (float*)take(nk * Rk * 4); w.dmh = (float*)take(nk * Rk * 4);
+  w.VHp = (float*)take((size_t)w.splits * F_ * Rk * 4); w.LHp = (float*)take((size_t)w.splits * F_ * Rk * 4);
+  w.n_div_part = (int)((nk / 64) * ((Fk + 63) / 64 + 1));            // upper bound over both GEMM tilings
+  w.n_h_part = (int)((nk + 31) / 32 * ((Rk + 31) / 32));
+  w.div_part = (double*)take((size_t)w.n_div_part * 8);
+  w.hsum_part = (double*)take((size_t)w.n_h_part * 8);
+  w.scal = (double*)take(64);
+  w.wnorm = (float*)take(Rk * 4);
+  w.bytes = off;
+  return w;
+}
+
+// ---- layout kernels (32x32 smem-tile transposes, coalesced on both sides) -------------------------------
+// src (rows x cols, ld_src) -> dst_rm (rows x ld_rm, zero padded), dst_tr (cols x ld_tr, zero padded), with remainders
+__global__ void k_split_both(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ rm_hi,
+                             float* __restrict__ rm_lo, int rm_rows, int ld_rm, float* __restrict__ tr_hi,
+                             float* __restrict__ tr_lo, int tr_rows, int ld_tr, const float* __restrict__ row_scale,
+                             const float* __restrict__ col_scale, int scale_is_div) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int r = r0 + y, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = src[(size_t)r * ld_src + c];
+      if (row_scale) v = scale_is_div ? v / row_scale[r] : v * row_scale[r];
+      if (col_scale) v = scale_is_div ? v / col_scale[c] : v * col_scale[c];
+    }
+    tile[y][threadIdx.x] = v;
+    if (rm_hi && r < rm_rows && c < ld_rm) { rm_hi[(size_t)r * ld_rm + c] = v; rm_lo[(size_t)r * ld_rm + c] = tf32_lo(v); }
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int c = c0 + y, r = r0 + threadIdx.x;
+    if (tr_hi && c < tr_rows && r < ld_tr) {
+      const float v = tile[threadIdx.x][y];
+      tr_hi[(size_t)c * ld_tr + r] = v; tr_lo[(size_t)c * ld_tr + r] = tf32_lo(v);
+    }
+  }
+}
+
+// column l2 norms of a row-major (rows x cols) matrix: grid ceil(cols/32), block (32, 8)
+__global__ void k_colnorm_rm(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ norm) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = threadIdx.y; r < rows; r += 8) { const float v = src[(size_t)r * ld + c]; s = fmaf(v, v, s); }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    norm[c] = sqrtf(t);
+  }
+}
+
+// H update on the frame-major layout: Ht[n][r] *= dmh / max(dph + mu, flr) for updated rows r; writes both layouts and
+// remainders, and the per-block partial of sum(H) (all entries, as in cost = div + sum(sparsity .* h)).
+// grid (Rk/32, nk/32), block (32, 8)
+__global__ void k_mu_h(float* __restrict__ Ht_hi, float* __restrict__ Ht_lo, float* __restrict__ Hm_hi,
+                       float* __restrict__ Hm_lo, const float* __restrict__ dph, const float* __restrict__ dmh, int n,
+                       int R, int Rk, int nk, float mu, float flr, const uint8_t* __restrict__ h_update, int do_update,
+                       double* __restrict__ hsum_part) {
+  __shared__ float tile[32][33];
+  __shared__ float red[8];
+  const int r0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  float local = 0.f;
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int fr = n0 + y, r = r0 + threadIdx.x;
+    float h = 0.f;
+    if (fr < n && r < R) {
+      const size_t o = (size_t)fr * Rk + r;
+      h = Ht_hi[o];
+      if (do_update && (!h_update || h_update[r])) h = h * dmh[o] / fmaxf(dph[o] + mu, flr);
+      Ht_hi[o] = h; Ht_lo[o] = tf32_lo(h);
+      local += h;
+    }
+    tile[y][threadIdx.x] = h;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int r = r0 + y, fr = n0 + threadIdx.x;
+    if (r < R && fr < nk) {
+      const float h = tile[threadIdx.x][y];
+      Hm_hi[(size_t)r * nk + fr] = h; Hm_lo[(size_t)r * nk + fr] = tf32_lo(h);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if (threadIdx.x == 0) red[threadIdx.y] = local;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    double t = 0.0;
+    for (int y = 0; y < 8; ++y) t += (double)red[y];
+    hsum_part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// W update for a block of 32 columns (all F rows): reduce split-K partials in split order, column sums, multiplicative
+// update of the updated columns, renormalisation of every column (:262), both layouts + remainders.
+// grid ceil(R/32), block (32, 8).  W is read from / written to Wm (F x Rk).
+__global__ void k_mu_w(float* __restrict__ Wm_hi, float* __restrict__ Wm_lo, float* __restrict__ WT_hi,
+                       float* __restrict__ WT_lo, float* __restrict__ VHp, float* __restrict__ LHp, int splits, int F, int R,
+                       int Rk, int Fk, float flr, const uint8_t* __restrict__ w_update) {
+  __shared__ float red_v[8][33], red_l[8][33];
+  __shared__ float sv[32], sl[32], nrm[32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t sstride = (size_t)F * Rk;
+  const bool upd = (c < R) && (!w_update || w_update[c]);
+  // pass 1: VH, LH = sum over splits (stored back into split 0), column sums of VH.*W and LH.*W
+  float a_v = 0.f, a_l = 0.f;
+  if (c < R)
+    for (int f = threadIdx.y; f < F; f += 8) {
+      const size_t o = (size_t)f * Rk + c;
+      float vh = 0.f, lh = 0.f;
+      for (int s = 0; s < splits; ++s) { vh += VHp[s * sstride + o]; lh += LHp[s * sstride + o]; }
+      VHp[o] = vh; LHp[o] = lh;
+      const float w = Wm_hi[o];
+      a_v = fmaf(vh, w, a_v); a_l = fmaf(lh, w, a_l);
+    }
+  red_v[threadIdx.y][threadIdx.x] = a_v; red_l[threadIdx.y][threadIdx.x] = a_l;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float tv = 0.f, tl = 0.f;
+    for (int y = 0; y < 8; ++y) { tv += red_v[y][threadIdx.x]; tl += red_l[y][threadIdx.x]; }
+    sv[threadIdx.x] = tv; sl[threadIdx.x] = tl;
+  }
+  __syncthreads();
+  // pass 2: multiplicative update, accumulate the new column norm
+  float a_n = 0.f;
+  if (c < R)
+    for (int f = threadIdx.y; f < F; f += 8) {
+      const size_t o = (size_t)f * Rk + c;
+      float w = Wm_hi[o];
+      if (upd) {
+        const float dpw = fmaxf(LHp[o] + sv[threadIdx.x] * w, flr);
+        const float dmw = VHp[o] + sl[threadIdx.x] * w;
+        w = w * dmw / dpw;
+        Wm_hi[o] = w;
+      }
+      a_n = fmaf(w, w, a_n);
+    }
+  red_v[threadIdx.y][threadIdx.x] = a_n;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+    for (int y = 0; y < 8; ++y) t += red_v[y][threadIdx.x];
+    nrm[threadIdx.x] = sqrtf(t);
+  }
+  __syncthreads();
+  // pass 3: normalise, write both layouts and remainders
+  if (c < Rk)
+    for (int f = threadIdx.y; f < F; f += 8) {
+      const size_t o = (size_t)f * Rk + c;
+      const float w = (c < R) ? Wm_hi[o] / nrm[threadIdx.x] : 0.f;
+      Wm_hi[o] = w; Wm_lo[o] = tf32_lo(w);
+      if (c < R) { WT_hi[(size_t)c * Fk + f] = w; WT_lo[(size_t)c * Fk + f] = tf32_lo(w); }
+    }
+}
+
+// scal[0] = sum(div partials), scal[1] = mu * sum(hsum partials)   (single block, fixed order)
+__global__ void k_mu_cost(const double* __restrict__ div_part, int n_div, const double* __restrict__ hsum_part, int n_h,
+                          double mu, double* __restrict__ scal) {
+  __shared__ double red[256];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n_div; i += 256) a += div_part[i];
+  for (int i = threadIdx.x; i < n_h; i += 256) b += hsum_part[i];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) scal[0] = red[0];
+  __syncthreads();
+  red[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) scal[1] = mu * red[0];
+}
+
+// copy back: W (F x R) from Wm, H (R x n) from Hm
+__global__ void k_unpad(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ dst) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (size_t)rows * cols) dst[idx] = src[(idx / cols) * ld_src + idx % cols];
+}
+
+static int run_gemm_impl(bool simt, GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
+  return simt ? launch_gemm_simt(epi, a, st) : launch_gemm_tc(epi, a, st);
+}
+
+size_t snmf_workspace_bytes(int F, int n, int R) { return carve_snmf(F, n, R, nullptr).bytes; }
+
+int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
+               int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
+               double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st) {
+  SnmfWs w = carve_snmf(F, n, R, ws);
+  if (ws_bytes < w.bytes) { set_error("snmf workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
+  const int Fk = w.Fk, Rk = w.Rk, nk = w.nk;
+  const float flr = 1e-9f;
+  const dim3 tb(32, 8);
+  // every padded buffer starts from zero (padding rows / columns are operands of the contractions)
+  DRNMF_CUDA(cudaMemsetAsync(ws, 0, w.bytes, st));
+  // ---- init (:163-173): normalise the columns of W, rescale the rows of H, L = max(W H, flr) ----
+  k_colnorm_rm<<<(R + 31) / 32, tb, 0, st>>>(W, F, R, R, w.wnorm);
+  k_split_both<<<dim3((R + 31) / 32, (F + 31) / 32), tb, 0, st>>>(W, F, R, R, w.Wm_hi, w.Wm_lo, F, Rk, w.WT_hi, w.WT_lo, R, Fk,
+                                                                  nullptr, w.wnorm, 1);
+  k_split_both<<<dim3((n + 31) / 32, (R + 31) / 32), tb, 0, st>>>(H, R, n, n, w.Hm_hi, w.Hm_lo, R, nk, w.Ht_hi, w.Ht_lo, nk, Rk,
+                                                                  w.wnorm, nullptr, 0);
+  k_split_both<<<dim3((n + 31) / 32, (F + 31) / 32), tb, 0, st>>>(V, F, n, n, w.Vm_hi, w.Vm_lo, F, nk, w.Vt_hi, w.Vt_lo, nk, Fk,
+                                                                  nullptr, nullptr, 0);
+  count_launch(4);
+  DRNMF_CUDA(cudaGetLastError());
+
+  auto lambda_gemm = [&]() {       // L = max(H^T-rows . W-rows, flr): (n x R).(F x R)^T, all layouts + squared error
+    GemmArgs a{};
+    a.A_hi = w.Ht_hi; a.A_lo = w.Ht_lo; a.lda = Rk;
+    a.B_hi = w.Wm_hi; a.B_lo = w.Wm_lo; a.ldb = Rk;
+    a.M = n; a.N = F; a.Kd = Rk; a.M_valid = n; a.N_valid = F;
+    a.C = w.Lt_hi; a.C_lo = w.Lt_lo; a.ldc = Fk; a.CT = w.Lm_hi; a.CT_lo = w.Lm_lo; a.ldct = nk;
+    a.Vref = w.Vt_hi; a.ldv = Fk; a.div_partials = w.div_part; a.flr = flr;
+    return run_gemm_impl(simt, EPI_LAMBDA, a, st);
+  };
+  auto proj_gemm = [&](const float* A_hi, const float* A_lo, float* out) {   // (n x F).(R x F)^T -> n x Rk
+    GemmArgs a{};
+    a.A_hi = A_hi; a.A_lo = A_lo; a.lda = Fk;
+    a.B_hi = w.WT_hi; a.B_lo = w.WT_lo; a.ldb = Fk;
+    a.M = n; a.N = R; a.Kd = Fk; a.M_valid = n; a.N_valid = Rk;
+    a.C = out; a.ldc = Rk;
+    return run_gemm_impl(simt, EPI_STORE, a, st);
+  };
+  auto corr_gemm = [&](const float* A_hi, const float* A_lo, float* out) {   // (F x n).(R x n)^T -> splits x F x Rk
+    GemmArgs a{};
+    a.A_hi = A_hi; a.A_lo = A_lo; a.lda = nk;
+    a.B_hi = w.Hm_hi; a.B_lo = w.Hm_lo; a.ldb = nk;
+    a.M = F; a.N = R; a.Kd = nk; a.M_valid = F; a.N_valid = Rk;
+    a.C = out; a.ldc = Rk; a.splits = w.splits; a.split_stride = (size_t)F * Rk;
+    return run_gemm_impl(simt, EPI_STORE, a, st);
+  };
+  // number of div partials the lambda GEMM writes depends on the tiling of the implementation in use
+  const int tile = simt ? 64 : 128;
+  const int n_div = ((n + tile - 1) / tile) * ((F + tile - 1) / tile);
+  const dim3 gh(Rk / 32, nk / 32);
+  const int n_h = gh.x * gh.y;
+
+  int rc;
+  if ((rc = lambda_gemm())) return rc;
+  if (!any_w_update && any_h_update) { if ((rc = proj_gemm(w.Vt_hi, w.Vt_lo, w.dmh))) return rc; }   // W^T V is constant
+  double last_cost = INFINITY;
+  int it = 0;
+  for (it = 1; it <= max_iter; ++it) {
+    if (any_h_update) {
+      if ((rc = proj_gemm(w.Lt_hi, w.Lt_lo, w.dph))) return rc;
+      if (any_w_update) { if ((rc = proj_gemm(w.Vt_hi, w.Vt_lo, w.dmh))) return rc; }
+      k_mu_h<<<gh, tb, 0, st>>>(w.Ht_hi, w.Ht_lo, w.Hm_hi, w.Hm_lo, w.dph, w.dmh, n, R, Rk, nk, sparsity, flr, h_update, 1, w.hsum_part);
+      count_launch();
+      if ((rc = lambda_gemm())) return rc;
+    } else if (it == 1) {   // sum(H) is constant: compute it once with a no-op update mask
+      k_mu_h<<<gh, tb, 0, st>>>(w.Ht_hi, w.Ht_lo, w.Hm_hi, w.Hm_lo, w.dph, w.dmh, n, R, Rk, nk, sparsity, flr, h_update, 0, w.hsum_part);
+      count_launch();
+    }
+    if (any_w_update) {
+      if ((rc = corr_gemm(w.Vm_hi, w.Vm_lo, w.VHp))) return rc;
+      if ((rc = corr_gemm(w.Lm_hi, w.Lm_lo, w.LHp))) return rc;
+      k_mu_w<<<(Rk + 31) / 32, tb, 0, st>>>(w.Wm_hi, w.Wm_lo, w.WT_hi, w.WT_lo, w.VHp, w.LHp, w.splits, F, R, Rk, Fk, flr, w_update);
+      count_launch();
+      if ((rc = lambda_gemm())) return rc;
+    }
+    k_mu_cost<<<1, 256, 0, st>>>(w.div_part, n_div, w.hsum_part, n_h, (double)sparsity, w.scal);
+    count_launch();
+    double sc[2];
+    DRNMF_CUDA(cudaMemcpyAsync(sc, w.scal, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    DRNMF_CUDA(cudaStreamSynchronize(st));
+    const double div = sc[0], cost = sc[0] + sc[1];
+    div_host[it - 1] = div; cost_host[it - 1] = cost;
+    if (it > 1 && conv_eps > 0) {
+      const double e = fabs(cost - last_cost) / last_cost;
+      if (e < conv_eps) { ++it; break; }
+    }
+    last_cost = cost;
+  }
+  *iters_host = it - 1;
+  k_unpad<<<(unsigned)(((size_t)F * R + 255) / 256), 256, 0, st>>>(w.Wm_hi, F, R, Rk, W);
+  k_unpad<<<(unsigned)(((size_t)R * n + 255) / 256), 256, 0, st>>>(w.Hm_hi, R, n, nk, H);
+  count_launch(2);
+  DRNMF_CUDA(cudaGetLastError());
+  return DRNMF_OK;
+}
+
+}  // namespace drnmf

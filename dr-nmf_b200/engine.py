@@ -257,3 +257,43 @@ def mask_istft(stack, mask, fidx, N, hop):
                                     int(counts.max()) if n_utt else 0, N, hop, total, _ptr(out),
                                     C.c_void_p(ws.data_ptr() + off), nb, _stream()))
     return [out[int(out_offs[u]):int(out_offs[u + 1])] for u in range(n_utt)]
+
+
+# ---- sparse NMF multiplicative updates -------------------------------------------------------------
+def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_update=None, impl=None):
+    """V (F,n), W (F,R), H (R,n): float32 CUDA tensors (W and H are updated IN PLACE).  w_update / h_update: boolean
+    arrays of length R (None = all).  Returns (cost, div) numpy arrays truncated at convergence
+    (sparse_nmf_gpu.m:288-296).  Replaces the MATLAB subprocess of snmf.py:88-113."""
+    _require_cuda()
+    lib = _lib.load()
+    for t in (V, W, H):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError("V, W, H must be contiguous float32 CUDA tensors")
+    F, n = V.shape
+    R = W.shape[1]
+    if tuple(W.shape) != (F, R) or tuple(H.shape) != (R, n):
+        raise ValueError("shape mismatch: V %s W %s H %s" % (tuple(V.shape), tuple(W.shape), tuple(H.shape)))
+    max_iter = int(max_iter)
+    cost = np.zeros(max_iter, np.float64)
+    div = np.zeros(max_iter, np.float64)
+    iters = C.c_int(0)
+
+    def mask(m):
+        if m is None:
+            return None, C.c_void_p(0)
+        a = np.ascontiguousarray(np.asarray(m).astype(bool).ravel().astype(np.uint8))
+        if a.size != R:
+            raise ValueError("update mask must have R entries")
+        return a, C.c_void_p(a.ctypes.data)
+
+    wm, wp = mask(w_update)
+    hm, hp = mask(h_update)
+    nb = lib.drnmf_snmf_workspace_bytes(F, n, R)
+    ws = torch.empty(nb + 256, dtype=torch.uint8, device=V.device)
+    off = (-ws.data_ptr()) % 256
+    flags = _lib.IMPL_SIMT if impl == "simt" else 0
+    _lib.check(lib.drnmf_snmf_mu_ed(F, n, R, _ptr(V), _ptr(W), _ptr(H), wp, hp, float(sparsity), max_iter, float(conv_eps),
+                                    C.c_void_p(cost.ctypes.data), C.c_void_p(div.ctypes.data), C.byref(iters), flags,
+                                    C.c_void_p(ws.data_ptr() + off), nb, _stream()))
+    k = iters.value
+    return cost[:k].copy(), div[:k].copy()

@@ -118,6 +118,17 @@ DRNMF_API int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const flo
                        size_t ws_bytes, void* stream);
 DRNMF_API size_t drnmf_enhance_workspace_bytes(const drnmf_handle* h, int B, int T, int N, int hop);
 
+/* ---- sparse NMF multiplicative updates, Euclidean (sparseNMF/sparse_nmf_gpu.m:163-298; snmf.py:88-113) -----
+ * Replaces the MATLAB subprocess of sparse_nmf_matlab_on_chunk: V (F,n), W (F,R) in/out, H (R,n) in/out, row-major
+ * device arrays; w_update_host / h_update_host: HOST byte masks of length R (NULL = update all; :150-155);
+ * cost_host / div_host: host arrays of max_iter doubles (objective.cost/.div, :271-281); *iters_host = iterations
+ * run (convergence test of :288-296).  W's columns are normalised and H rescaled on entry (:163-166).
+ * flags: DRNMF_IMPL_TCGEN05 / DRNMF_IMPL_SIMT. */
+DRNMF_API int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update_host,
+                     const uint8_t* h_update_host, float sparsity, int max_iter, float conv_eps, double* cost_host,
+                     double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream);
+DRNMF_API size_t drnmf_snmf_workspace_bytes(int F, int n, int R);
+
 #ifdef __cplusplus
 }
 #endif

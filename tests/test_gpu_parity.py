@@ -289,3 +289,65 @@ def test_enhance_main_synthetic(tmp_path, capsys):
     dat.write_text("maxlen: 500\nparams_stft: {N: 256, hop: 64, nch: 1}\n")
     assert enhance.main(["-c", str(cfg), "-d", str(dat), "--synthetic", "3", "--seconds", "0.4"]) == 0
     assert "mean SDR" in capsys.readouterr().out
+
+
+# ---- sparse NMF multiplicative updates (sparse_nmf_gpu.m, ED branch) -----------------------------------------
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("case", [dict(F=33, n=200, R=12, it=25, partial=False), dict(F=65, n=333, R=40, it=15, partial=True)])
+def test_snmf_mu_ed_vs_oracle(case, impl):
+    F, n, R, iters = case["F"], case["n"], case["R"], case["it"]
+    rng = np.random.default_rng(2016 + F)
+    V = (np.abs(rng.standard_normal((F, n))) * 2).astype(np.float32)
+    W0 = (np.abs(rng.standard_normal((F, R))) + 0.1).astype(np.float32)
+    H0 = (np.abs(rng.standard_normal((R, n))) + 0.1).astype(np.float32)
+    prm = {"cf": "ed", "sparsity": 0.7, "max_iter": iters, "conv_eps": 0.0, "r": R, "init_w": W0, "init_h": H0}
+    wu = None
+    if case["partial"]:
+        wu = np.arange(R) >= R // 2                 # first half frozen (train_snmf stage 2, enhance.py:110-116)
+        prm["w_update_ind"] = wu
+    Wo, Ho, obj = O.sparse_nmf_ed(V, prm, dtype=np.float64)
+    Vd, Wd, Hd = (torch.as_tensor(a, device="cuda") for a in (V, W0.copy(), H0.copy()))
+    cost, div = engine.snmf_mu_ed(Vd, Wd, Hd, 0.7, iters, 0.0, w_update=wu, impl=None if impl == "tc" else "simt")
+    assert len(cost) == iters
+    assert max(rel_err(Wd.cpu().numpy(), Wo)) < TOL, rel_err(Wd.cpu().numpy(), Wo)
+    assert max(rel_err(Hd.cpu().numpy(), Ho)) < TOL, rel_err(Hd.cpu().numpy(), Ho)
+    np.testing.assert_allclose(cost, obj["cost"], rtol=2e-5)
+    np.testing.assert_allclose(div, obj["div"], rtol=2e-5)
+    # properties of the algorithm: nonneg, unit-l2 columns, monotone cost when everything is updated
+    Wn = Wd.cpu().numpy()
+    assert np.all(Wn >= 0) and np.all(Hd.cpu().numpy() >= 0)
+    np.testing.assert_allclose(np.sqrt((Wn.astype(np.float64) ** 2).sum(0)), 1.0, rtol=1e-5)
+    if not case["partial"]:
+        assert np.all(np.diff(cost) <= 1e-6 * cost[:-1])
+
+
+def test_snmf_inference_mode_and_convergence():
+    """W frozen (enhance.py:838-845): only H moves; conv_eps stops early exactly like sparse_nmf_gpu.m:288-296."""
+    F, n, R = 40, 150, 16
+    rng = np.random.default_rng(5)
+    V = np.abs(rng.standard_normal((F, n))).astype(np.float32)
+    W0 = (np.abs(rng.standard_normal((F, R))) + 0.1).astype(np.float32)
+    prm = {"cf": "ed", "sparsity": 0.2, "max_iter": 200, "conv_eps": 1e-3, "r": R, "init_w": W0, "init_h": "ones",
+           "w_update_ind": np.zeros(R, bool)}
+    Wo, Ho, obj = O.sparse_nmf_ed(V, prm, dtype=np.float64)
+    Vd, Wd = torch.as_tensor(V, device="cuda"), torch.as_tensor(W0.copy(), device="cuda")
+    Hd = torch.ones((R, n), device="cuda")
+    cost, div = engine.snmf_mu_ed(Vd, Wd, Hd, 0.2, 200, 1e-3, w_update=np.zeros(R, bool))
+    assert len(cost) == len(obj["cost"]) < 200
+    assert max(rel_err(Hd.cpu().numpy(), Ho)) < TOL
+    W0n = W0 / np.sqrt((W0.astype(np.float64) ** 2).sum(0))
+    assert max(rel_err(Wd.cpu().numpy(), W0n)) < 1e-6
+
+
+def test_snmf_python_mirror_chunk_driver(golden_dir):
+    """snmf.sparse_nmf_matlab (chunk driver + parameter handling) on the golden fixture of the reference's driver."""
+    from drnmf_b200 import snmf
+    g = np.load(os.path.join(golden_dir, "snmf_ed.npz"))
+    prm = {"cf": "ed", "sparsity": float(g["sparsity"]), "max_iter": float(g["max_iter"]), "conv_eps": float(g["conv_eps"]),
+           "display": 0., "random_seed": 2016., "r": g["init_w"].shape[1], "init_w": g["init_w"].copy(),
+           "w_update_ind": g["w_update_ind"], "init_h": "ones"}
+    W, H, obj = snmf.sparse_nmf_matlab(g["V"], prm, verbose=False)
+    assert max(rel_err(W, g["W"])) < TOL and max(rel_err(H, g["H"])) < TOL
+    np.testing.assert_allclose(obj["cost"], g["cost"], rtol=2e-5)
+    with pytest.raises(NotImplementedError):
+        snmf.sparse_nmf_matlab_on_chunk(g["V"], dict(prm, cf="kl"))
