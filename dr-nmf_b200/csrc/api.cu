@@ -32,6 +32,7 @@ FwdWorkspace carve_forward_ws(const drnmf_handle* h, int B, int T, void* base) {
   w.psum = (float*)take(2 * 256 * (size_t)Bp * 4);
   w.leak = (float*)take((size_t)Bp * 4);
   w.flags = (unsigned int*)take(16384 * 4);
+  w.actT_hi = nullptr; w.actT_lo = nullptr;
   w.bytes = off;
   return w;
 }
@@ -105,7 +106,8 @@ int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags) {
       {&h->Dt_hi, K * Rp * Fp}, {&h->Dt_lo, K * Rp * Fp}, {&h->Wt_hi, K * Rp * Fp}, {&h->Wt_lo, K * Rp * Fp},
       {&h->bias, K * Rp}, {&h->ST_hi, nS * Rp * Rp}, {&h->ST_lo, nS * Rp * Rp},
       {&h->EcT_hi, Fq * Rp}, {&h->EcT_lo, Fq * Rp}, {&h->EnT_hi, Fq * Rp}, {&h->EnT_lo, Fq * Rp},
-      {&h->h0, Rp}, {&h->inv_norm, K * Rp}};
+      {&h->h0, Rp}, {&h->inv_norm, K * Rp}, {&h->Dm_hi, K * Fp * Rp}, {&h->Dm_lo, K * Fp * Rp},
+      {&h->EcB_hi, Rp * 2 * Fp}, {&h->EcB_lo, Rp * 2 * Fp}, {&h->alph, K * Rp}, {&h->log_h0, Rp}};
   for (auto& a : allocs) {
     cudaError_t e = cudaMalloc(a.p, a.n * sizeof(float));
     if (e != cudaSuccess) {
@@ -126,7 +128,7 @@ int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags) {
 int drnmf_destroy(drnmf_handle* h) {
   if (!h) return DRNMF_OK;
   float* ptrs[] = {h->Dt_hi, h->Dt_lo, h->Wt_hi, h->Wt_lo, h->bias, h->ST_hi, h->ST_lo, h->EcT_hi, h->EcT_lo,
-                   h->EnT_hi, h->EnT_lo, h->h0, h->inv_norm};
+                   h->EnT_hi, h->EnT_lo, h->h0, h->inv_norm, h->Dm_hi, h->Dm_lo, h->EcB_hi, h->EcB_lo, h->alph, h->log_h0};
   for (float* p : ptrs) if (p) cudaFree(p);
   if (h->dev_error) cudaFree(h->dev_error);
   if (h->ev_ready) for (auto& e : h->ev) cudaEventDestroy(e);
@@ -326,6 +328,28 @@ int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, co
   int g = gemm_device_error(st);
   if (g) { set_error("drnmf_snmf_mu_ed: device-side failure code %d in a GEMM kernel", g); return DRNMF_ERR_DEVICE; }
   return DRNMF_OK;
+}
+
+size_t drnmf_train_workspace_bytes(const drnmf_handle* h, int B, int T) {
+  if (!h || B < 1 || T < 1) return 0;
+  return train_workspace_bytes(h, B, T);
+}
+
+int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value, float* g_log_D,
+                         float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
+                         double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream) {
+  DRNMF_CHECK(h, "NULL handle");
+  int rc = check_device(h);
+  if (rc) return rc;
+  DRNMF_CHECK(h->params_set, "drnmf_loss_and_grads before drnmf_set_params");
+  DRNMF_CHECK(x && y && g_log_D && g_log_alph && g_log_lam1 && g_log_h0 && g_k_clean && g_k_noise && loss_host && ws,
+              "drnmf_loss_and_grads: NULL argument");
+  DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = train_loss_and_grads(h, x, y, B, T, mask_value, g_log_D, g_log_alph, g_log_lam1, g_log_h0, g_k_clean, g_k_noise,
+                            loss_host, irm, ws, ws_bytes, st);
+  if (rc) return rc;
+  return check_dev_error(h, st, "drnmf_loss_and_grads");
 }
 
 // ---- end-to-end with host buffers ----------------------------------------------------------------

@@ -7,7 +7,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
 mkdir -p "$HERE/../build"
 OBJS=""
-for f in runtime prep gemm stft recurrent_simt recurrent_tc snmf api; do
+for f in runtime prep gemm stft recurrent_simt recurrent_tc snmf train api; do
   src="$HERE/$f.cu"; obj="$HERE/../build/$f.o"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/internal.h" -nt "$obj" ] || [ "$HERE/gemm_simt.cuh" -nt "$obj" ] || [ "$HERE/../../include/drnmf.h" -nt "$obj" ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj" &

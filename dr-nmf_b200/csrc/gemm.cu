@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
         a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(v);
       } else if (EPI == EPI_RECON) {
         a.C[(size_t)m * a.ldc + n] = epi_irm_value(acc[i][j], acc2[i][j], a.square);
+        if (a.C_S) { a.C_S[(size_t)m * a.ldc + n] = acc[i][j]; a.C_N[(size_t)m * a.ldc + n] = acc2[i][j]; }
       } else {
         const float v = fmaxf(acc[i][j], a.flr);
         a.C[(size_t)m * a.ldc + n] = v; a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(v);
@@ -238,7 +239,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           } else if (EPI == EPI_RECON) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (n + i < a.N_valid) a.C[(size_t)m * a.ldc + n + i] = epi_irm_value(v[i], v2[i], a.square);
+              if (n + i < a.N_valid) {
+                a.C[(size_t)m * a.ldc + n + i] = epi_irm_value(v[i], v2[i], a.square);
+                if (a.C_S) { a.C_S[(size_t)m * a.ldc + n + i] = v[i]; a.C_N[(size_t)m * a.ldc + n + i] = v2[i]; }
+              }
           } else {
             // sparse-NMF reconstruction: Lambda = max(W H, flr) in both layouts (+ tf32 remainders) and the squared
             // error against V.  Row-major: 64 contiguous bytes per thread; transposed: lanes = consecutive rows.

@@ -15,6 +15,12 @@ struct drnmf_handle {
   float *EcT_hi, *EcT_lo;  // Fq x Rp       exp(k_clean)^T in columns [0,r), zero elsewhere   (custom_layers.py:24)
   float *EnT_hi, *EnT_lo;  // Fq x Rp       exp(k_noise)^T in columns [r,R), zero elsewhere
   float *h0;               // Rp            softplus(log_h0)                            (custom_layers.py:206)
+  // extra copies used by the backward pass
+  float *Dm_hi, *Dm_lo;    // K x Fp x Rp   D^_k (rows f): B operand of dD^ = Gsym . D^
+  float *EcB_hi, *EcB_lo;  // Rp x 2Fp      block-diagonal [exp(k_clean) | 0 ; 0 | exp(k_noise)]: B operand of dH = [dS|dN] . EcB^T
+  float *alph;             // K x Rp        exp(log_alph) per layer and atom
+  float *log_h0;           // Rp
+  int n_log_D, n_log_alph, alph_dim, n_log_lam1;
   float *inv_norm;         // K x Rp scratch
   float u0_d, u0_o, uk_d, uk_o;
   int* dev_error;          // device-side error word (watchdogs / protocol violations)
@@ -39,6 +45,7 @@ struct FwdWorkspace {
   float* psum;              // 2 x 256 x Bp partial row sums of the state (rank-1 leak)
   float* leak;              // Bp          SIMT path: sum_j state[b][j]
   unsigned int* flags;      // device flags for the persistent kernel
+  float *actT_hi, *actT_lo; // training only: K x Rp x (T*Bp) post-relu activations, time-major frames (t*Bp + b)
   size_t bytes;
   int Bp;
 };
@@ -61,6 +68,7 @@ struct GemmArgs {
   int R_valid, N_valid, M_valid;         // masks for the epilogues
   int square;                            // EPI_RECON: transform_before_irm == 'square'
   const float* bias;                     // EPI_STORE: optional per-column bias added in the epilogue (length N)
+  float *C_S, *C_N;                      // EPI_RECON: optional raw reconstructions S^, N^ (same ld as C) for the backward pass
   int splits;                            // split-K: grid.z partial products, split z written at C + z*split_stride (0/1 = off)
   size_t split_stride;
   // EPI_LAMBDA (sparse NMF): C/C_lo = max(acc, flr) (M x ldc), CT/CT_lo = its transpose (N x ldct), and the squared
@@ -89,6 +97,11 @@ size_t snmf_workspace_bytes(int F, int n, int R);
 int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
                int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
                double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st);
+// ---- train.cu --------------------------------------------------------------------------------------
+size_t train_workspace_bytes(const drnmf_handle* h, int B, int T);
+int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value, float* g_log_D,
+                         float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
+                         double* loss_host, float* irm_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_init_state(const drnmf_handle* h, FwdWorkspace& w, cudaStream_t st);
 int gemm_device_error(cudaStream_t st);
 const char* last_error();

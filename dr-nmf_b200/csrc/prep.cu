@@ -33,7 +33,8 @@ __global__ void k_colnorm(const float* __restrict__ log_D, int F, int R, int Rp,
 __global__ void k_prep_dict(const float* __restrict__ log_D, int n_log_D, const float* __restrict__ log_alph,
                             int n_log_alph, int alph_dim, const float* __restrict__ inv_norm, int F, int R, int Rp,
                             int Fp, float* __restrict__ Dt_hi, float* __restrict__ Dt_lo, float* __restrict__ Wt_hi,
-                            float* __restrict__ Wt_lo) {
+                            float* __restrict__ Wt_lo, float* __restrict__ Dm_hi, float* __restrict__ Dm_lo,
+                            float* __restrict__ alph_out) {
   __shared__ float tile[32][33];
   const int k = blockIdx.z;
   const int kD = (n_log_D == 1) ? 0 : k;
@@ -42,7 +43,11 @@ __global__ void k_prep_dict(const float* __restrict__ log_D, int n_log_D, const 
   const float* src = log_D + (size_t)kD * F * R;
   for (int y = threadIdx.y; y < 32; y += 8) {
     int f = f0 + y, j = j0 + threadIdx.x;
-    tile[y][threadIdx.x] = (f < F && j < R) ? expf(src[(size_t)f * R + j]) : 0.f;
+    const float e = (f < F && j < R) ? expf(src[(size_t)f * R + j]) : 0.f;
+    tile[y][threadIdx.x] = e;
+    const float dn = (j < R) ? e * inv_norm[(size_t)kD * Rp + j] : 0.f;       // D^_k[f][j], rows f (backward operand)
+    Dm_hi[((size_t)k * Fp + f) * Rp + j] = dn; Dm_lo[((size_t)k * Fp + f) * Rp + j] = tf32_lo(dn);
+    if (f == 0) alph_out[(size_t)k * Rp + j] = (j < R) ? expf(log_alph[(size_t)kA * alph_dim + (alph_dim == 1 ? 0 : j)]) : 1.f;
   }
   __syncthreads();
   for (int y = threadIdx.y; y < 32; y += 8) {
@@ -87,8 +92,9 @@ __global__ void k_prep_bias_h0(const float* __restrict__ log_alph, int n_log_alp
 // EcT[f][j] = exp(k_clean[j][f]) (j < r) ; EnT[f][j] = exp(k_noise[j-r][f]) (r <= j < R) ; zero elsewhere.
 // grid (Rp/32, Fq/32), block (32, 8)
 __global__ void k_prep_recon(const float* __restrict__ k_clean, const float* __restrict__ k_noise, int F, int R, int r,
-                             int Rp, float* __restrict__ EcT_hi, float* __restrict__ EcT_lo,
-                             float* __restrict__ EnT_hi, float* __restrict__ EnT_lo) {
+                             int Rp, int Fp, float* __restrict__ EcT_hi, float* __restrict__ EcT_lo,
+                             float* __restrict__ EnT_hi, float* __restrict__ EnT_lo, float* __restrict__ EcB_hi,
+                             float* __restrict__ EcB_lo) {
   __shared__ float tc[32][33], tn[32][33];
   const int j0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
   for (int y = threadIdx.y; y < 32; y += 8) {
@@ -99,6 +105,11 @@ __global__ void k_prep_recon(const float* __restrict__ k_clean, const float* __r
       else if (j < R) n = expf(k_noise[(size_t)(j - r) * F + f]);
     }
     tc[y][threadIdx.x] = c; tn[y][threadIdx.x] = n;
+    if (f < Fp) {   // block-diagonal copy, rows j: [clean | 0] for j < r, [0 | noise] for r <= j < R
+      const size_t o = (size_t)j * (2 * Fp);
+      EcB_hi[o + f] = c; EcB_lo[o + f] = tf32_lo(c);
+      EcB_hi[o + Fp + f] = n; EcB_lo[o + Fp + f] = tf32_lo(n);
+    }
   }
   __syncthreads();
   for (int y = threadIdx.y; y < 32; y += 8) {
@@ -117,11 +128,14 @@ int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const f
   k_colnorm<<<dim3((Rp + 31) / 32, n_log_D), dim3(32, 8), 0, st>>>(log_D, F, R, Rp, h->inv_norm);
   k_prep_dict<<<dim3(Fp / 32, Rp / 32, K), dim3(32, 8), 0, st>>>(log_D, n_log_D, log_alph, n_log_alph, alph_dim,
                                                                  h->inv_norm, F, R, Rp, Fp, h->Dt_hi, h->Dt_lo,
-                                                                 h->Wt_hi, h->Wt_lo);
+                                                                 h->Wt_hi, h->Wt_lo, h->Dm_hi, h->Dm_lo, h->alph);
   k_prep_bias_h0<<<(K * Rp + 255) / 256, 256, 0, st>>>(log_alph, n_log_alph, alph_dim, log_lam1, n_log_lam1, log_h0, R,
                                                        Rp, K, h->bias, h->h0);
-  k_prep_recon<<<dim3(Rp / 32, h->Fq / 32), dim3(32, 8), 0, st>>>(k_clean, k_noise, F, R, h->r, Rp, h->EcT_hi,
-                                                                  h->EcT_lo, h->EnT_hi, h->EnT_lo);
+  k_prep_recon<<<dim3(Rp / 32, h->Fq / 32), dim3(32, 8), 0, st>>>(k_clean, k_noise, F, R, h->r, Rp, Fp, h->EcT_hi,
+                                                                  h->EcT_lo, h->EnT_hi, h->EnT_lo, h->EcB_hi, h->EcB_lo);
+  DRNMF_CUDA(cudaMemsetAsync(h->log_h0, 0, sizeof(float) * Rp, st));
+  DRNMF_CUDA(cudaMemcpyAsync(h->log_h0, log_h0, sizeof(float) * R, cudaMemcpyDeviceToDevice, st));
+  h->n_log_D = n_log_D; h->n_log_alph = n_log_alph; h->alph_dim = alph_dim; h->n_log_lam1 = n_log_lam1;
   count_launch(4);
   DRNMF_CUDA(cudaGetLastError());
   return DRNMF_OK;

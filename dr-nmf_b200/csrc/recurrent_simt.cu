@@ -17,6 +17,7 @@ struct StepArgs {
   float* h_out_lo;
   float *Hp_hi, *Hp_lo;   // BT x Rp
   float* H_user;          // B x T x R or null
+  float *actT_hi, *actT_lo; int Bp;   // training: K x Rp x (T*Bp) activations (time-major frames) or null
   const float* ST;        // Rp x Rp for this layer
   int B, T, t, k, K, R, Rp;
   float dmo, off;         // (diag - offdiag), offdiag of U_k
@@ -58,6 +59,10 @@ __global__ void k_frame_begin(StepArgs a) {
   for (int j = threadIdx.x; j < a.Rp; j += blockDim.x) {
     float g = 0.f;
     if (j < a.R) g = fmaxf(st[j] * a.dmo + a.off * leak + xw[j], 0.f);
+    if (a.actT_hi) {
+      const size_t o3 = (size_t)j * ((size_t)a.T * a.Bp) + (size_t)a.t * a.Bp + b;
+      a.actT_hi[o3] = g; a.actT_lo[o3] = tf32_lo(g);
+    }
     if (a.K == 1) {
       finish_frame(a, b, j, g);
     } else {
@@ -88,6 +93,10 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_step_simt(StepArgs a) {
         float pre = a.off * leak + acc[i][jj] + xw[j];
         if (a.dmo != 0.f) pre += a.dmo * a.state[(size_t)b * a.Rp + j];
         g = fmaxf(pre, 0.f);
+      }
+      if (a.actT_hi) {
+        const size_t o3 = ((size_t)a.k * a.Rp + j) * ((size_t)a.T * a.Bp) + (size_t)a.t * a.Bp + b;
+        a.actT_hi[o3] = g; a.actT_lo[o3] = tf32_lo(g);
       }
       if (a.k == a.K - 1) {
         finish_frame(a, b, j, g);
@@ -122,6 +131,7 @@ int launch_recurrent_simt(drnmf_handle* h, FwdWorkspace& w, int B, int T, float*
   StepArgs a;
   a.XW = w.XW; a.bias = h->bias; a.mvalid = w.mvalid; a.state = w.state; a.leak = w.leak;
   a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;
+  a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo; a.Bp = w.Bp;
   a.B = B; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   dim3 grid(Rp / SIMT_BN, (B + SIMT_BM - 1) / SIMT_BM);
   for (int t = 0; t < T; ++t) {

@@ -37,6 +37,7 @@ struct RecArgs {
   // tensors
   const float* XW; const float* mvalid; const float* h0;   // XW includes the bias b_k
   float *state, *psum, *Hp_hi, *Hp_lo, *H_user, *hb_hi, *hb_lo;
+  float *actT_hi, *actT_lo;                  // training: K x Rp x (T*Bp) activations, time-major frames; else null
   unsigned int* flags;
   int* dev_error;
   long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
@@ -413,6 +414,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const int rowq = row0 + 4 * blk_rq[c];
           const float4 lk4 = *reinterpret_cast<const float4*>(leak_s + i * NB + 4 * blk_bq[c]);
           const float lkv[4] = {off * lk4.x, off * lk4.y, off * lk4.z, off * lk4.w};
+          float gall[4][4];                            // [batch bi][row e] kept for the transposed activation store
 #pragma unroll
           for (int bi = 0; bi < 4; ++bi) {
             const int bl = 4 * blk_bq[c] + bi, b = i * NB + bl;
@@ -428,6 +430,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             for (int e = 0; e < 4; ++e) {
               const bool valid = (b < a.B) && (rowq + e < a.R);
               g[e] = valid ? fmaxf(acc[c][e][bi] + xv[e] + lkv[bi] + (need_state ? dmo * sv[e] : 0.f), 0.f) : 0.f;
+              gall[bi][e] = g[e];
             }
             if (!last) {
               const size_t o2 = ((size_t)(k & 1) * a.Bp + b) * Rp + rowq;
@@ -461,6 +464,16 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             if (last) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) out_s[bl * (RO + 1) + 4 * blk_rq[c] + e] = stn[e];
+            }
+          }
+          if (a.actT_hi) {                             // backward needs every layer's post-relu output
+            const size_t TB = (size_t)T * a.Bp;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const size_t o3 = ((size_t)k * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + 4 * blk_bq[c];
+              __stcg(reinterpret_cast<float4*>(a.actT_hi + o3), make_float4(gall[0][e], gall[1][e], gall[2][e], gall[3][e]));
+              __stcg(reinterpret_cast<float4*>(a.actT_lo + o3), make_float4(tf32_lo(gall[0][e]), tf32_lo(gall[1][e]),
+                                                                           tf32_lo(gall[2][e]), tf32_lo(gall[3][e])));
             }
           }
         }
@@ -653,6 +666,7 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   a.XW = w.XW; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.state = w.state; a.psum = w.psum; a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;
   a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
+  a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo;
   static long long* dbg_dev = nullptr;
   const bool want_dbg = getenv("DRNMF_REC_DEBUG") != nullptr;
   if (want_dbg && !dbg_dev) DRNMF_CUDA(cudaMalloc(&dbg_dev, 16 * 8 * sizeof(long long)));

@@ -62,6 +62,7 @@ class DrnmfEngine:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self._ws = None
         self._ews = None
+        self._tws = None
         self._keep = None
         rp, fp = C.c_int(), C.c_int()
         _lib.check(self.lib.drnmf_padded_dims(self.h, C.byref(rp), C.byref(fp)))
@@ -158,6 +159,29 @@ class DrnmfEngine:
         _lib.check(self.lib.drnmf_enhance_host(self.h, _ptr(x_host), _ptr(stack_host), _ptr(frames_host), B, T, N, hop,
                                                float(mask_value), _ptr(out), ws, wsb, _stream()))
         return out
+
+    def loss_and_grads(self, x, y, mask_value=-1.0, want_irm=False):
+        """Training step on the device: forward with stored activations, masked-MSE loss (enhance.py:1040-1073) and
+        hand-written BPTT.  Returns (loss_sum, mask_sum, grads dict of CUDA tensors [, irm]); the loss is
+        loss_sum / mask_sum and the gradients are those of loss_sum (divide by the all-reduced frame count)."""
+        if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32):
+            raise TypeError("x must be a float32 CUDA tensor")
+        x, y = x.contiguous(), y.contiguous()
+        B, T, F = x.shape
+        dev = x.device
+        log_D, log_alph, log_lam1 = self._keep[0], self._keep[1], self._keep[2]
+        g = {"log_D": torch.zeros_like(log_D), "log_alph": torch.zeros_like(log_alph).reshape(-1),
+             "log_lam1": torch.zeros_like(log_lam1), "log_h0": torch.zeros(self.R, device=dev),
+             "k_clean": torch.zeros((self.R // 2, F), device=dev), "k_noise": torch.zeros((self.R // 2, F), device=dev)}
+        irm = torch.empty((B, T, F), dtype=torch.float32, device=dev) if want_irm else None
+        need = self.lib.drnmf_train_workspace_bytes(self.h, B, T)
+        ws, wsb = self._workspace(need, "_tws")
+        loss = (C.c_double * 2)()
+        _lib.check(self.lib.drnmf_loss_and_grads(self.h, _ptr(x), _ptr(y), B, T, float(mask_value), _ptr(g["log_D"]),
+                                                 _ptr(g["log_alph"]), _ptr(g["log_lam1"]), _ptr(g["log_h0"]),
+                                                 _ptr(g["k_clean"]), _ptr(g["k_noise"]), loss, _ptr(irm), ws, wsb, _stream()))
+        out = (float(loss[0]), float(loss[1]), g)
+        return out + (irm,) if want_irm else out
 
     def stage_times(self):
         """ms of (masking, projection GEMM, recurrence, recon+mask GEMM) of the last forward (CUDA events)."""

@@ -129,6 +129,18 @@ DRNMF_API int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, fl
                      double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream);
 DRNMF_API size_t drnmf_snmf_workspace_bytes(int F, int n, int R);
 
+/* ---- training: loss and gradients through the unfolded layers (enhance.py:1040-1073, 1152-1157) -----------------
+ * The reference trains with Keras/Theano autodiff (BPTT through scan); this is the hand-written equivalent.
+ * x, y (B,T,F) padded with mask_value (y is only read at valid frames).  loss_host[0] = sum_{b,t} m * mean_f (x*irm-y)^2,
+ * loss_host[1] = sum m; the training loss is loss_host[0]/loss_host[1] and every gradient returned is the gradient of
+ * loss_host[0] (divide by the -- possibly all-reduced -- frame count).  Gradient shapes follow drnmf_set_params:
+ * g_log_D (n_log_D,F,R), g_log_alph (n_log_alph), g_log_lam1 (n_log_lam1), g_log_h0 (R), g_k_clean/g_k_noise (R/2,F);
+ * tied parameters receive the sum over layers.  irm (B,T,F) optional output.  Scalar alph per layer only. */
+DRNMF_API int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value,
+                         float* g_log_D, float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean,
+                         float* g_k_noise, double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream);
+DRNMF_API size_t drnmf_train_workspace_bytes(const drnmf_handle* h, int B, int T);
+
 #ifdef __cplusplus
 }
 #endif

@@ -351,3 +351,38 @@ def test_snmf_python_mirror_chunk_driver(golden_dir):
     np.testing.assert_allclose(obj["cost"], g["cost"], rtol=2e-5)
     with pytest.raises(NotImplementedError):
         snmf.sparse_nmf_matlab_on_chunk(g["V"], dict(prm, cf="kl"))
+
+
+# ---- training: loss + hand-written BPTT against torch.autograd on the float64 oracle ---------------------------
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("case", [dict(F=33, R=16, K=3, B=3, T=6, tied=False), dict(F=65, R=40, K=4, B=5, T=8, tied=False),
+                                  dict(F=40, R=24, K=3, B=2, T=5, tied=True)])
+def test_loss_and_grads_vs_autograd(case, impl):
+    from oracle import torch_oracle as TO
+    F, R, K, B, T = (case[k] for k in "FRKBT")
+    rng = np.random.default_rng(99 + F)
+    p = synth.model_params(F, R, K, alph=15.0, lam1=0.3, untied=not case["tied"])
+    if not case["tied"]:
+        p["log_alph"] = (p["log_alph"] + 0.05 * rng.standard_normal(K)).astype(np.float32)
+    x = (np.abs(rng.standard_normal((B, T, F))) * 2).astype(np.float32)
+    y = (x * rng.uniform(0.2, 0.9, size=x.shape)).astype(np.float32)
+    lens = rng.integers(2, T + 1, size=B); lens[0] = T
+    for b in range(B):
+        x[b, lens[b]:] = -1.0; y[b, lens[b]:] = -1.0
+    loss_o, g_o, H_o, irm_o = TO.loss_and_grads(x, y, p)
+    pe = dict(p)
+    if case["tied"]:     # one shared dictionary / step size: gradients are summed over the layers
+        pe["log_D"], pe["log_alph"], pe["log_lam1"] = p["log_D"][:1], p["log_alph"][:1], p["log_lam1"][:1]
+        for k in ("log_D", "log_alph", "log_lam1"):
+            g_o[k] = g_o[k].sum(axis=0, keepdims=True)
+        assert np.all(p["log_D"] == p["log_D"][0])
+    eng = engine.DrnmfEngine(F, R, K, impl=impl)
+    eng.set_params(pe)
+    ls, ms, g, irm = eng.loss_and_grads(torch.as_tensor(x, device="cuda"), torch.as_tensor(y, device="cuda"), want_irm=True)
+    assert ms == float(lens.sum())
+    assert abs(ls / ms - loss_o) < 2e-5 * abs(loss_o)
+    assert max(rel_err(irm.cpu().numpy(), irm_o)) < TOL
+    for key in ("log_D", "log_alph", "log_lam1", "log_h0", "k_clean", "k_noise"):
+        got = g[key].cpu().numpy().reshape(g_o[key].shape) / ms
+        fro, mx = rel_err(got, g_o[key])
+        assert fro < 2e-4 and mx < 2e-4, (impl, case, key, fro, mx)
