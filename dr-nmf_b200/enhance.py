@@ -98,8 +98,16 @@ class UnfoldedSNMFModel:
         irm = irm.cpu().numpy()
         return (irm, H.cpu().numpy()) if return_hidden else irm
 
-    def fit(self, *args, **kwargs):
-        raise NotImplementedError("training (enhance.py:1152-1157) is not built in this round: see DESIGN.md section 7")
+    def fit(self, x, y, sample_weight=None, batch_size=32, epochs=1, validation_data=None, learning_rate=1e-3,
+            clipnorm=0.0, decay=0.0, patience=50, savefile=None, verbose=0):
+        """enhance.py:1152-1157 (loss 'mse' on x*irm with temporal sample weights, Adam): see training.Trainer.
+        sample_weight is accepted for signature compatibility; the frame mask is derived from the -1 padding."""
+        from .training import Trainer
+        if getattr(self, "_trainer", None) is None:
+            self._trainer = Trainer(self, learning_rate=learning_rate, clipnorm=clipnorm, decay=decay)
+        vd = None if validation_data is None else (validation_data[0], validation_data[1])
+        return self._trainer.fit(x, y, batch_size=batch_size, epochs=epochs, validation_data=vd, patience=patience,
+                                 savefile=savefile, verbose=verbose)
 
 
 def build_unfolded_snmf(params_unfolded_snmf):
