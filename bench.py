@@ -24,6 +24,23 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1; the CPU arms of this benchmark are meant to use every host core the BLAS can
+# take, so the thread count is restored before numpy (and its BLAS) is imported.
+if "--impl" in sys.argv and "reference" in sys.argv or os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ.pop("MKL_NUM_THREADS", None)
+    os.environ.pop("OPENBLAS_NUM_THREADS", None)
+
+# Exactly ONE line goes to stdout (the JSON).  Everything else that libraries print there (e.g. NCCL's version banner)
+# is diverted to stderr by pointing fd 1 at fd 2 for the duration of the run.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -176,7 +193,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -316,7 +333,7 @@ def main():
                     "d2h_bytes_per_step": int(out_host.numel() * 4)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -330,6 +330,25 @@ int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, co
   return DRNMF_OK;
 }
 
+size_t drnmf_ista_workspace_bytes(int F, int n, int R) {
+  if (F < 1 || n < 1 || R < 1) return 0;
+  return ista_workspace_bytes(F, n, R);
+}
+
+int drnmf_ista_ed(int F, int n, int R, const float* x, const float* W, float* H, float lam1, float alph, int iters, int flags,
+                  void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  DRNMF_CHECK(x && W && H && ws && F >= 1 && n >= 1 && R >= 1 && iters >= 0 && alph > 0, "drnmf_ista_ed: bad arguments");
+  DRNMF_CHECK(n % 4 == 0, "drnmf_ista_ed: the frame count must be a multiple of 4 (16-byte rows of H)");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ista_ed(F, n, R, x, W, H, lam1, alph, iters, ws, ws_bytes, pick_impl(flags) == DRNMF_IMPL_SIMT, st);
+  if (rc) return rc;
+  int g = gemm_device_error(st);
+  if (g) { set_error("drnmf_ista_ed: device-side failure code %d in a GEMM kernel", g); return DRNMF_ERR_DEVICE; }
+  return DRNMF_OK;
+}
+
 size_t drnmf_train_workspace_bytes(const drnmf_handle* h, int B, int T) {
   if (!h || B < 1 || T < 1) return 0;
   return train_workspace_bytes(h, B, T);

@@ -53,7 +53,7 @@ struct RecArgs {
 };
 
 struct RecBars {   // all mbarriers, laid out at off_bar
-  uint64_t h_full[4], h_empty[4], t_full[RT_AST], t_empty[RT_AST], red_full[4], red_free[4];
+  uint64_t h_full[4][4], h_empty[4], t_full[RT_AST], t_empty[RT_AST], red_full[4], red_free[4];
   uint64_t pub_full[RT_PST], pub_empty[RT_PST];
   uint64_t wt_full, wt_empty;                // weights of the current step are in TMEM / may be overwritten
   uint32_t tmem_slot;
@@ -118,7 +118,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo);
     mbar_init(&bars->wt_full, 128); mbar_init(&bars->wt_empty, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(&bars->h_full[i], 1); mbar_init(&bars->h_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { for (int a2 = 0; a2 < 4; ++a2) mbar_init(&bars->h_full[i][a2], 1); mbar_init(&bars->h_empty[i], 1); }
     for (int i = 0; i < RT_AST; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
     for (int i = 0; i < 4; ++i) { mbar_init(&bars->red_full[i], 1); mbar_init(&bars->red_free[i], 4 * a.KS); }
     for (int i = 0; i < RT_PST; ++i) { mbar_init(&bars->pub_full[i], 4); mbar_init(&bars->pub_empty[i], 1); }
@@ -153,11 +153,11 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             }
             RT_TIMED(2, fence_proxy_async());          // generic-proxy writes of the owners -> async-proxy (TMA) reads
             uint8_t* dst = smem + a.off_h + hs * a.h_stage_bytes;
-            mbar_expect_tx(&bars->h_full[hs], 2 * ATOMS * H_ATOM_BYTES);
-            for (int at = 0; at < ATOMS; ++at) {
+            for (int at = 0; at < ATOMS; ++at) {   // one barrier per 32-atom slab: the MMA starts on the first to land
               const int c0 = s * a.KSLICE + at * 32, c1 = slot * a.Bp + i * NB;
-              tma_load_2d(dst + (2 * at) * H_ATOM_BYTES, &tmH_hi, &bars->h_full[hs], c0, c1);
-              tma_load_2d(dst + (2 * at + 1) * H_ATOM_BYTES, &tmH_lo, &bars->h_full[hs], c0, c1);
+              mbar_expect_tx(&bars->h_full[hs][at], 2 * H_ATOM_BYTES);
+              tma_load_2d(dst + (2 * at) * H_ATOM_BYTES, &tmH_hi, &bars->h_full[hs][at], c0, c1);
+              tma_load_2d(dst + (2 * at + 1) * H_ATOM_BYTES, &tmH_lo, &bars->h_full[hs][at], c0, c1);
             }
           }
         }
@@ -176,8 +176,6 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const int as = it % RT_AST, hs = it % a.HST;
           RT_TIMED(0, okm = mbar_wait(&bars->t_empty[as], ((it / RT_AST) & 1) ^ 1, err, RT_WATCHDOG));
           if (!okm) { atomicCAS(a.dev_error, 0, 204); break; }
-          RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs], (it / a.HST) & 1, err, RT_WATCHDOG));
-          if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
           if (i == 0) {      // this step's S_k^T block (hi | lo) has been written to TMEM by the loader warpgroup
             RT_TIMED(2, okm = mbar_wait(&bars->wt_full, (uint32_t)(ms & 1), err, RT_WATCHDOG));
             if (!okm) { atomicCAS(a.dev_error, 0, 206); break; }
@@ -190,6 +188,11 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 #pragma unroll 4
           for (int ks = 0; ks < nks; ++ks) {
             const int at = ks >> 2, kk = ks & 3;
+            if (kk == 0) {
+              RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs][at], (it / a.HST) & 1, err, RT_WATCHDOG));
+              if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
+              tc_fence_after();
+            }
             const uint32_t w_hi = tmem_base + ks * 8, w_lo = tmem_base + a.KSLICE + ks * 8;
             const uint64_t h_hi = umma_desc_k128(hbase + (2 * at) * H_ATOM_BYTES + kk * 32);
             const uint64_t h_lo = umma_desc_k128(hbase + (2 * at + 1) * H_ATOM_BYTES + kk * 32);
@@ -199,6 +202,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
               umma_tf32_ts(d_tmem, w_hi, h_hi, idesc, true);
             }
           }
+          if (!okm) break;
           if (leader) {
             if (i == n_tiles - 1) tc_commit(&bars->wt_empty);          // TMEM weights of this step fully consumed
             tc_commit(&bars->h_empty[hs]);

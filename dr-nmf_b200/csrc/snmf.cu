@@ -338,4 +338,67 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
   return DRNMF_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame-parallel ISTA with a tied dictionary (enhance.py:402-418, `ista_ed`: dead code in the reference, oracle "A"):
+//   xhat = W H ; repeat K times:  H <- max(0, -lam1/alph + H + (1/alph) W^T (x - xhat)) ; xhat = W H
+// Frames are independent, so this is two GEMMs + two elementwise kernels per iteration on the frame-major layout.
+__global__ void k_ista_residual(const float* __restrict__ xt, const float* __restrict__ xhat, size_t n, float* __restrict__ e_hi,
+                                float* __restrict__ e_lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float e = xt[i] - xhat[i]; e_hi[i] = e; e_lo[i] = tf32_lo(e); }
+}
+__global__ void k_ista_update(float* __restrict__ Ht_hi, float* __restrict__ Ht_lo, const float* __restrict__ G, int n, int R,
+                              int Rk, float lam_over_alph, float inv_alph) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * Rk) return;
+  const int r = (int)(i % Rk);
+  float h = 0.f;
+  if (r < R) h = fmaxf(0.f, -lam_over_alph + Ht_hi[i] + inv_alph * G[i]);
+  Ht_hi[i] = h; Ht_lo[i] = tf32_lo(h);
+}
+
+size_t ista_workspace_bytes(int F, int n, int R) {
+  const size_t Fk = round_up(F, 32), Rk = round_up(R, 32), nk = round_up(n, 128);
+  return al256((size_t)F * Rk * 4) * 2 + al256((size_t)R * Fk * 4) * 2 + al256(nk * Rk * 4) * 3 + al256(nk * Fk * 4) * 4 + 4096;
+}
+
+int ista_ed(int F, int n, int R, const float* x, const float* W, float* H, float lam1, float alph, int iters, void* ws,
+            size_t ws_bytes, bool simt, cudaStream_t st) {
+  const int Fk = round_up(F, 32), Rk = round_up(R, 32), nk = round_up(n, 128);
+  if (ws_bytes < ista_workspace_bytes(F, n, R)) { set_error("ista workspace too small"); return DRNMF_ERR_WORKSPACE; }
+  uint8_t* p = (uint8_t*)ws;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* q = p + off; off += al256(bytes); return (float*)q; };
+  float *Wm_hi = take((size_t)F * Rk * 4), *Wm_lo = take((size_t)F * Rk * 4);
+  float *WT_hi = take((size_t)R * Fk * 4), *WT_lo = take((size_t)R * Fk * 4);
+  float *Ht_hi = take((size_t)nk * Rk * 4), *Ht_lo = take((size_t)nk * Rk * 4), *G = take((size_t)nk * Rk * 4);
+  float *xt = take((size_t)nk * Fk * 4), *xhat = take((size_t)nk * Fk * 4), *e_hi = take((size_t)nk * Fk * 4), *e_lo = take((size_t)nk * Fk * 4);
+  DRNMF_CUDA(cudaMemsetAsync(ws, 0, off, st));
+  const dim3 tb(32, 8);
+  k_split_both<<<dim3((R + 31) / 32, (F + 31) / 32), tb, 0, st>>>(W, F, R, R, Wm_hi, Wm_lo, F, Rk, WT_hi, WT_lo, R, Fk, nullptr, nullptr, 0);
+  k_split_both<<<dim3((n + 31) / 32, (R + 31) / 32), tb, 0, st>>>(H, R, n, n, nullptr, nullptr, 0, 0, Ht_hi, Ht_lo, nk, Rk, nullptr, nullptr, 0);
+  k_split_both<<<dim3((n + 31) / 32, (F + 31) / 32), tb, 0, st>>>(x, F, n, n, nullptr, nullptr, 0, 0, xt, e_lo, nk, Fk, nullptr, nullptr, 0);
+  count_launch(3);
+  int rc;
+  for (int it = 0; it < iters; ++it) {
+    GemmArgs a{};      // xhat^T = H^T-rows . W-rows
+    a.A_hi = Ht_hi; a.A_lo = Ht_lo; a.lda = Rk; a.B_hi = Wm_hi; a.B_lo = Wm_lo; a.ldb = Rk;
+    a.M = n; a.N = F; a.Kd = Rk; a.M_valid = n; a.N_valid = Fk; a.C = xhat; a.ldc = Fk;
+    if ((rc = run_gemm_impl(simt, EPI_STORE, a, st))) return rc;
+    k_ista_residual<<<(unsigned)(((size_t)nk * Fk + 255) / 256), 256, 0, st>>>(xt, xhat, (size_t)nk * Fk, e_hi, e_lo);
+    GemmArgs g{};      // G^T = (x - xhat)^T-rows . W^T-rows
+    g.A_hi = e_hi; g.A_lo = e_lo; g.lda = Fk; g.B_hi = WT_hi; g.B_lo = WT_lo; g.ldb = Fk;
+    g.M = n; g.N = R; g.Kd = Fk; g.M_valid = n; g.N_valid = Rk; g.C = G; g.ldc = Rk;
+    if ((rc = run_gemm_impl(simt, EPI_STORE, g, st))) return rc;
+    k_ista_update<<<(unsigned)(((size_t)n * Rk + 255) / 256), 256, 0, st>>>(Ht_hi, Ht_lo, G, n, R, Rk, lam1 / alph, 1.f / alph);
+    count_launch(2);
+  }
+  // H (R x n) <- Ht (n x Rk): transposed copy through the tile kernel (hi only; the lo output goes to scratch)
+  k_split_both<<<dim3((Rk + 31) / 32, (n + 31) / 32), tb, 0, st>>>(Ht_hi, n, R, Rk, nullptr, nullptr, 0, 0, H, G, R, n, nullptr, nullptr, 0);
+  count_launch();
+  DRNMF_CUDA(cudaGetLastError());
+  return DRNMF_OK;
+}
+
 }  // namespace drnmf

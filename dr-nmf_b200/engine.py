@@ -321,3 +321,22 @@ def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_updat
                                     C.c_void_p(ws.data_ptr() + off), nb, _stream()))
     k = iters.value
     return cost[:k].copy(), div[:k].copy()
+
+
+def ista_ed(x, W, H, lam1, alph, K, impl=None):
+    """enhance.py:402-418 on the GPU: x (F,n), W (F,R), H (R,n) float32 CUDA tensors; returns the updated H (new tensor)."""
+    _require_cuda()
+    lib = _lib.load()
+    F, n = x.shape
+    R = W.shape[1]
+    pad = (-n) % 4
+    if pad:   # frames are independent: pad with zero frames, drop them afterwards
+        x = torch.cat([x, x.new_zeros(F, pad)], dim=1)
+        H = torch.cat([H, H.new_zeros(R, pad)], dim=1)
+    x, W, Hn = x.contiguous(), W.contiguous(), H.contiguous().clone()
+    nb = lib.drnmf_ista_workspace_bytes(F, n + pad, R)
+    ws = torch.empty(nb + 256, dtype=torch.uint8, device=x.device)
+    off = (-ws.data_ptr()) % 256
+    _lib.check(lib.drnmf_ista_ed(F, n + pad, R, _ptr(x), _ptr(W), _ptr(Hn), float(lam1), float(alph), int(K),
+                                 _lib.IMPL_SIMT if impl == "simt" else 0, C.c_void_p(ws.data_ptr() + off), nb, _stream()))
+    return Hn[:, :n]

@@ -129,6 +129,13 @@ DRNMF_API int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, fl
                      double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream);
 DRNMF_API size_t drnmf_snmf_workspace_bytes(int F, int n, int R);
 
+/* ---- frame-parallel ISTA with a tied dictionary (enhance.py:402-418 `ista_ed`; defined but never called there) ---
+ * x (F,n), W (F,R), H (R,n) in/out, row-major device arrays: H <- max(0, -lam1/alph + H + (1/alph) W^T (x - W H)),
+ * `iters` times.  n must be a multiple of 4. */
+DRNMF_API int drnmf_ista_ed(int F, int n, int R, const float* x, const float* W, float* H, float lam1, float alph,
+                  int iters, int flags, void* ws, size_t ws_bytes, void* stream);
+DRNMF_API size_t drnmf_ista_workspace_bytes(int F, int n, int R);
+
 /* ---- training: loss and gradients through the unfolded layers (enhance.py:1040-1073, 1152-1157) -----------------
  * The reference trains with Keras/Theano autodiff (BPTT through scan); this is the hand-written equivalent.
  * x, y (B,T,F) padded with mask_value (y is only read at valid frames).  loss_host[0] = sum_{b,t} m * mean_f (x*irm-y)^2,

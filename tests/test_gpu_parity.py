@@ -412,3 +412,21 @@ def test_fit_reduces_loss_and_checkpoints(tmp_path):
     model2.load_weights(str(tmp_path / "best.npz"))
     irm_a = model2.predict_on_batch(x)
     assert irm_a.shape == x.shape and np.isfinite(irm_a).all()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_ista_ed_golden_and_oracle(golden_dir, impl):
+    """enhance.py:402-418 (oracle "A"): golden vectors produced by the reference's own function + a larger case."""
+    g = np.load(os.path.join(golden_dir, "ista_ed.npz"))
+    cu = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device="cuda")
+    H = engine.ista_ed(cu(g["x"]), cu(g["W"]), cu(g["H0"]), float(g["lam1"]), float(g["alph"]), int(g["K"]),
+                       impl=None if impl == "tc" else "simt")
+    assert max(rel_err(H.cpu().numpy(), g["H"])) < TOL
+    rng = np.random.default_rng(4)
+    F, R, n, K = 129, 200, 333, 25
+    W = synth.dictionary(F, R).astype(np.float64); W /= np.sqrt((W ** 2).sum(0, keepdims=True))
+    x = np.abs(rng.standard_normal((F, n))) * 3
+    H0 = np.abs(rng.standard_normal((R, n))) * 0.1
+    Ho = O.ista_ed(x, W, H0.copy(), 1.0, 60.0, K)
+    Hg = engine.ista_ed(cu(x), cu(W), cu(H0), 1.0, 60.0, K, impl=None if impl == "tc" else "simt")
+    assert max(rel_err(Hg.cpu().numpy(), Ho)) < TOL
