@@ -84,6 +84,8 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 // ---- recurrent.cu ----------------------------------------------------------------------------------
 int launch_recurrent_simt(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
+int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,
+                            float* deltaT_lo, float* G, float* psum2, cudaStream_t st);
 
 // ---- stft.cu -------------------------------------------------------------------------------------
 // fidx: (n_utt, 2) int64 (start, end) frame indices per utterance, the reference's fidx (util.py:335-337)

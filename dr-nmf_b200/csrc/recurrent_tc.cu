@@ -38,6 +38,9 @@ struct RecArgs {
   const float* XW; const float* mvalid; const float* h0;   // XW includes the bias b_k
   float *state, *psum, *Hp_hi, *Hp_lo, *H_user, *hb_hi, *hb_lo;
   float *actT_hi, *actT_lo;                  // training: K x Rp x (T*Bp) activations, time-major frames; else null
+  // backward chain (BWD instantiation): dL/dH from the head, dL/dz^k out, state-gradient carry, partial row sums
+  const float* dH; float *deltaT_hi, *deltaT_lo, *G, *psum2;
+  float d0mo_b, o0_b, ok_b;
   unsigned int* flags;
   int* dev_error;
   long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
@@ -89,7 +92,7 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int ta
     else { stmt; }                                             \
   } while (0)
 
-template <int NB>
+template <int NB, bool BWD>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo, RecArgs a) {
   // No static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below).  Keeping `smem`
@@ -285,7 +288,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         j = jend;
       }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= 8 && warp < 12 && !BWD) {
     // ================= owners: reduce the KS partials of rows [o*RO, (o+1)*RO), epilogue, hand off to the publisher ====
     const int otid = threadIdx.x - 256;              // 0..127
     const int RO = a.RO;
@@ -502,6 +505,179 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       if (lane == 0) mbar_arrive(&bars->pub_full[ps_]);   // release.cta, cumulative over the warp's stores (after __syncwarp)
     }
   }
+  if (BWD && warp >= 8 && warp < 12) {
+    // ================= owners, BACKWARD chain =================
+    // Same item structure as the forward pass with u = position in the frame: u = 0 builds delta^{K-1}(t) from the head
+    // gradient and the carried state gradient G (needs the row sums of the previous processed frame, exchanged through
+    // psum2 like the forward leak); u >= 1 turns the reduced product delta^k . S_k into delta^{k-1} by masking with the
+    // stored activation.  Every delta is also written transposed (time-major) for the weight-gradient GEMMs.
+    const int otid = threadIdx.x - 256;
+    const int RO = a.RO;
+    const int row0 = m * 128 + s * RO;
+    const int cta_lin = m * a.KS + s, n_cta = a.MT * a.KS;
+    constexpr int BQ = NB / 4;
+    constexpr int SWZ = (BQ >= 8) ? 7 : BQ - 1;
+    const int RQ = RO / 4;
+    const int n_blk = RQ * BQ;
+    const bool bv = otid < n_blk;
+    const int bq = bv ? otid % BQ : 0, rq = bv ? otid / BQ : 0;
+    const int rowq = row0 + 4 * rq;
+    const size_t TB = (size_t)T * a.Bp;
+    float* add_s = leak_s;                                   // n_tiles x NB : o0*R0 + ok*Rk of the previous processed frame
+    float* rk_acc = leak_s + n_tiles * NB;                   // n_tiles x NB : running sum over layers >= 1 of this frame
+    float* part_s = out_s;                                   // 2 x RQ x NB  : per-item row-sum partials (double buffered)
+    auto fetch_act = [&](int fi, int u, int i, float4 (&av)[4]) {
+      const int fic = fi < T ? fi : T - 1;
+      const int t = T - 1 - fic;
+      const int la = (u == 0) ? K - 1 : K - u - 1;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        av[e] = __ldcg(reinterpret_cast<const float4*>(a.actT_hi + ((size_t)la * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + 4 * bq));
+    };
+    float4 act_next[4];
+    fetch_act(0, 0, 0, act_next);
+    int it = 0;
+    long long j = 0;
+    for (int fi = 0; fi < T; ++fi)
+    for (int u = 0; u < K; ++u)
+    for (int i = 0; i < n_tiles; ++i, ++j) {
+      const int t = T - 1 - fi;
+      const int la = (u == 0) ? K - 1 : K - u - 1;           // layer of the delta this item produces
+      float4 act4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) act4[e] = act_next[e];
+      {
+        int i2 = i + 1, u2 = u, f2 = fi;
+        if (i2 == n_tiles) { i2 = 0; if (++u2 == K) { u2 = 0; ++f2; } }
+        fetch_act(f2, u2, i2, act_next);
+      }
+      float d[4][4];                                          // [row e][batch bi]
+      if (u == 0) {
+        if (fi > 0) {
+          const unsigned int target = (unsigned int)a.KS * (unsigned int)(fi * K);
+          if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) atomicCAS(a.dev_error, 0, 219);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
+          float s0 = 0.f, s1 = 0.f;
+          const float* ps = a.psum2 + (size_t)((fi - 1) & 1) * 256 * 2 * a.Bp + i * NB + b;
+          for (int c = part; c < n_cta; c += nparts) { s0 += __ldcg(ps + (size_t)c * 2 * a.Bp); s1 += __ldcg(ps + (size_t)c * 2 * a.Bp + a.Bp); }
+          part_s[part * NB + b] = a.o0_b * s0 + a.ok_b * s1;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (otid < NB) {
+            float tot = 0.f;
+            for (int p = 0; p < nparts; ++p) tot += part_s[p * NB + otid];
+            add_s[i * NB + otid] = tot;
+          }
+        }
+        if (otid < NB) rk_acc[i * NB + otid] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (bv) {
+#pragma unroll
+          for (int bi = 0; bi < 4; ++bi) {
+            const int bl = 4 * bq + bi, b = i * NB + bl;
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float dg[4] = {0.f, 0.f, 0.f, 0.f};
+            if (b < a.B) {
+              const size_t bt = (size_t)b * T + t;
+              if (fi > 0) {
+                g4 = __ldcg(reinterpret_cast<const float4*>(a.G + (size_t)b * Rp + rowq));
+                if (__ldg(a.mvalid + bt + 1) != 0.f) {          // frame t+1 was valid: its state gradient is complete now
+                  const float ad = add_s[i * NB + bl];
+                  g4.x = (rowq + 0 < a.R) ? g4.x + ad : 0.f; g4.y = (rowq + 1 < a.R) ? g4.y + ad : 0.f;
+                  g4.z = (rowq + 2 < a.R) ? g4.z + ad : 0.f; g4.w = (rowq + 3 < a.R) ? g4.w + ad : 0.f;
+                  __stcg(reinterpret_cast<float4*>(a.G + (size_t)b * Rp + rowq), g4);
+                }
+              }
+              if (__ldg(a.mvalid + bt) != 0.f) {
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(a.dH + bt * Rp + rowq));
+                dg[0] = h4.x + g4.x; dg[1] = h4.y + g4.y; dg[2] = h4.z + g4.z; dg[3] = h4.w + g4.w;
+              }
+            }
+            d[0][bi] = dg[0]; d[1][bi] = dg[1]; d[2][bi] = dg[2]; d[3][bi] = dg[3];
+          }
+        }
+      } else {
+        const int rs = it % a.RST;
+        if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
+        if (!mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 220);
+        const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
+        uint32_t qaddr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = 4 * rq + e;
+          qaddr[e] = red + (uint32_t)(r * (NB * 4) + ((bq & ~SWZ) | ((bq ^ r) & SWZ)) * 16);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) d[e][0] = d[e][1] = d[e][2] = d[e][3] = 0.f;
+        const uint32_t src_stride = (uint32_t)(RO * NB * 4);
+#pragma unroll 2
+        for (int src = 0; src < a.KS; ++src) {
+          float4 ld[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ld[e].x), "=f"(ld[e].y), "=f"(ld[e].z), "=f"(ld[e].w)
+                         : "r"(qaddr[e] + src * src_stride));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { d[e][0] += ld[e].x; d[e][1] += ld[e].y; d[e][2] += ld[e].z; d[e][3] += ld[e].w; }
+        }
+        __syncwarp();
+        if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);
+        ++it;
+      }
+      // ---- mask with the stored activation, store both layouts, row-sum partials ----
+      float psb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (bv) {
+        const float av[4][4] = {{act4[0].x, act4[0].y, act4[0].z, act4[0].w}, {act4[1].x, act4[1].y, act4[1].z, act4[1].w},
+                                {act4[2].x, act4[2].y, act4[2].z, act4[2].w}, {act4[3].x, act4[3].y, act4[3].z, act4[3].w}};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int bi = 0; bi < 4; ++bi) {
+            const bool keep = (av[e][bi] > 0.f) && (rowq + e < a.R) && (i * NB + 4 * bq + bi < a.B);
+            d[e][bi] = keep ? d[e][bi] : 0.f;
+            psb[bi] += d[e][bi];
+          }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {                          // transposed (time-major) copy for the weight gradients
+          const size_t o3 = ((size_t)la * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + 4 * bq;
+          __stcg(reinterpret_cast<float4*>(a.deltaT_hi + o3), make_float4(d[e][0], d[e][1], d[e][2], d[e][3]));
+          __stcg(reinterpret_cast<float4*>(a.deltaT_lo + o3), make_float4(tf32_lo(d[e][0]), tf32_lo(d[e][1]), tf32_lo(d[e][2]), tf32_lo(d[e][3])));
+        }
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi) {
+          const int b = i * NB + 4 * bq + bi;
+          if (la > 0) {                                        // operand of the next product
+            const size_t o2 = ((size_t)(u & 1) * a.Bp + b) * Rp + rowq;
+            __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(d[0][bi], d[1][bi], d[2][bi], d[3][bi]));
+            __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(d[0][bi]), tf32_lo(d[1][bi]), tf32_lo(d[2][bi]), tf32_lo(d[3][bi])));
+          } else if (b < a.B && __ldg(a.mvalid + (size_t)b * T + t) != 0.f) {
+            // delta^0: start of the new state gradient  G = (d0-o0) delta^0 (+ rank-1 terms added at the next frame start)
+            __stcg(reinterpret_cast<float4*>(a.G + (size_t)b * Rp + rowq),
+                   make_float4(a.d0mo_b * d[0][bi], a.d0mo_b * d[1][bi], a.d0mo_b * d[2][bi], a.d0mo_b * d[3][bi]));
+          }
+        }
+        const int pb = (int)(j & 1);
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi) part_s[(pb * RQ + rq) * NB + 4 * bq + bi] = psb[bi];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (otid < NB) {
+        const int pb = (int)(j & 1);
+        float sum = 0.f;
+        for (int q2 = 0; q2 < RQ; ++q2) sum += part_s[(pb * RQ + q2) * NB + otid];
+        if (la > 0) rk_acc[i * NB + otid] += sum;
+        if (la == 0 || K == 1) {
+          float* ps = a.psum2 + (size_t)(fi & 1) * 256 * 2 * a.Bp + (size_t)cta_lin * 2 * a.Bp + i * NB + otid;
+          __stcg(ps, (la == 0) ? sum : 0.f);
+          __stcg(ps + a.Bp, rk_acc[i * NB + otid]);
+        }
+      }
+      const int ps_ = (int)(j % RT_PST);
+      if (!mbar_wait(&bars->pub_empty[ps_], (uint32_t)(((j / RT_PST) & 1) ^ 1), err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 222);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->pub_full[ps_]);
+    }
+  }
   if (warp >= 12) {
     // ================= weight loaders: S_k^T[m*128 + row][s*KSLICE ..] -> registers -> (hi | lo) in TMEM =================
     const int q = warp - 12;                          // TMEM lane quarter (warp % 4)
@@ -509,7 +685,8 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nchunk = a.KSLICE / 32;
     for (int ms = 0; ms < n_mma_steps; ++ms) {
-      const int k = ms % (K - 1) + 1;
+      // forward walks the layers 1..K-1 of every frame, backward K-1..1 (S_k is symmetric for scalar alph)
+      const int k = BWD ? (K - 1 - ms % (K - 1)) : (ms % (K - 1) + 1);
       const float* src = a.ST + ((size_t)(k - 1) * Rp + (size_t)m * 128 + row) * Rp + (size_t)s * a.KSLICE;
       float v[32];
       // first chunk is fetched before waiting for the buffer (latency of L2 overlaps the previous step's tail)
@@ -569,7 +746,7 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
   if (p.KSLICE > 128) { p.why = "K-slice wider than 128 atoms: weights (hi|lo) do not fit the 256 TMEM columns reserved for them"; return p; }
   if (p.RO * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
   const int h_stage = 2 * p.ATOMS * p.NB * 128, red_slot = 128 * p.NB * 4;   // slot = KS blocks of RO x NB fp32
-  const int leak_b = round_up(p.n_tiles * p.NB * 4, 128), out_b = round_up(max(p.NB * (p.RO + 1), 128) * 4, 128);
+  const int leak_b = round_up(2 * p.n_tiles * p.NB * 4, 128), out_b = round_up(max(p.NB * (p.RO + 1), 128) * 4, 128);
   const int fixed = leak_b + out_b + (int)sizeof(RecBars) + 256;
   const int budget = 232448 - 1024 - fixed;
   // every reduction slot has a twin staging slot on the pusher side (same index), hence 2 * red_slot per depth
@@ -600,7 +777,7 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
 // co-resident clusters the device offers for this plan (the kernel spins on peers: all CTAs must be resident)
 template <int NB>
 static int rec_max_clusters(const RecPlan& p, int* out) {
-  auto kern = k_recurrent_tc<NB>;
+  auto kern = k_recurrent_tc<NB, false>;
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
   cudaLaunchConfig_t cfg{};
@@ -617,9 +794,9 @@ static int rec_max_clusters(const RecPlan& p, int* out) {
   return DRNMF_OK;
 }
 
-template <int NB>
+template <int NB, bool BWD>
 static int launch_rec(const RecPlan& p, const CUtensorMap& tH_hi, const CUtensorMap& tH_lo, cudaStream_t st) {
-  auto kern = k_recurrent_tc<NB>;
+  auto kern = k_recurrent_tc<NB, BWD>;
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
   cudaLaunchConfig_t cfg{};
@@ -636,10 +813,9 @@ static int launch_rec(const RecPlan& p, const CUtensorMap& tH_hi, const CUtensor
   return DRNMF_OK;
 }
 
-int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
-  const int K = h->K, Rp = h->Rp;
-  // Candidate tilings, preferred first: more K-splits = more SMs streaming the weights; the cluster (= the K-splits of
-  // one M-tile) must be co-resident MT times, which depends on the board's GPC layout -> ask the occupancy API.
+// Candidate tilings, preferred first: more K-splits = more SMs streaming the weights; the cluster (= the K-splits of
+// one M-tile) must be co-resident MT times, which depends on the board's GPC layout -> ask the occupancy API.
+static RecPlan choose_plan(const drnmf_handle* h, int B) {
   RecPlan p{};
   p.ok = false; p.why = "no candidate tiling";
   const char* env_ks = getenv("DRNMF_REC_KS");
@@ -657,10 +833,45 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
       p = c;
     }
   }
-  if (!p.ok || p.n_tiles * p.MT > 16384) {
+  if (p.ok && p.n_tiles * p.MT > 16384) { p.ok = false; p.why = "too many batch tiles"; }
+  return p;
+}
+
+// Backward chain on the persistent kernel.  Returns 1 (no error set) when the shape is not covered and the caller
+// should use the CUDA-core chain instead.
+int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,
+                            float* deltaT_lo, float* G, float* psum2, cudaStream_t st) {
+  const int K = h->K, Rp = h->Rp;
+  if (K < 2 || h->alph_dim != 1) return 1;
+  RecPlan p = choose_plan(h, B);
+  if (!p.ok) return 1;
+  RecArgs& a = p.a;
+  a.XW = nullptr; a.mvalid = w.mvalid; a.h0 = h->h0;
+  a.state = nullptr; a.psum = nullptr; a.Hp_hi = nullptr; a.Hp_lo = nullptr; a.H_user = nullptr;
+  a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
+  a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo;
+  a.dH = dH; a.deltaT_hi = deltaT_hi; a.deltaT_lo = deltaT_lo; a.G = G; a.psum2 = psum2;
+  a.d0mo_b = h->u0_d - h->u0_o; a.o0_b = h->u0_o; a.ok_b = h->uk_o;
+  a.dbg = nullptr;
+  a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
+  a.u0_dmo = 0.f; a.u0_off = 0.f; a.uk_dmo = 0.f; a.uk_off = 0.f;
+  a.ST = h->ST_hi;
+  DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles * p.MT, st));
+  CUtensorMap tH_hi, tH_lo;
+  int rc;
+  if ((rc = make_tmap_2d(&tH_hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
+  if ((rc = make_tmap_2d(&tH_lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
+  return (p.NB == 16) ? launch_rec<16, true>(p, tH_hi, tH_lo, st)
+       : (p.NB == 32) ? launch_rec<32, true>(p, tH_hi, tH_lo, st) : launch_rec<64, true>(p, tH_hi, tH_lo, st);
+}
+
+int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
+  const int K = h->K, Rp = h->Rp;
+  RecPlan p = choose_plan(h, B);
+  if (!p.ok) {
     // Shapes the persistent kernel does not cover yet run on the CUDA-core recurrence (still on the GPU).
     static bool warned = false;
-    if (!warned) { fprintf(stderr, "[libdrnmf] persistent tcgen05 recurrence unavailable (%s); using the SIMT recurrence\n", p.ok ? "too many tiles" : p.why); warned = true; }
+    if (!warned) { fprintf(stderr, "[libdrnmf] persistent tcgen05 recurrence unavailable (%s); using the SIMT recurrence\n", p.why); warned = true; }
     h->last_rec_impl = 1;
     return launch_recurrent_simt(h, w, B, T, H_user, st);
   }
@@ -684,8 +895,8 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   int rc;
   if ((rc = make_tmap_2d(&tH_hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
   if ((rc = make_tmap_2d(&tH_lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
-  rc = (p.NB == 16) ? launch_rec<16>(p, tH_hi, tH_lo, st)
-     : (p.NB == 32) ? launch_rec<32>(p, tH_hi, tH_lo, st) : launch_rec<64>(p, tH_hi, tH_lo, st);
+  rc = (p.NB == 16) ? launch_rec<16, false>(p, tH_hi, tH_lo, st)
+     : (p.NB == 32) ? launch_rec<32, false>(p, tH_hi, tH_lo, st) : launch_rec<64, false>(p, tH_hi, tH_lo, st);
   if (rc == DRNMF_OK && want_dbg) {
     long long d[16 * 8];
     DRNMF_CUDA(cudaMemcpyAsync(d, dbg_dev, sizeof(d), cudaMemcpyDeviceToHost, st));

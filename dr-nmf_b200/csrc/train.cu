@@ -28,6 +28,7 @@ struct TrainWs {
   float *xT_hi, *xT_lo;        // Fx x TB     masked input transposed (time-major) + a row of ones (bias gradient)
   float *deltaT_hi, *deltaT_lo;// K x Rp x TB dL/dz^k
   float *G, *dbuf;             // Bp x Rp ; 2 x Bp x Rp   state-gradient carry ; delta ping-pong (frame-major)
+  float *psum2;                // 2 x 256 x 2 x Bp  partial row sums of the persistent backward chain
   float *rs_part;              // K x NC x Bp  partial row sums of delta^k (rank-1 leak gradient), NC = Rp/64 column tiles
   float *part;                 // split-K partials (max over the GEMMs that use them)
   float *gsym_hi, *gsym_lo;    // Rp x Rp
@@ -59,6 +60,7 @@ static TrainWs carve_train(const drnmf_handle* h, int B, int T, void* base) {
   w.xT_hi = (float*)take((size_t)w.Fx * TB * 4); w.xT_lo = (float*)take((size_t)w.Fx * TB * 4);
   w.deltaT_hi = (float*)take(K * Rp * TB * 4); w.deltaT_lo = (float*)take(K * Rp * TB * 4);
   w.G = (float*)take(Bp * Rp * 4); w.dbuf = (float*)take(2 * Bp * Rp * 4);
+  w.psum2 = (float*)take(2 * 256 * 2 * Bp * 4);
   w.rs_part = (float*)take(K * (Rp / SIMT_BN) * Bp * 4);
   const int kb = (int)(TB / 32);
   w.splits_w = kb >= 256 ? 8 : (kb >= 64 ? 4 : (kb >= 16 ? 2 : 1));
@@ -266,6 +268,22 @@ __global__ void k_bwd_frame_end(BwdArgs a) {
     a.G[(size_t)b * a.Rp + j] = (j < a.R) ? a.d0mo * d0[(size_t)b * a.Rp + j] + add : 0.f;
 }
 
+// persistent backward chain: the rank-1 terms of the LAST processed frame (t = 0) are still missing from G
+__global__ void k_bwd_finalize_G(float* __restrict__ G, const float* __restrict__ psum2, const float* __restrict__ mvalid,
+                                 int T, int Bp, int R, int Rp, int n_cta, int parity, float o0, float ok) {
+  const int b = blockIdx.x;
+  if (mvalid[(size_t)b * T] == 0.f) return;
+  __shared__ float add;
+  if (threadIdx.x == 0) {
+    float s0 = 0.f, s1 = 0.f;
+    const float* ps = psum2 + (size_t)parity * 256 * 2 * Bp + b;
+    for (int c = 0; c < n_cta; ++c) { s0 += ps[(size_t)c * 2 * Bp]; s1 += ps[(size_t)c * 2 * Bp + Bp]; }
+    add = o0 * s0 + ok * s1;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < R; j += blockDim.x) G[(size_t)b * Rp + j] += add;
+}
+
 // ---- parameter chain -------------------------------------------------------------------------------------------------
 // P = sum over splits of the partial dS_k^T (Rp x Rp).  Gsym[j][i] = -(P[j][i]/alph_j + P[i][j]/alph_i) (hi, lo) and the
 // per-row partial of  d log alph (S term) = sum_i P[j][i] (delta_ij - S^T[j][i]).  grid (Rp/32, Rp/32), block (32,8)
@@ -445,7 +463,22 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   ba.G = w.G; ba.dbuf = w.dbuf; ba.rs_part = w.rs_part; ba.B = B; ba.Bp = Bp; ba.T = T; ba.K = K; ba.R = R; ba.Rp = Rp; ba.TB = TB;
   ba.d0mo = h->u0_d - h->u0_o; ba.o0 = h->u0_o; ba.ok = h->uk_o; ba.nc = Rp / SIMT_BN;
   const dim3 gstep(Rp / SIMT_BN, (B + SIMT_BM - 1) / SIMT_BM);
-  for (int t = T - 1; t >= 0; --t) {
+  int bwd_rc = 1;
+  {
+    bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
+    const char* e = getenv("DRNMF_RECURRENT");
+    if (e && !strcmp(e, "simt")) rec_simt = true;
+    if (!rec_simt) {
+      bwd_rc = launch_recurrent_bwd_tc(h, w.fwd, B, T, w.dH, w.deltaT_hi, w.deltaT_lo, w.G, w.psum2, st);
+      if (bwd_rc != 0 && bwd_rc != 1) return bwd_rc;
+      if (bwd_rc == 0) {
+        const int KSx = h->rec_cfg[1], MTx = h->rec_cfg[2];
+        k_bwd_finalize_G<<<B, 128, 0, st>>>(w.G, w.psum2, w.fwd.mvalid, T, Bp, R, Rp, KSx * MTx, (T - 1) & 1, h->u0_o, h->uk_o);
+        count_launch();
+      }
+    }
+  }
+  for (int t = T - 1; t >= 0 && bwd_rc == 1; --t) {
     ba.t = t; ba.k = K - 1; ba.ST = nullptr;
     k_bwd_frame_begin<<<B, 256, 0, st>>>(ba);
     for (int k = K - 1; k >= 1; --k) {
