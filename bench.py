@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--throughput-batch", type=int, default=0,
                     help="also time a large device-resident batch (reported under config.throughput_mode)")
+    ap.add_argument("--extras", action="store_true",
+                    help="also time a training step (B=32) and sparse-NMF iterations (reported under config.extras)")
     return ap.parse_args()
 
 
@@ -308,6 +310,45 @@ def main():
                                      "recurrence_ms": float(st_t[2]),
                                      "recurrence_useful_tflops": fl_rec * Bt * T / (float(st_t[2]) / 1e3) / 1e12,
                                      "recurrence": eng.recurrent_config()}
+
+    if args.extras and rank == 0 and world == 1:
+        ex = {}
+        Bt = 32
+        xt, yt = x_dev[:Bt].contiguous(), (x_dev[:Bt] * 0.5).contiguous()
+        eng.loss_and_grads(xt, yt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.loss_and_grads(xt, yt)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        ex["training_step"] = {"B": Bt, "T": T, "ms": 1e3 * dt, "frames_per_s": Bt * T / dt,
+                               "note": "forward with stored activations + loss + BPTT + weight-gradient GEMMs + parameter chain"}
+        n_mu = 22528
+        V = torch.rand(F, n_mu, device=dev) * 4
+        Wm = torch.rand(F, R, device=dev) + 0.1
+        Hm = torch.rand(R, n_mu, device=dev) + 0.1
+        engine.snmf_mu_ed(V, Wm, Hm, 1.0, 2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        engine.snmf_mu_ed(V, Wm, Hm, 1.0, 10)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 10
+        ex["snmf_mu_ed"] = {"F": F, "R": R, "n_frames": n_mu, "ms_per_iteration": 1e3 * dt,
+                            "useful_tflops": 12.0 * F * R * n_mu / dt / 1e12,
+                            "note": "W and H updated; includes one host sync per iteration for the convergence test"}
+        config["extras"] = ex
+
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("B") == B and tj.get("T") == T and tj.get("R") == R and tj.get("K_layers") == K:
+            traffic = tj["dram_bytes_per_launch"]
+            roofline["traffic_source"] = tj.get("source")
+    except Exception:
+        pass
+    roofline["traffic"] = traffic
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -261,6 +261,20 @@ __device__ __forceinline__ unsigned int flag_ld_acquire(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+// L2 residency hints: the per-layer weights (96 MB at R=1000, K=25) are re-read every frame and should stay in the
+// 126 MB L2 (evict_last); the input projections are read once and should not displace them (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float4 ldg_hint4(const float* ptr, uint64_t policy) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr), "l"(policy));
+  return r;
+}
 #endif  // __CUDACC__
 
 }  // namespace drnmf

@@ -316,6 +316,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     }
     // x~W_k + b_k of an item does not depend on the recurrence: fetched one item ahead, unconditionally from clamped
     // addresses, and only consumed an iteration later, so the in-order warp never waits on a load it just issued.
+    const uint64_t pol_x = l2_policy_evict_first();
     auto fetch_xw = [&](int t, int k, int i, float4 (&xa)[MAXB][4]) {
       const int tc = t < T ? t : T - 1;
 #pragma unroll
@@ -323,7 +324,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 #pragma unroll
         for (int bi = 0; bi < 4; ++bi) {
           int b = i * NB + 4 * blk_bq[c] + bi; b = b < a.B ? b : a.B - 1;
-          xa[c][bi] = __ldg(reinterpret_cast<const float4*>(a.XW + ((size_t)b * T + tc) * KRp + (size_t)k * Rp + row0 + 4 * blk_rq[c]));
+          xa[c][bi] = ldg_hint4(a.XW + ((size_t)b * T + tc) * KRp + (size_t)k * Rp + row0 + 4 * blk_rq[c], pol_x);
         }
     };
     float4 xa_next[MAXB][4];
@@ -684,6 +685,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int nchunk = a.KSLICE / 32;
+    const uint64_t pol_w = l2_policy_evict_last();
     for (int ms = 0; ms < n_mma_steps; ++ms) {
       // forward walks the layers 1..K-1 of every frame, backward K-1..1 (S_k is symmetric for scalar alph)
       const int k = BWD ? (K - 1 - ms % (K - 1)) : (ms % (K - 1) + 1);
@@ -692,7 +694,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       // first chunk is fetched before waiting for the buffer (latency of L2 overlaps the previous step's tail)
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(src) + c4);
+        const float4 f = ldg_hint4(src + 4 * c4, pol_w);
         v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
       }
       bool okl;
@@ -708,7 +710,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (ch + 1 < nchunk) {
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(src + (ch + 1) * 32) + c4);
+            const float4 f = ldg_hint4(src + (ch + 1) * 32 + 4 * c4, pol_w);
             v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
           }
         }
