@@ -90,7 +90,12 @@ template <int EPI> struct TcCfg {
   static constexpr int STAGES = DUAL ? 2 : 3;
   static constexpr int STAGE_BYTES = TILES_PER_STAGE * TC_TILE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr uint32_t TMEM_COLS = DUAL ? 256 : 128;
+  // tcgen05 accumulates with round-toward-zero: a long chain of MMAs into one accumulator is biased low by about half an
+  // ulp per instruction.  The k-blocks are therefore dealt round-robin to NACC independent TMEM accumulators (all 512
+  // columns) that the epilogue adds in fp32 round-to-nearest: chains are NACC times shorter, so is the bias.
+  static constexpr int NACC = DUAL ? 2 : 4;
+  static constexpr uint32_t ACC_COLS = DUAL ? 256 : 128;
+  static constexpr uint32_t TMEM_COLS = 512;
 };
 
 template <int EPI>
@@ -169,19 +174,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const uint64_t a_lo = umma_desc_k128(st + 1 * TC_TILE_BYTES + koff);
           const uint64_t b_hi = umma_desc_k128(st + 2 * TC_TILE_BYTES + koff);
           const uint64_t b_lo = umma_desc_k128(st + 3 * TC_TILE_BYTES + koff);
-          const bool first = (kb == 0 && ks == 0);
+          const bool first = (kb < Cfg::NACC && ks == 0);          // first MMA into this accumulator overwrites
+          const uint32_t acc_t = tmem_base + (uint32_t)(kb % Cfg::NACC) * Cfg::ACC_COLS;
           if (leader) {
-            umma_tf32(tmem_base, a_lo, b_hi, idesc, !first);
-            umma_tf32(tmem_base, a_hi, b_lo, idesc, true);
-            umma_tf32(tmem_base, a_hi, b_hi, idesc, true);
+            umma_tf32(acc_t, a_lo, b_hi, idesc, !first);
+            umma_tf32(acc_t, a_hi, b_lo, idesc, true);
+            umma_tf32(acc_t, a_hi, b_hi, idesc, true);
           }
           if (Cfg::DUAL) {
             const uint64_t c_hi = umma_desc_k128(st + 4 * TC_TILE_BYTES + koff);
             const uint64_t c_lo = umma_desc_k128(st + 5 * TC_TILE_BYTES + koff);
             if (leader) {
-              umma_tf32(tmem_base + TC_BN, a_lo, c_hi, idesc, !first);
-              umma_tf32(tmem_base + TC_BN, a_hi, c_lo, idesc, true);
-              umma_tf32(tmem_base + TC_BN, a_hi, c_hi, idesc, true);
+              umma_tf32(acc_t + TC_BN, a_lo, c_hi, idesc, !first);
+              umma_tf32(acc_t + TC_BN, a_hi, c_lo, idesc, true);
+              umma_tf32(acc_t + TC_BN, a_hi, c_hi, idesc, true);
             }
           }
         }
@@ -207,6 +213,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         tmem_ld16(trow + c, v);
         if (Cfg::DUAL) tmem_ld16(trow + TC_BN + c, v2);
         tc_wait_ld();
+        const int nacc = num_kb < Cfg::NACC ? num_kb : Cfg::NACC;   // accumulators that received at least one k-block
+        for (int q2 = 1; q2 < nacc; ++q2) {
+          float t1[16], t2[16];
+          tmem_ld16(trow + q2 * Cfg::ACC_COLS + c, t1);
+          if (Cfg::DUAL) tmem_ld16(trow + q2 * Cfg::ACC_COLS + TC_BN + c, t2);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] += t1[i]; if (Cfg::DUAL) v2[i] += t2[i]; }
+        }
+        if (num_kb == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] = 0.f; v2[i] = 0.f; }
+        }
         const int n = n0 + c;
         if (m < a.M_valid) {
           if (EPI == EPI_STORE) {

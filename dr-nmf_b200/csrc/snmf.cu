@@ -39,7 +39,11 @@ static SnmfWs carve_snmf(int F, int n, int R, void* base) {
   SnmfWs w;
   w.Fk = round_up(F, 32); w.Rk = round_up(R, 32); w.nk = round_up(n, 128);
   int total_kb = w.nk / 32;
-  w.splits = total_kb >= 64 ? 16 : (total_kb >= 8 ? 4 : 1);
+  // split-K: parallelism for the 5 x 8 output tiles AND short tensor-core accumulation chains (<= 64 k-blocks per split,
+  // dealt to 4 accumulators: the round-toward-zero bias of tcgen05 accumulation grows with the chain length)
+  w.splits = total_kb >= 64 ? (total_kb + 63) / 64 : (total_kb >= 8 ? 4 : 1);
+  if (w.splits < 16 && total_kb >= 64) w.splits = 16;
+  if (w.splits > 128) w.splits = 128;
   uint8_t* p = (uint8_t*)base;
   size_t off = 0;
   auto take = [&](size_t bytes) { void* q = p ? p + off : nullptr; off += al256(bytes); return q; };

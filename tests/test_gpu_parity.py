@@ -466,3 +466,18 @@ def test_full_size_batch_independence_and_impl_agreement():
     for b in range(0, B, 7):                                                  # masked frames carry the state
         for t in range(lens[b], T):
             assert np.array_equal(Hn[b, t], Hn[b, lens[b] - 1])
+
+
+def test_snmf_long_contraction_vs_oracle():
+    """Frames-long contractions (V H^T, L H^T over n = 4096 frames: split-K + multi-accumulator path) against float64."""
+    F, n, R, iters = 129, 4096, 200, 8
+    rng = np.random.default_rng(7)
+    V = (np.abs(rng.standard_normal((F, n))) * 2).astype(np.float32)
+    W0 = (np.abs(rng.standard_normal((F, R))) + 0.1).astype(np.float32)
+    H0 = (np.abs(rng.standard_normal((R, n))) + 0.1).astype(np.float32)
+    prm = {"cf": "ed", "sparsity": 1.0, "max_iter": iters, "conv_eps": 0.0, "r": R, "init_w": W0, "init_h": H0}
+    Wo, Ho, obj = O.sparse_nmf_ed(V, prm, dtype=np.float64)
+    Vd, Wd, Hd = (torch.as_tensor(a, device="cuda") for a in (V, W0.copy(), H0.copy()))
+    cost, div = engine.snmf_mu_ed(Vd, Wd, Hd, 1.0, iters, 0.0)
+    assert max(rel_err(Wd.cpu().numpy(), Wo)) < TOL and max(rel_err(Hd.cpu().numpy(), Ho)) < TOL
+    np.testing.assert_allclose(cost, obj["cost"], rtol=2e-5)
