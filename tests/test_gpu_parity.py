@@ -82,6 +82,7 @@ def test_derived_weights(impl):
     dict(F=129, R=200, K=5, B=3, T=9, alph=50.0),           # reference-like r=100 (Rp=256)
     dict(F=257, R=200, K=2, B=70, T=6, alph=50.0),          # B above one batch tile
     dict(F=33, R=16, K=1, B=2, T=5, alph=10.0),             # single layer: no Gram term at all
+    dict(F=65, R=1200, K=3, B=5, T=4, alph=300.0),          # R > 1024: weights stream through TMEM in several chunks
 ])
 def test_forward_vs_oracle(shape, impl):
     F, R, K, B, T = (shape[k] for k in "FRKBT")
