@@ -23,6 +23,8 @@ class DrnmfError(RuntimeError):
         self.code = code
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+
 _lib = None
 
 
@@ -64,6 +66,8 @@ def load():
         "drnmf_enhance_workspace_bytes": (sz, [vp, i32, i32, i32, i32]),
         "drnmf_snmf_mu_ed": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, C.POINTER(i32), i32, vp, sz, vp]),
         "drnmf_snmf_workspace_bytes": (sz, [i32, i32, i32]),
+        "drnmf_snmf_mu_ed_dist": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, C.POINTER(i32), i32, vp, sz, vp,
+                                        ALLREDUCE_FN, vp]),
         "drnmf_ista_ed": (i32, [i32, i32, i32, vp, vp, vp, f32, f32, i32, i32, vp, sz, vp]),
         "drnmf_ista_workspace_bytes": (sz, [i32, i32, i32]),
         "drnmf_loss_and_grads": (i32, [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),

@@ -76,6 +76,19 @@ int drnmf_version(void) { return 100; }
 const char* drnmf_last_error(void) { return drnmf::last_error(); }
 unsigned long long drnmf_launch_count(void) { return drnmf::launch_count(); }
 
+// R is padded with zero atoms (exact: a zero atom never activates, prep.cu) to the next multiple of 128 for which the
+// persistent recurrence has a tiling: K-splits of at most 128 atoms, or of 256/384/512 streamed through TMEM in
+// 128-column chunks (plan_recurrent, recurrent_tc.cu).  Beyond 2048 atoms nothing fits and the pad stays minimal.
+static int padded_atoms(int R, int num_sms) {
+  const int m0 = (R + 127) / 128;
+  for (int m = m0; m <= 16; ++m)
+    for (int KS = 16; KS >= 1; KS >>= 1) {
+      const int ksl = 128 * m / KS;
+      if ((128 * m) % (32 * KS) == 0 && KS * m <= num_sms && (ksl <= 128 || (ksl <= 512 && ksl % 128 == 0))) return 128 * m;
+    }
+  return 128 * m0;
+}
+
 int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags) {
   DRNMF_CHECK(out != nullptr, "drnmf_create: out is NULL");
   *out = nullptr;
@@ -98,7 +111,7 @@ int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags) {
   DRNMF_CHECK(h != nullptr, "out of host memory");
   memset(h, 0, sizeof(*h));
   h->F = F; h->R = R; h->K = K_layers; h->r = R / 2;
-  h->Rp = round_up(R, 128); h->Fp = round_up(F, 32); h->Fq = round_up(F, 128);
+  h->Rp = padded_atoms(R, prop.multiProcessorCount); h->Fp = round_up(F, 32); h->Fq = round_up(F, 128);
   h->flags = flags; h->impl = pick_impl(flags); h->device = dev; h->num_sms = prop.multiProcessorCount;
   const size_t K = K_layers, Rp = h->Rp, Fp = h->Fp, Fq = h->Fq;
   const size_t nS = (K > 1 ? K - 1 : 1);
@@ -306,6 +319,14 @@ size_t drnmf_snmf_workspace_bytes(int F, int n, int R) {
 int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update_host,
                      const uint8_t* h_update_host, float sparsity, int max_iter, float conv_eps, double* cost_host,
                      double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream) {
+  return drnmf_snmf_mu_ed_dist(F, n, R, V, W, H, w_update_host, h_update_host, sparsity, max_iter, conv_eps, cost_host,
+                               div_host, iters_host, flags, ws, ws_bytes, stream, nullptr, nullptr);
+}
+
+int drnmf_snmf_mu_ed_dist(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update_host,
+                          const uint8_t* h_update_host, float sparsity, int max_iter, float conv_eps, double* cost_host,
+                          double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream,
+                          drnmf_allreduce_fn allreduce, void* user) {
   int rc = check_device(nullptr);
   if (rc) return rc;
   DRNMF_CHECK(V && W && H && cost_host && div_host && iters_host && ws, "drnmf_snmf_mu_ed: NULL argument");
@@ -323,7 +344,7 @@ int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, co
   if (h_update_host) { hmask = (uint8_t*)ws + core + al((size_t)R); DRNMF_CUDA(cudaMemcpyAsync(hmask, h_update_host, R, cudaMemcpyHostToDevice, st)); }
   const bool simt = pick_impl(flags) == DRNMF_IMPL_SIMT;
   rc = snmf_mu_ed(F, n, R, V, W, H, wmask, hmask, any_w, any_h, sparsity, max_iter, conv_eps, cost_host, div_host, iters_host,
-                  ws, core, simt, st);
+                  ws, core, simt, st, allreduce, user);
   if (rc) return rc;
   int g = gemm_device_error(st);
   if (g) { set_error("drnmf_snmf_mu_ed: device-side failure code %d in a GEMM kernel", g); return DRNMF_ERR_DEVICE; }

@@ -98,7 +98,8 @@ int launch_mask_istft(const float* stack, const float* mask, const int64_t* fidx
 size_t snmf_workspace_bytes(int F, int n, int R);
 int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
                int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
-               double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st);
+               double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st,
+               drnmf_allreduce_fn allreduce, void* user);
 size_t ista_workspace_bytes(int F, int n, int R);
 int ista_ed(int F, int n, int R, const float* x, const float* W, float* H, float lam1, float alph, int iters, void* ws,
             size_t ws_bytes, bool simt, cudaStream_t st);

@@ -246,9 +246,19 @@ static int run_gemm_impl(bool simt, GemmEpi epi, const GemmArgs& a, cudaStream_t
 
 size_t snmf_workspace_bytes(int F, int n, int R) { return carve_snmf(F, n, R, nullptr).bytes; }
 
+// sum the split-K partials into split 0 (fixed order), so that one buffer per matrix can be all-reduced across ranks
+__global__ void k_reduce_splits(float* __restrict__ part, int splits, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += part[(size_t)s * n + i];
+  part[i] = v;
+}
+
 int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
                int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
-               double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st) {
+               double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st,
+               drnmf_allreduce_fn allreduce, void* user) {
   SnmfWs w = carve_snmf(F, n, R, ws);
   if (ws_bytes < w.bytes) { set_error("snmf workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
   const int Fk = w.Fk, Rk = w.Rk, nk = w.nk;
@@ -317,12 +327,22 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
     if (any_w_update) {
       if ((rc = corr_gemm(w.Vm_hi, w.Vm_lo, w.VHp))) return rc;
       if ((rc = corr_gemm(w.Lm_hi, w.Lm_lo, w.LHp))) return rc;
-      k_mu_w<<<(Rk + 31) / 32, tb, 0, st>>>(w.Wm_hi, w.Wm_lo, w.WT_hi, w.WT_lo, w.VHp, w.LHp, w.splits, F, R, Rk, Fk, flr, w_update);
+      int splits_w = w.splits;
+      if (allreduce) {   // frames are sharded over ranks: V H^T and L H^T are sums over ALL frames
+        const size_t ne = (size_t)F * Rk;
+        k_reduce_splits<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(w.VHp, w.splits, ne);
+        k_reduce_splits<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(w.LHp, w.splits, ne);
+        count_launch(2);
+        if (allreduce(user, w.VHp, ne, 0, st) || allreduce(user, w.LHp, ne, 0, st)) { set_error("all-reduce callback failed"); return DRNMF_ERR_CUDA; }
+        splits_w = 1;
+      }
+      k_mu_w<<<(Rk + 31) / 32, tb, 0, st>>>(w.Wm_hi, w.Wm_lo, w.WT_hi, w.WT_lo, w.VHp, w.LHp, splits_w, F, R, Rk, Fk, flr, w_update);
       count_launch();
       if ((rc = lambda_gemm())) return rc;
     }
     k_mu_cost<<<1, 256, 0, st>>>(w.div_part, n_div, w.hsum_part, n_h, (double)sparsity, w.scal);
     count_launch();
+    if (allreduce && allreduce(user, w.scal, 2, 1, st)) { set_error("all-reduce callback failed"); return DRNMF_ERR_CUDA; }
     double sc[2];
     DRNMF_CUDA(cudaMemcpyAsync(sc, w.scal, sizeof(sc), cudaMemcpyDeviceToHost, st));
     DRNMF_CUDA(cudaStreamSynchronize(st));

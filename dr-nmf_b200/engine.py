@@ -284,7 +284,8 @@ def mask_istft(stack, mask, fidx, N, hop):
 
 
 # ---- sparse NMF multiplicative updates -------------------------------------------------------------
-def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_update=None, impl=None):
+def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_update=None, impl=None, group=None,
+               distributed=False):
     """V (F,n), W (F,R), H (R,n): float32 CUDA tensors (W and H are updated IN PLACE).  w_update / h_update: boolean
     arrays of length R (None = all).  Returns (cost, div) numpy arrays truncated at convergence
     (sparse_nmf_gpu.m:288-296).  Replaces the MATLAB subprocess of snmf.py:88-113."""
@@ -316,9 +317,31 @@ def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_updat
     ws = torch.empty(nb + 256, dtype=torch.uint8, device=V.device)
     off = (-ws.data_ptr()) % 256
     flags = _lib.IMPL_SIMT if impl == "simt" else 0
-    _lib.check(lib.drnmf_snmf_mu_ed(F, n, R, _ptr(V), _ptr(W), _ptr(H), wp, hp, float(sparsity), max_iter, float(conv_eps),
-                                    C.c_void_p(cost.ctypes.data), C.c_void_p(div.ctypes.data), C.byref(iters), flags,
-                                    C.c_void_p(ws.data_ptr() + off), nb, _stream()))
+    import torch.distributed as dist
+    if distributed and not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("snmf_mu_ed(distributed=True) needs an initialised torch.distributed process group")
+    cb = _lib.ALLREDUCE_FN(0)
+    if distributed:
+        # frames (columns of V, H) are sharded over ranks, W is replicated: the library asks for the sums of V H^T,
+        # Lambda H^T and of the cost terms through this callback; the buffers live inside `ws`, so they are exposed to
+        # torch.distributed as zero-copy views of it.
+        base = ws.data_ptr()
+
+        def _allreduce(user, ptr, count, dtype, stream):
+            try:
+                item, tdt = (4, torch.float32) if dtype == 0 else (8, torch.float64)
+                o = int(ptr) - base
+                view = ws[o:o + count * item].view(tdt)
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+                return 0
+            except Exception as e:      # an exception must not unwind through the C frames
+                import sys
+                print("[drnmf] all-reduce callback failed: %r" % (e,), file=sys.stderr)
+                return 1
+        cb = _lib.ALLREDUCE_FN(_allreduce)
+    _lib.check(lib.drnmf_snmf_mu_ed_dist(F, n, R, _ptr(V), _ptr(W), _ptr(H), wp, hp, float(sparsity), max_iter,
+                                         float(conv_eps), C.c_void_p(cost.ctypes.data), C.c_void_p(div.ctypes.data),
+                                         C.byref(iters), flags, C.c_void_p(ws.data_ptr() + off), nb, _stream(), cb, None))
     k = iters.value
     return cost[:k].copy(), div[:k].copy()
 

@@ -128,6 +128,16 @@ DRNMF_API int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, fl
                      const uint8_t* h_update_host, float sparsity, int max_iter, float conv_eps, double* cost_host,
                      double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream);
 DRNMF_API size_t drnmf_snmf_workspace_bytes(int F, int n, int R);
+/* Frame-sharded (multi-GPU) variant: every rank holds a slice of the frames (columns of V and H) and a replica of W.
+ * `allreduce(user, dev_buf, count, dtype, stream)` must sum `count` elements (dtype 0 = float32, 1 = float64) of
+ * dev_buf in place over all ranks, ordered on `stream`, and return 0.  It is called twice per W-update (V H^T and
+ * Lambda H^T, F x ceil32(R) floats each) and once per iteration for (div, mu*sum H); this is the un-chunked reference
+ * algorithm (n_chunks == 1, snmf.py:82-83) with identical results on every rank.  NULL = single process. */
+typedef int (*drnmf_allreduce_fn)(void* user, void* dev_buf, size_t count, int dtype, void* stream);
+DRNMF_API int drnmf_snmf_mu_ed_dist(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update_host,
+                          const uint8_t* h_update_host, float sparsity, int max_iter, float conv_eps, double* cost_host,
+                          double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream,
+                          drnmf_allreduce_fn allreduce, void* user);
 
 /* ---- frame-parallel ISTA with a tied dictionary (enhance.py:402-418 `ista_ed`; defined but never called there) ---
  * x (F,n), W (F,R), H (R,n) in/out, row-major device arrays: H <- max(0, -lam1/alph + H + (1/alph) W^T (x - W H)),

@@ -5,6 +5,7 @@ Tolerances are the ones BASELINE.json's north_star states: relative error <= 1e-
 (Frobenius AND max-abs/max), <= 0.01 dB on the SDR of the reconstructed audio.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -82,7 +83,8 @@ def test_derived_weights(impl):
     dict(F=129, R=200, K=5, B=3, T=9, alph=50.0),           # reference-like r=100 (Rp=256)
     dict(F=257, R=200, K=2, B=70, T=6, alph=50.0),          # B above one batch tile
     dict(F=33, R=16, K=1, B=2, T=5, alph=10.0),             # single layer: no Gram term at all
-    dict(F=65, R=1200, K=3, B=5, T=4, alph=300.0),          # R > 1024: weights stream through TMEM in several chunks
+    dict(F=65, R=1200, K=3, B=5, T=4, alph=300.0),          # R > 1024: padded to 1536, weights stream through TMEM in chunks
+    dict(F=40, R=600, K=3, B=3, T=3, alph=150.0),           # 5 x 128 atoms has no tiling: padded to 768
 ])
 def test_forward_vs_oracle(shape, impl):
     F, R, K, B, T = (shape[k] for k in "FRKBT")
@@ -482,3 +484,18 @@ def test_snmf_long_contraction_vs_oracle():
     cost, div = engine.snmf_mu_ed(Vd, Wd, Hd, 1.0, iters, 0.0)
     assert max(rel_err(Wd.cpu().numpy(), Wo)) < TOL and max(rel_err(Hd.cpu().numpy(), Ho)) < TOL
     np.testing.assert_allclose(cost, obj["cost"], rtol=2e-5)
+
+
+@pytest.mark.gpu
+def test_snmf_frame_sharded():
+    """MU-ED with the frames sharded over 2 GPUs (all-reduce of V H^T, Lambda H^T and the cost) equals the
+    single-GPU solve.  Needs two devices; on a 1-GPU box it is skipped (the gloo CPU tests cover the sharding maths)."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(here, "dist_snmf_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "replicas identical: True" in p.stdout

@@ -74,3 +74,65 @@ def test_data_parallel_gradient_allreduce_gloo():
         assert abs(loss - 6.0 / total_frames) < 1e-12
         torch.testing.assert_close(gD, torch.full((4, 3), 3.0 / total_frames))
         torch.testing.assert_close(gh, torch.arange(3, dtype=torch.float32) * 3.0 / total_frames)
+
+
+def _mu_sharded_worker(rank, world, port, q):
+    """The frame-sharded MU-ED iteration of drnmf_snmf_mu_ed_dist, restated in numpy over gloo: H-update is local to a
+    rank's frames; V H^T, Lambda H^T and (div, sum H) are the only cross-rank sums (snmf.cu)."""
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    F, R, n, iters, mu = 33, 12, 40, 8, 0.7
+    V = np.abs(rng.standard_normal((F, n))) + 0.01
+    W = np.abs(rng.standard_normal((F, R))) + 0.01
+    H = np.abs(rng.standard_normal((R, n))) + 0.01
+    sl = slice(rank * n // world, (rank + 1) * n // world)
+    v, h, flr = V[:, sl], H[:, sl].copy(), 1e-9
+    wn = np.sqrt((W ** 2).sum(0)); w = W / wn; h *= wn[:, None]
+    lam = np.maximum(w @ h, flr)
+    costs = []
+
+    def allsum(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)); dist.all_reduce(t); return t.numpy()
+    for _ in range(iters):
+        h = h * (w.T @ v) / np.maximum(w.T @ lam + mu, flr)
+        lam = np.maximum(w @ h, flr)
+        VH, LH = allsum(v @ h.T), allsum(lam @ h.T)
+        dpw = np.maximum(LH + (VH * w).sum(0, keepdims=True) * w, flr)
+        w = w * (VH + (LH * w).sum(0, keepdims=True) * w) / dpw
+        wn = np.sqrt((w ** 2).sum(0)); w = w / wn
+        lam = np.maximum(w @ h, flr)
+        sc = allsum(np.array([((v - lam) ** 2).sum(), mu * h.sum()]))
+        costs.append(sc[0] + sc[1])
+    q.put((rank, w, h, np.array(costs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_mu_frame_sharding_gloo():
+    """world_size 2: the sharded iteration reproduces the oracle's unsharded MU-ED (W replicated, H sliced, same cost)."""
+    import numpy as np
+    import oracle as O
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mu_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    F, R, n, iters, mu = 33, 12, 40, 8, 0.7
+    V = np.abs(rng.standard_normal((F, n))) + 0.01
+    W = np.abs(rng.standard_normal((F, R))) + 0.01
+    H = np.abs(rng.standard_normal((R, n))) + 0.01
+    w, h, info = O.sparse_nmf_ed(V, dict(sparsity=mu, max_iter=iters, conv_eps=0.0, init_w=W, init_h=H, r=R))
+    for rank, wr, hr, cr in res:
+        np.testing.assert_allclose(wr, w, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(hr, h[:, rank * n // 2:(rank + 1) * n // 2], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(cr, info["cost"], rtol=1e-10)
+    np.testing.assert_array_equal(res[0][1], res[1][1])
