@@ -95,7 +95,7 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int ta
     else { stmt; }                                             \
   } while (0)
 
-template <int NB, bool BWD>
+template <int NB, bool BWD, int CB>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
                const __grid_constant__ CUtensorMap tmW, RecArgs a) {
@@ -332,58 +332,46 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       }
     }
   } else if (warp >= 8 && warp < 12 && !BWD) {
-    // ================= owners: reduce the KS partials of rows [o*RO, (o+1)*RO), epilogue, hand off to the publisher ====
+    // ================= owners: reduce the KS partials of rows [o*RO, (o+1)*RO), epilogue, publish =================
     const int otid = threadIdx.x - 256;              // 0..127
     const int RO = a.RO;
     const int row0 = m * 128 + s * RO;               // first global output row this CTA owns
     const int cta_lin = m * a.KS + s, n_cta = a.MT * a.KS;
     const size_t KRp = (size_t)K * Rp;
-    // The RO x NB outputs of a tile are dealt to ALL 128 threads as blocks of 4 rows x CB batch columns (a thread owns
-    // up to MAXB blocks: 16 outputs).  Partials are read as LDS.(32*CB) over the batch columns, results leave as
-    // float4 over the rows (K-major state).  Within a warp the lanes cover 2 row-quads x 16 column groups: reads of a
-    // row are contiguous (conflict-free with the pusher's swizzle) and the two row-quads fill whole 32-byte sectors
-    // of the stores.
-    constexpr int CB = (NB >= 64) ? 2 : 1;
-    constexpr int MAXB = 4 / CB;
+    // The RO x NB outputs of a tile are dealt to the 128 threads as ONE block of 4 rows x CB batch columns each
+    // (CB = RO*NB/512, chosen by the host; fewer threads work when the tile is smaller).  Partials are read as
+    // LDS.(32*CB) over the batch columns, results leave as float4 over the rows (K-major state).  Within a warp the
+    // lanes cover 2 row-quads x 16 column groups: reads of a row are contiguous (conflict-free with the pusher's
+    // swizzle) and the two row-quads fill whole 32-byte sectors of the stores.
     constexpr int CQ = NB / CB;                      // column groups per row
     constexpr int CQW = (CQ < 16) ? CQ : 16;
     constexpr int CHUNKS = NB / 4;
     constexpr int SWZ = (CHUNKS >= 8) ? 7 : CHUNKS - 1;
-    const int n_blk = (RO / 4) * CQ;                 // a multiple of 32: the number of blocks of a thread is warp-uniform
+    const int n_blk = (RO / 4) * CQ;                 // a multiple of 32: whole warps are active or idle
+    const bool mine = otid < n_blk;
+    const int uu = mine ? otid : 0;
+    const int my_cq = (uu % CQW) + CQW * ((uu / (2 * CQW)) % (CQ / CQW));
+    const int my_rq = ((uu / CQW) % 2) + 2 * (uu / (2 * CQ));
+    const int rowq = row0 + 4 * my_rq;
     // sum_j h0[j]: leak of frame 0 (state = h0 for every utterance), same fixed order in every CTA
     float h0sum = 0.f;
     for (int j = 0; j < a.R; ++j) h0sum += a.h0[j];
-    int blk_cq[MAXB], blk_rq[MAXB];
-    int nb_mine = 0;
-#pragma unroll
-    for (int c = 0; c < MAXB; ++c) {
-      const int u = otid + 128 * c;
-      const bool v = u < n_blk;
-      nb_mine += v ? 1 : 0;
-      const int uu = v ? u : 0;
-      blk_cq[c] = (uu % CQW) + CQW * ((uu / (2 * CQW)) % (CQ / CQW));
-      blk_rq[c] = ((uu / CQW) % 2) + 2 * (uu / (2 * CQ));
-    }
     // x~W_k + b_k of an item does not depend on the recurrence: fetched one item ahead, unconditionally from clamped
     // addresses, and only consumed an iteration later, so the in-order warp never waits on a load it just issued.
     const uint64_t pol_x = l2_policy_evict_first();
-    auto fetch_xw = [&](int t, int k, int i, float4 (&xa)[MAXB][CB]) {
+    auto fetch_xw = [&](int t, int k, int i, float4 (&xa)[CB]) {
       const int tc = t < T ? t : T - 1;
+      if (mine) {
 #pragma unroll
-      for (int c = 0; c < MAXB; ++c)
-        if (c < nb_mine) {
-#pragma unroll
-          for (int bi = 0; bi < CB; ++bi) {
-            int b = i * NB + CB * blk_cq[c] + bi; b = b < a.B ? b : a.B - 1;
-            xa[c][bi] = ldg_hint4(a.XW + ((size_t)b * T + tc) * KRp + (size_t)k * Rp + row0 + 4 * blk_rq[c], pol_x);
-          }
+        for (int bi = 0; bi < CB; ++bi) {
+          int b = i * NB + CB * my_cq + bi; b = b < a.B ? b : a.B - 1;
+          xa[bi] = ldg_hint4(a.XW + ((size_t)b * T + tc) * KRp + (size_t)k * Rp + rowq, pol_x);
         }
+      }
     };
-    float4 xa_next[MAXB][CB];
+    float4 xa_next[CB];
 #pragma unroll
-    for (int c = 0; c < MAXB; ++c)
-#pragma unroll
-      for (int bi = 0; bi < CB; ++bi) xa_next[c][bi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int bi = 0; bi < CB; ++bi) xa_next[bi] = make_float4(0.f, 0.f, 0.f, 0.f);
     fetch_xw(0, 0, 0, xa_next);
     int it = 0;
     long long j = 0;
@@ -392,17 +380,15 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     for (int i = 0; i < n_tiles; ++i, ++j) {
       const bool last = (k == K - 1);
       const float dmo = (k == 0) ? a.u0_dmo : a.uk_dmo, off = (k == 0) ? a.u0_off : a.uk_off;
-      float4 xw[MAXB][CB];
-      float acc[MAXB][4][CB];                          // [block][row e][batch bi]
+      float4 xw[CB];
+      float acc[4][CB];                                // [row e][batch bi]
       long long _ts = dbg_on ? clock64() : 0;
 #pragma unroll
-      for (int c = 0; c < MAXB; ++c)
+      for (int bi = 0; bi < CB; ++bi) {
+        xw[bi] = xa_next[bi];
 #pragma unroll
-        for (int bi = 0; bi < CB; ++bi) {
-          xw[c][bi] = xa_next[c][bi];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[c][e][bi] = 0.f;
-        }
+        for (int e = 0; e < 4; ++e) acc[e][bi] = 0.f;
+      }
       {
         int i2 = i + 1, k2 = k, t2 = t;
         if (i2 == n_tiles) { i2 = 0; if (++k2 == K) { k2 = 0; ++t2; } }
@@ -413,25 +399,23 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       //    one layer earlier into the ping-pong buffer (raw fp32 in the "hi" half);
       //  * k == 0: the recurrent state (written by this thread at the last layer of the previous frame);
       //  * last layer: the Keras mask of the frame.
-      float4 pre[MAXB][CB];
-      float mvp[MAXB][CB];
+      float4 pre[CB];
+      float mvp[CB];
 #pragma unroll
-      for (int c = 0; c < MAXB; ++c)
-#pragma unroll
-        for (int bi = 0; bi < CB; ++bi) {
-          pre[c][bi] = make_float4(0.f, 0.f, 0.f, 0.f);
-          mvp[c][bi] = 0.f;
-          if (c < nb_mine) {
-            const int bcol = i * NB + CB * blk_cq[c] + bi, rowq = row0 + 4 * blk_rq[c];
-            const int bc = bcol < a.B ? bcol : a.B - 1;
-            if (k > 0)
-              pre[c][bi] = __ldcg(reinterpret_cast<const float4*>(a.hb_hi + ((size_t)((k - 1) & 1) * a.Bp + bcol) * Rp + rowq));
-            else
-              pre[c][bi] = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
-                                    : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)bc * Rp + rowq));
-            if (last) mvp[c][bi] = __ldg(a.mvalid + (size_t)bc * T + t);
-          }
+      for (int bi = 0; bi < CB; ++bi) {
+        pre[bi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mvp[bi] = 0.f;
+        if (mine) {
+          const int bcol = i * NB + CB * my_cq + bi;
+          const int bc = bcol < a.B ? bcol : a.B - 1;
+          if (k > 0)
+            pre[bi] = __ldcg(reinterpret_cast<const float4*>(a.hb_hi + ((size_t)((k - 1) & 1) * a.Bp + bcol) * Rp + rowq));
+          else
+            pre[bi] = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
+                               : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)bc * Rp + rowq));
+          if (last) mvp[bi] = __ldg(a.mvalid + (size_t)bc * T + t);
         }
+      }
       if (dbg_on) { long long _n = clock64(); dbg_acc[2] += _n - _ts; _ts = _n; }
       if (k == 0) {
         // ---- frame start: leak[b] = sum_j state[b][j] from the published partial sums of the previous frame ----
@@ -466,109 +450,112 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         // address of (row r, columns CB*cq..) inside a source block: row-major, 16-byte chunk index swizzled by
         // (row & 7); the pusher's row index rho = o*RO + r has the same low 3 bits as r because RO is a multiple of 8.
         const uint32_t src_stride = (uint32_t)(RO * NB * 4);
+        if (mine) {
+          uint32_t qaddr[4];
 #pragma unroll
-        for (int c = 0; c < MAXB; ++c)
-          if (c < nb_mine) {
-            uint32_t qaddr[4];
+          for (int e = 0; e < 4; ++e) {
+            const int r = 4 * my_rq + e, col = CB * my_cq, ch = col >> 2;
+            qaddr[e] = red + (uint32_t)(r * (NB * 4) + ((ch & ~SWZ) | ((ch ^ r) & SWZ)) * 16 + (col & 3) * 4);
+          }
+#pragma unroll 4
+          for (int src = 0; src < a.KS; ++src) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int r = 4 * blk_rq[c] + e, col = CB * blk_cq[c], ch = col >> 2;
-              qaddr[e] = red + (uint32_t)(r * (NB * 4) + ((ch & ~SWZ) | ((ch ^ r) & SWZ)) * 16 + (col & 3) * 4);
-            }
-#pragma unroll 8
-            for (int src = 0; src < a.KS; ++src) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if constexpr (CB == 2) {
-                  float x0, x1;
-                  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(qaddr[e] + src * src_stride));
-                  acc[c][e][0] += x0; acc[c][e][CB - 1] += x1;
-                } else {
-                  float x0;
-                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(qaddr[e] + src * src_stride));
-                  acc[c][e][0] += x0;
-                }
+              const uint32_t ad = qaddr[e] + src * src_stride;
+              if constexpr (CB == 4) {
+                float x0, x1, x2, x3;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(ad));
+                acc[e][0] += x0; acc[e][CB > 1 ? 1 : 0] += x1; acc[e][CB > 2 ? 2 : 0] += x2; acc[e][CB > 3 ? 3 : 0] += x3;
+              } else if constexpr (CB == 2) {
+                float x0, x1;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(ad));
+                acc[e][0] += x0; acc[e][CB > 1 ? 1 : 0] += x1;
+              } else {
+                float x0;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(ad));
+                acc[e][0] += x0;
               }
             }
           }
+        }
         __syncwarp();                                  // this warp has consumed the slot (values are in registers):
         if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);   // 4 warps x KS owners arrivals
         if (dbg_on) { long long _n = clock64(); dbg_acc[3] += _n - _ts; _ts = _n; }
         ++it;
       }
       // ---- fused epilogue: relu(acc + x~W_k + b_k + leak terms), Keras mask carry on the last layer ----
+      if (mine) {
+        float gall[CB][4];                             // [batch bi][row e] kept for the transposed activation store
 #pragma unroll
-      for (int c = 0; c < MAXB; ++c) {
-        if (c < nb_mine) {
-          const int rowq = row0 + 4 * blk_rq[c];
-          float gall[CB][4];                           // [batch bi][row e] kept for the transposed activation store
-#pragma unroll
-          for (int bi = 0; bi < CB; ++bi) {
-            const int bl = CB * blk_cq[c] + bi, b = i * NB + bl;
-            const float lkv = off * leak_s[i * NB + bl];
-            const float pv[4] = {pre[c][bi].x, pre[c][bi].y, pre[c][bi].z, pre[c][bi].w};
-            const float xv[4] = {xw[c][bi].x, xw[c][bi].y, xw[c][bi].z, xw[c][bi].w};
-            float sv[4] = {0.f, 0.f, 0.f, 0.f};        // state entering the frame (only for U with d != o beyond layer 0)
-            if (k > 0 && dmo != 0.f && b < a.B) {
-              const float4 so = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
-                                         : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)b * Rp + rowq));
-              sv[0] = so.x; sv[1] = so.y; sv[2] = so.z; sv[3] = so.w;
-            }
-            float g[4], stn[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const bool valid = (b < a.B) && (rowq + e < a.R);
-              // k == 0: pre = state, weighted by the diagonal excess of U_0;  k > 0: pre = g^{k-1} (identity of S_k)
-              const float base = (k == 0) ? dmo * pv[e] : (pv[e] + dmo * sv[e]);
-              g[e] = valid ? fmaxf(acc[c][e][bi] + xv[e] + lkv + base, 0.f) : 0.f;
-              gall[bi][e] = g[e];
-            }
-            if (!last) {
-              const size_t o2 = ((size_t)(k & 1) * a.Bp + b) * Rp + rowq;
-              __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(g[0], g[1], g[2], g[3]));
-              __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(g[0]), tf32_lo(g[1]), tf32_lo(g[2]), tf32_lo(g[3])));
-            } else if (b < a.B) {
-              // Keras masked scan: out_t = m ? g : out_{t-1} (zeros before the first step); state = m ? g : state
-              const size_t bt = (size_t)b * T + t;
-              const bool mv = mvp[c][bi] != 0.f;
-              float outv[4];
-              if (mv) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { outv[e] = g[e]; stn[e] = g[e]; }
-              } else {
-                float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t > 0) po = __ldcg(reinterpret_cast<const float4*>(a.Hp_hi + (bt - 1) * Rp + rowq));
-                const float4 ss = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
-                                           : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)b * Rp + rowq));
-                outv[0] = po.x; outv[1] = po.y; outv[2] = po.z; outv[3] = po.w;
-                stn[0] = ss.x; stn[1] = ss.y; stn[2] = ss.z; stn[3] = ss.w;
-              }
-              __stcg(reinterpret_cast<float4*>(a.Hp_hi + bt * Rp + rowq), make_float4(outv[0], outv[1], outv[2], outv[3]));
-              __stcg(reinterpret_cast<float4*>(a.Hp_lo + bt * Rp + rowq),
-                     make_float4(tf32_lo(outv[0]), tf32_lo(outv[1]), tf32_lo(outv[2]), tf32_lo(outv[3])));
-              if (a.H_user) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) if (rowq + e < a.R) a.H_user[bt * a.R + rowq + e] = outv[e];
-              }
-              __stcg(reinterpret_cast<float4*>(a.state + (size_t)b * Rp + rowq), make_float4(stn[0], stn[1], stn[2], stn[3]));
-            }
-            if (last) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) out_s[bl * (RO + 1) + 4 * blk_rq[c] + e] = stn[e];
-            }
+        for (int bi = 0; bi < CB; ++bi) {
+          const int bl = CB * my_cq + bi, b = i * NB + bl;
+          const float lkv = off * leak_s[i * NB + bl];
+          const float pv[4] = {pre[bi].x, pre[bi].y, pre[bi].z, pre[bi].w};
+          const float xv[4] = {xw[bi].x, xw[bi].y, xw[bi].z, xw[bi].w};
+          float sv[4] = {0.f, 0.f, 0.f, 0.f};          // state entering the frame (only for U with d != o beyond layer 0)
+          if (k > 0 && dmo != 0.f && b < a.B) {
+            const float4 so = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
+                                       : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)b * Rp + rowq));
+            sv[0] = so.x; sv[1] = so.y; sv[2] = so.z; sv[3] = so.w;
           }
-          if (a.actT_hi) {                             // backward needs every layer's post-relu output
-            const size_t TB = (size_t)T * a.Bp;
+          float g[4], stn[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const size_t o3 = ((size_t)k * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + CB * blk_cq[c];
-              if constexpr (CB == 2) {
-                __stcg(reinterpret_cast<float2*>(a.actT_hi + o3), make_float2(gall[0][e], gall[CB - 1][e]));
-                __stcg(reinterpret_cast<float2*>(a.actT_lo + o3), make_float2(tf32_lo(gall[0][e]), tf32_lo(gall[CB - 1][e])));
-              } else {
-                __stcg(a.actT_hi + o3, gall[0][e]);
-                __stcg(a.actT_lo + o3, tf32_lo(gall[0][e]));
-              }
+          for (int e = 0; e < 4; ++e) {
+            const bool valid = (b < a.B) && (rowq + e < a.R);
+            // k == 0: pre = state, weighted by the diagonal excess of U_0;  k > 0: pre = g^{k-1} (identity of S_k)
+            const float base = (k == 0) ? dmo * pv[e] : (pv[e] + dmo * sv[e]);
+            g[e] = valid ? fmaxf(acc[e][bi] + xv[e] + lkv + base, 0.f) : 0.f;
+            gall[bi][e] = g[e];
+          }
+          if (!last) {
+            const size_t o2 = ((size_t)(k & 1) * a.Bp + b) * Rp + rowq;
+            __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(g[0], g[1], g[2], g[3]));
+            __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(g[0]), tf32_lo(g[1]), tf32_lo(g[2]), tf32_lo(g[3])));
+          } else if (b < a.B) {
+            // Keras masked scan: out_t = m ? g : out_{t-1} (zeros before the first step); state = m ? g : state
+            const size_t bt = (size_t)b * T + t;
+            const bool mv = mvp[bi] != 0.f;
+            float outv[4];
+            if (mv) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { outv[e] = g[e]; stn[e] = g[e]; }
+            } else {
+              float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (t > 0) po = __ldcg(reinterpret_cast<const float4*>(a.Hp_hi + (bt - 1) * Rp + rowq));
+              const float4 ss = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
+                                         : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)b * Rp + rowq));
+              outv[0] = po.x; outv[1] = po.y; outv[2] = po.z; outv[3] = po.w;
+              stn[0] = ss.x; stn[1] = ss.y; stn[2] = ss.z; stn[3] = ss.w;
+            }
+            __stcg(reinterpret_cast<float4*>(a.Hp_hi + bt * Rp + rowq), make_float4(outv[0], outv[1], outv[2], outv[3]));
+            __stcg(reinterpret_cast<float4*>(a.Hp_lo + bt * Rp + rowq),
+                   make_float4(tf32_lo(outv[0]), tf32_lo(outv[1]), tf32_lo(outv[2]), tf32_lo(outv[3])));
+            if (a.H_user) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (rowq + e < a.R) a.H_user[bt * a.R + rowq + e] = outv[e];
+            }
+            __stcg(reinterpret_cast<float4*>(a.state + (size_t)b * Rp + rowq), make_float4(stn[0], stn[1], stn[2], stn[3]));
+          }
+          if (last) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out_s[bl * (RO + 1) + 4 * my_rq + e] = stn[e];
+          }
+        }
+        if (a.actT_hi) {                               // backward needs every layer's post-relu output
+          const size_t TB = (size_t)T * a.Bp;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const size_t o3 = ((size_t)k * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + CB * my_cq;
+            if constexpr (CB == 4) {
+              __stcg(reinterpret_cast<float4*>(a.actT_hi + o3), make_float4(gall[0][e], gall[CB > 1 ? 1 : 0][e], gall[CB > 2 ? 2 : 0][e], gall[CB > 3 ? 3 : 0][e]));
+              __stcg(reinterpret_cast<float4*>(a.actT_lo + o3), make_float4(tf32_lo(gall[0][e]), tf32_lo(gall[CB > 1 ? 1 : 0][e]),
+                                                                           tf32_lo(gall[CB > 2 ? 2 : 0][e]), tf32_lo(gall[CB > 3 ? 3 : 0][e])));
+            } else if constexpr (CB == 2) {
+              __stcg(reinterpret_cast<float2*>(a.actT_hi + o3), make_float2(gall[0][e], gall[CB > 1 ? 1 : 0][e]));
+              __stcg(reinterpret_cast<float2*>(a.actT_lo + o3), make_float2(tf32_lo(gall[0][e]), tf32_lo(gall[CB > 1 ? 1 : 0][e])));
+            } else {
+              __stcg(a.actT_hi + o3, gall[0][e]);
+              __stcg(a.actT_lo + o3, tf32_lo(gall[0][e]));
             }
           }
         }
@@ -587,13 +574,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         const long long _n = clock64(), _d = _n - _ts; _ts = _n;
         if (k == 0) dbg_acc[4] += _d; else if (last) dbg_acc[6] += _d; else dbg_acc[5] += _d;
       }
-      // ---- hand the item to the publisher (release.cta arrive; the publisher's fence makes it gpu-visible) ----
       if (a.pub_unit != 1) {
         // latency mode (one batch tile): every owner warp releases its own stores - ONE wait for the write acks on the
         // critical path instead of release.cta arrive + the publisher's gpu fence back to back
         __syncwarp();
         if (lane == 0) RT_TIMED(1, flag_add_release(a.flags + i * a.MT + m, 1u));
       } else {
+        // ---- hand the item to the publisher (release.cta arrive; the publisher's fence makes it gpu-visible) ----
         const int ps_ = (int)(j % RT_PST);
         bool okq;
         RT_TIMED(1, okq = mbar_wait(&bars->pub_empty[ps_], (uint32_t)(((j / RT_PST) & 1) ^ 1), err, RT_WATCHDOG));
@@ -823,10 +810,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         // is added exactly, in fp32, by the row owner.  tcgen05 accumulates with round-toward-zero, and with the
         // identity inside the product that bias (relative to |h|) piles up over the K_layers x T chain (measured
         // 1.1e-4 on H at R=1000, K=25 against 5e-6 for this form).
-        {
-          const int dcol = (m * 128 + row) - (col0 + ch * 32);           // column of this chunk that holds the diagonal
+        if (col0 + ch * 32 == m * 128 + q * 32) {       // warp-uniform: this chunk holds the diagonal, in column `lane`
 #pragma unroll
-          for (int e = 0; e < 32; ++e) if (e == dcol) v[e] -= 1.0f;
+          for (int e = 0; e < 32; ++e) v[e] -= (e == lane) ? 1.0f : 0.0f;     // select, not a branch (a 32-way jump table otherwise)
         }
         float lo[32];
 #pragma unroll
@@ -869,6 +855,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           RT_TIMED(1, okl = mbar_wait(&bars->w_full[ws], (uint32_t)((wc / a.WST) & 1), err, RT_WATCHDOG));
           if (!okl) { atomicCAS(a.dev_error, 0, 215); break; }
           const uint32_t rbase = smem_u32(smem + a.off_w + ws * 16384) + (uint32_t)row * 128u;
+          long long _tl = dbg_on ? clock64() : 0;
           float v[32];
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4)
@@ -883,10 +870,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           // itself) is added exactly, in fp32, by the row owner.  tcgen05 accumulates with round-toward-zero, and with
           // the identity inside the product that bias (relative to |h|) piles up over the K_layers x T chain (measured
           // 1.1e-4 on H at R=1000, K=25 against 5e-6 for this form).
-          {
-            const int dcol = (m * 128 + row) - (col0 + ch * 32);         // column of this chunk that holds the diagonal
+          if (col0 + ch * 32 == m * 128 + q * 32) {     // warp-uniform: this chunk holds the diagonal, in column `lane`
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (e == dcol) v[e] -= 1.0f;
+            for (int e = 0; e < 32; ++e) v[e] -= (e == lane) ? 1.0f : 0.0f;   // select, not a branch (a 32-way jump table otherwise)
           }
           float lo[32];
 #pragma unroll
@@ -894,14 +880,17 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           // Hand the stage back only now: the arithmetic above depends on every loaded value, so the LDS have really
           // completed (an arrive issued right behind the loads let the refill overtake them: measured, non-repeatable
           // results), and the generic-proxy reads are fenced against the async-proxy (TMA) refill.
+          if (dbg_on) { long long _n = clock64(); dbg_acc[2] += _n - _tl; _tl = _n; }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->w_free[ws]);
+          if (dbg_on) { long long _n = clock64(); dbg_acc[3] += _n - _tl; _tl = _n; }
           tmem_st32(trow + ch * 32, v);
           tmem_st32(trow + a.KCH + ch * 32, lo);
+          if (dbg_on) { long long _n = clock64(); dbg_acc[4] += _n - _tl; _tl = _n; }
         }
         if (!okl) break;
-        tc_wait_st();
+        RT_TIMED(5, tc_wait_st());
         tc_fence_before();
         mbar_arrive(&bars->wt_full);
       }
@@ -921,7 +910,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct RecPlan { int NB, KS, MT, RO, ATOMS, KSLICE, n_tiles, WST, HST, RST; size_t smem; RecArgs a; bool ok; const char* why; };
+struct RecPlan { int NB, KS, MT, RO, ATOMS, KSLICE, n_tiles, WST, HST, RST, CB; size_t smem; RecArgs a; bool ok; const char* why; };
 
 static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
   RecPlan p{};
@@ -937,6 +926,8 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
   p.a.KCH = p.KSLICE > 128 ? 128 : p.KSLICE;
   p.a.NCH = p.KSLICE / p.a.KCH;
   if (p.RO * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
+  p.CB = p.RO * p.NB >= 2048 ? 4 : (p.RO * p.NB >= 1024 ? 2 : 1);     // batch columns per owner thread (4 rows x CB)
+  if (((p.RO / 4) * (p.NB / p.CB)) % 32 != 0) { p.why = "owner tile smaller than a warp"; return p; }
   const int h_stage = 2 * p.ATOMS * p.NB * 128, red_slot = 128 * p.NB * 4;   // slot = KS blocks of RO x NB fp32
   const int leak_b = round_up(2 * p.n_tiles * p.NB * 4, 128), out_b = round_up(max(p.NB * (p.RO + 1), 128) * 4, 128);
   const int fixed = leak_b + out_b + (int)sizeof(RecBars) + 256;
@@ -977,41 +968,48 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
   return p;
 }
 
-// co-resident clusters the device offers for this plan (the kernel spins on peers: all CTAs must be resident)
+using RecKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, RecArgs);
+
 template <int NB>
-static int rec_max_clusters(const RecPlan& p, int* out) {
-  auto kern = k_recurrent_tc<NB, false>;
-  DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
-  cudaLaunchConfig_t cfg{};
+static RecKernel rec_kernel_nb(bool bwd, int CB) {
+  if (bwd) return k_recurrent_tc<NB, true, 4>;            // the backward owners keep their own 4 x 4 blocks
+  return CB == 4 ? k_recurrent_tc<NB, false, 4> : (CB == 2 ? k_recurrent_tc<NB, false, 2> : k_recurrent_tc<NB, false, 1>);
+}
+static RecKernel rec_kernel(const RecPlan& p, bool bwd) {
+  return p.NB == 16 ? rec_kernel_nb<16>(bwd, p.CB) : (p.NB == 32 ? rec_kernel_nb<32>(bwd, p.CB) : rec_kernel_nb<64>(bwd, p.CB));
+}
+
+static void rec_launch_config(const RecPlan& p, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3(p.KS, p.MT, 1);
   cfg.blockDim = dim3(RT_THREADS, 1, 1);
   cfg.dynamicSmemBytes = p.smem;
-  cudaLaunchAttribute attr[1];
+  cfg.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.KS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+}
+
+// co-resident clusters the device offers for this plan (the kernel spins on peers: all CTAs must be resident)
+static int rec_max_clusters(const RecPlan& p, int* out) {
+  RecKernel kern = rec_kernel(p, false);
+  DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  rec_launch_config(p, cfg, attr, nullptr);
   *out = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(out, kern, &cfg);
   if (e != cudaSuccess) { cudaGetLastError(); *out = 0; }
   return DRNMF_OK;
 }
 
-template <int NB, bool BWD>
-static int launch_rec(const RecPlan& p, const CUtensorMap& tH_hi, const CUtensorMap& tH_lo, const CUtensorMap& tW,
+static int launch_rec(const RecPlan& p, bool bwd, const CUtensorMap& tH_hi, const CUtensorMap& tH_lo, const CUtensorMap& tW,
                       cudaStream_t st) {
-  auto kern = k_recurrent_tc<NB, BWD>;
+  RecKernel kern = rec_kernel(p, bwd);
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.KS, p.MT, 1);
-  cfg.blockDim = dim3(RT_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = p.smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p.KS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  rec_launch_config(p, cfg, attr, st);
   DRNMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tH_hi, tH_lo, tW, p.a));
   count_launch();
   return DRNMF_OK;
@@ -1032,7 +1030,7 @@ static RecPlan choose_plan(const drnmf_handle* h, int B) {
       RecPlan c = plan_recurrent(h, B, KS, NB);
       if (!c.ok) { if (!p.why || !p.ok) p.why = c.why; continue; }
       int mc = 0;
-      if (NB == 16) rec_max_clusters<16>(c, &mc); else if (NB == 32) rec_max_clusters<32>(c, &mc); else rec_max_clusters<64>(c, &mc);
+      rec_max_clusters(c, &mc);
       if (mc < c.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
       p = c;
     }
@@ -1066,8 +1064,7 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
   if ((rc = make_tmap_2d(&tH_hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
   if ((rc = make_tmap_2d(&tH_lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
-  return (p.NB == 16) ? launch_rec<16, true>(p, tH_hi, tH_lo, tW, st)
-       : (p.NB == 32) ? launch_rec<32, true>(p, tH_hi, tH_lo, tW, st) : launch_rec<64, true>(p, tH_hi, tH_lo, tW, st);
+  return launch_rec(p, true, tH_hi, tH_lo, tW, st);
 }
 
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
@@ -1101,8 +1098,7 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
   if ((rc = make_tmap_2d(&tH_hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
   if ((rc = make_tmap_2d(&tH_lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
-  rc = (p.NB == 16) ? launch_rec<16, false>(p, tH_hi, tH_lo, tW, st)
-     : (p.NB == 32) ? launch_rec<32, false>(p, tH_hi, tH_lo, tW, st) : launch_rec<64, false>(p, tH_hi, tH_lo, tW, st);
+  rc = launch_rec(p, false, tH_hi, tH_lo, tW, st);
   if (rc == DRNMF_OK && want_dbg) {
     long long d[16 * 8];
     DRNMF_CUDA(cudaMemcpyAsync(d, dbg_dev, sizeof(d), cudaMemcpyDeviceToHost, st));
