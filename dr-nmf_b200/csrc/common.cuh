@@ -100,6 +100,26 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
+// Blocking flavours for the wait loops: with a suspend-time hint the hardware parks the warp until the phase completes
+// (or the hint expires) instead of letting it spin through the issue slots of the warps that do the work.
+__device__ __forceinline__ bool mbar_try_wait_park(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster_park(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: returns false if the watchdog expires (caller records an error and bails out) so that a
 // protocol bug can never hang the GPU.  `budget` is in try_wait rounds (each is a HW-suspended wait).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag = nullptr,
@@ -108,7 +128,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   if (abort_flag && *abort_flag) return false;
   long long t0 = clock64();
   uint32_t it = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_park(bar, parity)) {
     if ((++it & 0x3FF) == 0) {
       if (clock64() - t0 > budget_cycles) return false;
       if (abort_flag && *abort_flag) return false;
@@ -122,7 +142,7 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity
   if (abort_flag && *abort_flag) return false;
   long long t0 = clock64();
   uint32_t it = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
+  while (!mbar_try_wait_cluster_park(bar, parity)) {
     if ((++it & 0x3FF) == 0) {
       if (clock64() - t0 > budget_cycles) return false;
       if (abort_flag && *abort_flag) return false;
