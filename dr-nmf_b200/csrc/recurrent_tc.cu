@@ -596,30 +596,53 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     // gradient and the carried state gradient G (needs the row sums of the previous processed frame, exchanged through
     // psum2 like the forward leak); u >= 1 turns the reduced product delta^k . S_k into delta^{k-1} by masking with the
     // stored activation.  Every delta is also written transposed (time-major) for the weight-gradient GEMMs.
+    // Work split as in the forward owners: one block of 4 rows x CB batch columns per thread, all loads that do not
+    // depend on the item's product issued before the wait.
     const int otid = threadIdx.x - 256;
     const int RO = a.RO;
     const int row0 = m * 128 + s * RO;
     const int cta_lin = m * a.KS + s, n_cta = a.MT * a.KS;
-    constexpr int BQ = NB / 4;
-    constexpr int SWZ = (BQ >= 8) ? 7 : BQ - 1;
+    constexpr int CQ = NB / CB;
+    constexpr int CQW = (CQ < 16) ? CQ : 16;
+    constexpr int CHUNKS = NB / 4;
+    constexpr int SWZ = (CHUNKS >= 8) ? 7 : CHUNKS - 1;
     const int RQ = RO / 4;
-    const int n_blk = RQ * BQ;
-    const bool bv = otid < n_blk;
-    const int bq = bv ? otid % BQ : 0, rq = bv ? otid / BQ : 0;
-    const int rowq = row0 + 4 * rq;
+    const int n_blk = RQ * CQ;
+    const bool mine = otid < n_blk;
+    const int uu = mine ? otid : 0;
+    const int my_cq = (uu % CQW) + CQW * ((uu / (2 * CQW)) % (CQ / CQW));
+    const int my_rq = ((uu / CQW) % 2) + 2 * (uu / (2 * CQ));
+    const int rowq = row0 + 4 * my_rq;
+    const int col0b = CB * my_cq;                            // first batch column of the block inside the tile
     const size_t TB = (size_t)T * a.Bp;
     float* add_s = leak_s;                                   // n_tiles x NB : o0*R0 + ok*Rk of the previous processed frame
     float* rk_acc = leak_s + n_tiles * NB;                   // n_tiles x NB : running sum over layers >= 1 of this frame
     float* part_s = out_s;                                   // 2 x RQ x NB  : per-item row-sum partials (double buffered)
-    auto fetch_act = [&](int fi, int u, int i, float4 (&av)[4]) {
+    auto fetch_act = [&](int fi, int u, int i, float (&av)[4][CB]) {
       const int fic = fi < T ? fi : T - 1;
       const int t = T - 1 - fic;
       const int la = (u == 0) ? K - 1 : K - u - 1;
+      if (mine) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        av[e] = __ldcg(reinterpret_cast<const float4*>(a.actT_hi + ((size_t)la * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + 4 * bq));
+        for (int e = 0; e < 4; ++e) {
+          const float* src = a.actT_hi + ((size_t)la * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + col0b;
+          if constexpr (CB == 4) {
+            const float4 f = __ldcg(reinterpret_cast<const float4*>(src));
+            av[e][0] = f.x; av[e][CB > 1 ? 1 : 0] = f.y; av[e][CB > 2 ? 2 : 0] = f.z; av[e][CB > 3 ? 3 : 0] = f.w;
+          } else if constexpr (CB == 2) {
+            const float2 f = __ldcg(reinterpret_cast<const float2*>(src));
+            av[e][0] = f.x; av[e][CB > 1 ? 1 : 0] = f.y;
+          } else {
+            av[e][0] = __ldcg(src);
+          }
+        }
+      }
     };
-    float4 act_next[4];
+    float act_next[4][CB];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int bi = 0; bi < CB; ++bi) act_next[e][bi] = 0.f;
     fetch_act(0, 0, 0, act_next);
     int it = 0;
     long long j = 0;
@@ -628,15 +651,39 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     for (int i = 0; i < n_tiles; ++i, ++j) {
       const int t = T - 1 - fi;
       const int la = (u == 0) ? K - 1 : K - u - 1;           // layer of the delta this item produces
-      float4 act4[4];
+      float av[4][CB];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) act4[e] = act_next[e];
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int bi = 0; bi < CB; ++bi) av[e][bi] = act_next[e][bi];
       {
         int i2 = i + 1, u2 = u, f2 = fi;
         if (i2 == n_tiles) { i2 = 0; if (++u2 == K) { u2 = 0; ++f2; } }
         fetch_act(f2, u2, i2, act_next);
       }
-      float d[4][4];                                          // [row e][batch bi]
+      // ---- loads that do not depend on this item's product (this thread wrote them itself, or they are inputs) ----
+      float4 pre[CB];                                         // u > 0: own rows of delta^k (identity of S_k); u == 0: G
+      float4 dh4[CB];                                         // u == 0: head gradient
+      float mvt[CB], mvn[CB];                                 // mask of frame t / t+1
+#pragma unroll
+      for (int bi = 0; bi < CB; ++bi) {
+        pre[bi] = make_float4(0.f, 0.f, 0.f, 0.f); dh4[bi] = pre[bi]; mvt[bi] = 0.f; mvn[bi] = 0.f;
+        const int b = i * NB + col0b + bi;
+        if (mine) {
+          if (u > 0) {
+            pre[bi] = __ldcg(reinterpret_cast<const float4*>(a.hb_hi + ((size_t)((u - 1) & 1) * a.Bp + b) * Rp + rowq));
+          } else if (b < a.B) {
+            const size_t bt = (size_t)b * T + t;
+            dh4[bi] = __ldg(reinterpret_cast<const float4*>(a.dH + bt * Rp + rowq));
+            if (fi > 0) {
+              pre[bi] = __ldcg(reinterpret_cast<const float4*>(a.G + (size_t)b * Rp + rowq));
+              mvn[bi] = __ldg(a.mvalid + bt + 1);
+            }
+          }
+          if ((u == 0 || la == 0) && b < a.B) mvt[bi] = __ldg(a.mvalid + (size_t)b * T + t);
+        }
+      }
+      float d[4][CB];                                         // [row e][batch bi]
       if (u == 0) {
         if (fi > 0) {
           const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(fi * K);
@@ -656,94 +703,106 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         }
         if (otid < NB) rk_acc[i * NB + otid] = 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (bv) {
 #pragma unroll
-          for (int bi = 0; bi < 4; ++bi) {
-            const int bl = 4 * bq + bi, b = i * NB + bl;
-            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float dg[4] = {0.f, 0.f, 0.f, 0.f};
-            if (b < a.B) {
-              const size_t bt = (size_t)b * T + t;
-              if (fi > 0) {
-                g4 = __ldcg(reinterpret_cast<const float4*>(a.G + (size_t)b * Rp + rowq));
-                if (__ldg(a.mvalid + bt + 1) != 0.f) {          // frame t+1 was valid: its state gradient is complete now
-                  const float ad = add_s[i * NB + bl];
-                  g4.x = (rowq + 0 < a.R) ? g4.x + ad : 0.f; g4.y = (rowq + 1 < a.R) ? g4.y + ad : 0.f;
-                  g4.z = (rowq + 2 < a.R) ? g4.z + ad : 0.f; g4.w = (rowq + 3 < a.R) ? g4.w + ad : 0.f;
-                  __stcg(reinterpret_cast<float4*>(a.G + (size_t)b * Rp + rowq), g4);
-                }
-              }
-              if (__ldg(a.mvalid + bt) != 0.f) {
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(a.dH + bt * Rp + rowq));
-                dg[0] = h4.x + g4.x; dg[1] = h4.y + g4.y; dg[2] = h4.z + g4.z; dg[3] = h4.w + g4.w;
-              }
+        for (int bi = 0; bi < CB; ++bi) {
+          const int bl = col0b + bi, b = i * NB + bl;
+          float4 g4 = pre[bi];
+          float dg[4] = {0.f, 0.f, 0.f, 0.f};
+          if (mine && b < a.B) {
+            if (fi > 0 && mvn[bi] != 0.f) {                   // frame t+1 was valid: its state gradient is complete now
+              const float ad = add_s[i * NB + bl];
+              g4.x = (rowq + 0 < a.R) ? g4.x + ad : 0.f; g4.y = (rowq + 1 < a.R) ? g4.y + ad : 0.f;
+              g4.z = (rowq + 2 < a.R) ? g4.z + ad : 0.f; g4.w = (rowq + 3 < a.R) ? g4.w + ad : 0.f;
+              __stcg(reinterpret_cast<float4*>(a.G + (size_t)b * Rp + rowq), g4);
             }
-            d[0][bi] = dg[0]; d[1][bi] = dg[1]; d[2][bi] = dg[2]; d[3][bi] = dg[3];
+            if (mvt[bi] != 0.f) {
+              dg[0] = dh4[bi].x + g4.x; dg[1] = dh4[bi].y + g4.y; dg[2] = dh4[bi].z + g4.z; dg[3] = dh4[bi].w + g4.w;
+            }
           }
+          d[0][bi] = dg[0]; d[1][bi] = dg[1]; d[2][bi] = dg[2]; d[3][bi] = dg[3];
         }
       } else {
         const int rs = it % a.RST;
         if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
         if (!mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 220);
         const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
-        uint32_t qaddr[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = 4 * rq + e;
-          qaddr[e] = red + (uint32_t)(r * (NB * 4) + ((bq & ~SWZ) | ((bq ^ r) & SWZ)) * 16);
-        }
+        for (int e = 0; e < 4; ++e)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) d[e][0] = d[e][1] = d[e][2] = d[e][3] = 0.f;
+          for (int bi = 0; bi < CB; ++bi) d[e][bi] = 0.f;
         const uint32_t src_stride = (uint32_t)(RO * NB * 4);
-#pragma unroll 2
-        for (int src = 0; src < a.KS; ++src) {
-          float4 ld[4];
+        if (mine) {
+          uint32_t qaddr[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ld[e].x), "=f"(ld[e].y), "=f"(ld[e].z), "=f"(ld[e].w)
-                         : "r"(qaddr[e] + src * src_stride));
+          for (int e = 0; e < 4; ++e) {
+            const int r = 4 * my_rq + e, ch = col0b >> 2;
+            qaddr[e] = red + (uint32_t)(r * (NB * 4) + ((ch & ~SWZ) | ((ch ^ r) & SWZ)) * 16 + (col0b & 3) * 4);
+          }
+#pragma unroll 4
+          for (int src = 0; src < a.KS; ++src) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { d[e][0] += ld[e].x; d[e][1] += ld[e].y; d[e][2] += ld[e].z; d[e][3] += ld[e].w; }
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t ad = qaddr[e] + src * src_stride;
+              if constexpr (CB == 4) {
+                float x0, x1, x2, x3;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(ad));
+                d[e][0] += x0; d[e][CB > 1 ? 1 : 0] += x1; d[e][CB > 2 ? 2 : 0] += x2; d[e][CB > 3 ? 3 : 0] += x3;
+              } else if constexpr (CB == 2) {
+                float x0, x1;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(ad));
+                d[e][0] += x0; d[e][CB > 1 ? 1 : 0] += x1;
+              } else {
+                float x0;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(ad));
+                d[e][0] += x0;
+              }
+            }
+          }
         }
         __syncwarp();
         if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);
         ++it;
-        if (bv) {   // identity part of S_k: this owner's rows of delta^k (written by these threads one item earlier)
 #pragma unroll
-          for (int bi = 0; bi < 4; ++bi) {
-            const float4 dp = __ldcg(reinterpret_cast<const float4*>(
-                a.hb_hi + ((size_t)((u - 1) & 1) * a.Bp + i * NB + 4 * bq + bi) * Rp + rowq));
-            d[0][bi] += dp.x; d[1][bi] += dp.y; d[2][bi] += dp.z; d[3][bi] += dp.w;
-          }
+        for (int bi = 0; bi < CB; ++bi) {   // identity part of S_k: this owner's rows of delta^k
+          d[0][bi] += pre[bi].x; d[1][bi] += pre[bi].y; d[2][bi] += pre[bi].z; d[3][bi] += pre[bi].w;
         }
       }
       // ---- mask with the stored activation, store both layouts, row-sum partials ----
-      float psb[4] = {0.f, 0.f, 0.f, 0.f};
-      if (bv) {
-        const float av[4][4] = {{act4[0].x, act4[0].y, act4[0].z, act4[0].w}, {act4[1].x, act4[1].y, act4[1].z, act4[1].w},
-                                {act4[2].x, act4[2].y, act4[2].z, act4[2].w}, {act4[3].x, act4[3].y, act4[3].z, act4[3].w}};
+      if (mine) {
+        float psb[CB];
+#pragma unroll
+        for (int bi = 0; bi < CB; ++bi) psb[bi] = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
-          for (int bi = 0; bi < 4; ++bi) {
-            const bool keep = (av[e][bi] > 0.f) && (rowq + e < a.R) && (i * NB + 4 * bq + bi < a.B);
+          for (int bi = 0; bi < CB; ++bi) {
+            const bool keep = (av[e][bi] > 0.f) && (rowq + e < a.R) && (i * NB + col0b + bi < a.B);
             d[e][bi] = keep ? d[e][bi] : 0.f;
             psb[bi] += d[e][bi];
           }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {                          // transposed (time-major) copy for the weight gradients
-          const size_t o3 = ((size_t)la * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + 4 * bq;
-          __stcg(reinterpret_cast<float4*>(a.deltaT_hi + o3), make_float4(d[e][0], d[e][1], d[e][2], d[e][3]));
-          __stcg(reinterpret_cast<float4*>(a.deltaT_lo + o3), make_float4(tf32_lo(d[e][0]), tf32_lo(d[e][1]), tf32_lo(d[e][2]), tf32_lo(d[e][3])));
+          const size_t o3 = ((size_t)la * Rp + rowq + e) * TB + (size_t)t * a.Bp + i * NB + col0b;
+          if constexpr (CB == 4) {
+            __stcg(reinterpret_cast<float4*>(a.deltaT_hi + o3), make_float4(d[e][0], d[e][CB > 1 ? 1 : 0], d[e][CB > 2 ? 2 : 0], d[e][CB > 3 ? 3 : 0]));
+            __stcg(reinterpret_cast<float4*>(a.deltaT_lo + o3), make_float4(tf32_lo(d[e][0]), tf32_lo(d[e][CB > 1 ? 1 : 0]),
+                                                                             tf32_lo(d[e][CB > 2 ? 2 : 0]), tf32_lo(d[e][CB > 3 ? 3 : 0])));
+          } else if constexpr (CB == 2) {
+            __stcg(reinterpret_cast<float2*>(a.deltaT_hi + o3), make_float2(d[e][0], d[e][CB > 1 ? 1 : 0]));
+            __stcg(reinterpret_cast<float2*>(a.deltaT_lo + o3), make_float2(tf32_lo(d[e][0]), tf32_lo(d[e][CB > 1 ? 1 : 0])));
+          } else {
+            __stcg(a.deltaT_hi + o3, d[e][0]);
+            __stcg(a.deltaT_lo + o3, tf32_lo(d[e][0]));
+          }
         }
 #pragma unroll
-        for (int bi = 0; bi < 4; ++bi) {
-          const int b = i * NB + 4 * bq + bi;
+        for (int bi = 0; bi < CB; ++bi) {
+          const int b = i * NB + col0b + bi;
           if (la > 0) {                                        // operand of the next product
             const size_t o2 = ((size_t)(u & 1) * a.Bp + b) * Rp + rowq;
             __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(d[0][bi], d[1][bi], d[2][bi], d[3][bi]));
             __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(d[0][bi]), tf32_lo(d[1][bi]), tf32_lo(d[2][bi]), tf32_lo(d[3][bi])));
-          } else if (b < a.B && __ldg(a.mvalid + (size_t)b * T + t) != 0.f) {
+          } else if (b < a.B && mvt[bi] != 0.f) {
             // delta^0: start of the new state gradient  G = (d0-o0) delta^0 (+ rank-1 terms added at the next frame start)
             __stcg(reinterpret_cast<float4*>(a.G + (size_t)b * Rp + rowq),
                    make_float4(a.d0mo_b * d[0][bi], a.d0mo_b * d[1][bi], a.d0mo_b * d[2][bi], a.d0mo_b * d[3][bi]));
@@ -751,7 +810,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         }
         const int pb = (int)(j & 1);
 #pragma unroll
-        for (int bi = 0; bi < 4; ++bi) part_s[(pb * RQ + rq) * NB + 4 * bq + bi] = psb[bi];
+        for (int bi = 0; bi < CB; ++bi) part_s[(pb * RQ + my_rq) * NB + col0b + bi] = psb[bi];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (otid < NB) {
@@ -972,7 +1031,7 @@ using RecKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorM
 
 template <int NB>
 static RecKernel rec_kernel_nb(bool bwd, int CB) {
-  if (bwd) return k_recurrent_tc<NB, true, 4>;            // the backward owners keep their own 4 x 4 blocks
+  if (bwd) return CB == 4 ? k_recurrent_tc<NB, true, 4> : (CB == 2 ? k_recurrent_tc<NB, true, 2> : k_recurrent_tc<NB, true, 1>);
   return CB == 4 ? k_recurrent_tc<NB, false, 4> : (CB == 2 ? k_recurrent_tc<NB, false, 2> : k_recurrent_tc<NB, false, 1>);
 }
 static RecKernel rec_kernel(const RecPlan& p, bool bwd) {
