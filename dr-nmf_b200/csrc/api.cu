@@ -145,6 +145,7 @@ int drnmf_destroy(drnmf_handle* h) {
   for (float* p : ptrs) if (p) cudaFree(p);
   if (h->dev_error) cudaFree(h->dev_error);
   if (h->ev_ready) for (auto& e : h->ev) cudaEventDestroy(e);
+  if (h->side_ready) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_side[0]); cudaEventDestroy(h->ev_side[1]); }
   delete h;
   return DRNMF_OK;
 }
@@ -449,13 +450,25 @@ int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const float* stack_
   const size_t BT = (size_t)B * T, F = h->F;
   const long long L = (long long)hop * (T - 1) - N;
   DRNMF_CHECK(L > 0, "utterances too short for N=%d hop=%d", N, hop);
+  if (!h->side_ready) {
+    DRNMF_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_side[0], cudaEventDisableTiming));
+    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_side[1], cudaEventDisableTiming));
+    h->side_ready = true;
+  }
   DRNMF_CUDA(cudaMemcpyAsync(e.x, x_host, BT * F * 4, cudaMemcpyHostToDevice, st));
-  DRNMF_CUDA(cudaMemcpyAsync(e.stack, stack_host, 2 * F * BT * 4, cudaMemcpyHostToDevice, st));
   DRNMF_CUDA(cudaMemcpyAsync(e.frames, frames_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  // the [Re;Im] stack (2/3 of the input bytes) is only read by the synthesis: it travels on a side stream under the
+  // network, ordered after whatever used the workspace before this call and before the mask/iSTFT kernels
+  DRNMF_CUDA(cudaEventRecord(h->ev_side[0], st));
+  DRNMF_CUDA(cudaStreamWaitEvent(h->side, h->ev_side[0], 0));
+  DRNMF_CUDA(cudaMemcpyAsync(e.stack, stack_host, 2 * F * BT * 4, cudaMemcpyHostToDevice, h->side));
+  DRNMF_CUDA(cudaEventRecord(h->ev_side[1], h->side));
   k_enh_tables<<<(B + 127) / 128, 128, 0, st>>>(e.frames, B, T, L, e.fidx, e.out_offs);
   count_launch();
   DRNMF_CUDA(cudaMemsetAsync(e.audio, 0, (size_t)B * L * 4, st));
   if ((rc = drnmf_forward(h, e.x, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream))) return rc;
+  DRNMF_CUDA(cudaStreamWaitEvent(st, h->ev_side[1], 0));
   if ((rc = launch_mask_istft(e.stack, e.irm, e.fidx, e.out_offs, B, T, N, hop, (int64_t)BT, e.frames_tmp, e.audio, st))) return rc;
   DRNMF_CUDA(cudaMemcpyAsync(audio_out_host, e.audio, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
   DRNMF_CUDA(cudaStreamSynchronize(st));

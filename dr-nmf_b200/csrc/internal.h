@@ -26,6 +26,9 @@ struct drnmf_handle {
   int* dev_error;          // device-side error word (watchdogs / protocol violations)
   cudaEvent_t ev[5];       // stage boundaries of the last drnmf_forward (mask | projection | recurrence | recon)
   bool ev_ready, ev_valid;
+  cudaStream_t side;       // copy stream of drnmf_enhance_host (the complex STFT is only needed after the recurrence)
+  cudaEvent_t ev_side[2];  // [0] main stream reached the call, [1] side copy done
+  bool side_ready;
   int last_rec_impl;       // 0 = persistent tcgen05 kernel, 1 = SIMT per-step kernels (last drnmf_forward)
   int rec_cfg[8];          // NB, KS, MT, ATOMS, n_tiles, WST, HST, RST of the last persistent launch
 };

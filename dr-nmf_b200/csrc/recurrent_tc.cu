@@ -47,6 +47,7 @@ struct RecArgs {
   // shapes
   int B, Bp, T, K, R, Rp;
   int MT, KS, RO, ATOMS, KSLICE, n_tiles;
+  int sym;                                   // S_k symmetric and square blocks: CTAs below the diagonal read the mirrored block
   int pub_unit;                              // flag increments per (CTA, item): 1 = publisher thread, 4 = each owner warp releases its own stores
   int KCH, NCH;                              // weight chunk held in TMEM at a time (<= 128 K-columns), chunks per K-slice
   int WST, HST, RST;                         // WST unused (weights live in TMEM); hidden-tile / reduction-slot ring depths
@@ -160,8 +161,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
               RT_TIMED(0, okw = mbar_wait(&bars->w_free[ws], (uint32_t)(((wc / a.WST) & 1) ^ 1), err, RT_WATCHDOG));
               if (!okw) { atomicCAS(a.dev_error, 0, 214); break; }
               mbar_expect_tx(&bars->w_full[ws], 16384u);
-              tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW, &bars->w_full[ws], s * a.KSLICE + ch2 * a.KCH + ch * 32,
-                               (k - 1) * Rp + m * 128, pol_w);
+              // block (m, s) of S_k^T - or, below the diagonal of a symmetric S_k, the mirrored block (s, m), cut
+              // into 32-row slabs of the M-tile: only 36 of the 64 blocks of a layer are ever fetched (54 of 96 MB at
+              // R = 1000, K = 25), which is what fits in L2 across a frame
+              const bool tr = a.sym && s < m;
+              const int c0 = tr ? m * 128 + ch * 32 : s * a.KSLICE + ch2 * a.KCH + ch * 32;
+              const int c1 = (k - 1) * Rp + (tr ? s * 128 : m * 128);
+              tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW, &bars->w_full[ws], c0, c1, pol_w);
             }
       }
     }
@@ -892,7 +898,50 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       }
     }
   }
-  if (warp >= 12 && a.WST > 0) {
+  if (warp >= 12 && a.WST > 0 && a.sym && s < m) {
+    // ================= weight loaders, mirrored block (symmetric S_k, CTA below the diagonal) =================
+    // The ring holds block (s, m): stage ch = [K index c (128 rows)] x [output rows 32*ch .. +32 of the M-tile (128
+    // bytes)].  Warp q owns TMEM lanes = output rows 32q..32q+31, i.e. exactly stage q, and reads it transposed: for a
+    // fixed c the 32 lanes read one 128-byte row (conflict-free).  No diagonal in these blocks.  The four stages are
+    // handed back after the last piece (every warp waits for and arrives on every stage so that the arrival counts of
+    // consecutive steps cannot mix).
+    const int q = warp - 12;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    int wl = 0;
+    long long wc = 0;
+    bool okl = true;
+    for (int ms = 0; ms < n_mma_steps && okl; ++ms, ++wl, wc += 4) {
+      for (int ch = 0; ch < 4 && okl; ++ch) {
+        const long long w2 = wc + ch;
+        RT_TIMED(1, okl = mbar_wait(&bars->w_full[(int)(w2 % a.WST)], (uint32_t)((w2 / a.WST) & 1), err, RT_WATCHDOG));
+        if (!okl) atomicCAS(a.dev_error, 0, 215);
+      }
+      if (!okl) break;
+      RT_TIMED(0, okl = mbar_wait(&bars->wt_empty, (uint32_t)((wl & 1) ^ 1), err, RT_WATCHDOG));
+      if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
+      tc_fence_after();
+      const uint32_t tile = smem_u32(smem + a.off_w + (int)((wc + q) % a.WST) * 16384);
+      const uint32_t lcol = (uint32_t)(lane & 3) * 4u, lchunk = (uint32_t)(lane >> 2);
+      for (int pc = 0; pc < 4; ++pc) {                  // 32 K-columns at a time
+        float v[32], lo[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const uint32_t c = (uint32_t)(pc * 32 + e);
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[e]) : "r"(tile + c * 128u + ((lchunk ^ (c & 7u)) << 4) + lcol));
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(v[e]);
+        tmem_st32(trow + pc * 32, v);
+        tmem_st32(trow + a.KCH + pc * 32, lo);
+      }
+      fence_proxy_async_smem();                          // all values have been consumed by the arithmetic above
+      __syncwarp();
+      if (lane < 4) mbar_arrive(&bars->w_free[(int)((wc + lane) % a.WST)]);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->wt_full);
+    }
+  } else if (warp >= 12 && a.WST > 0) {
     // ================= weight loaders: smem ring -> registers -> (hi | lo) in TMEM =================
     // Thread = row of the M-tile = TMEM lane.  A chunk is 128 rows x 128 bytes in the TMA 128B-swizzle layout (16-byte
     // piece c of row r sits at r*128 + ((c ^ (r & 7)) << 4)): eight consecutive rows read eight different pieces, so the
@@ -1011,6 +1060,7 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
     while (p.RST < 4 && rem >= 2 * red_slot) { ++p.RST; rem -= 2 * red_slot; }
   }
   while (p.WST > 0 && p.WST < wst_max && p.WST < p.ATOMS && rem >= w_stage) { ++p.WST; rem -= w_stage; }
+  p.a.sym = (h->alph_dim == 1 && p.KSLICE == 128 && p.a.NCH == 1 && p.KS == p.MT && p.WST >= 4 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
   int off = 0;
   p.a.off_w = off; off += p.WST * w_stage;
   p.a.off_h = off; off += p.HST * h_stage;
