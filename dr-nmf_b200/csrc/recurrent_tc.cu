@@ -43,6 +43,7 @@ struct RecArgs {
   float d0mo_b, o0_b, ok_b;
   unsigned int* flags;
   int* dev_error;
+  int dbg_m;                                 // M-tile of the observed CTA (K-split 0)
   long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
   // shapes
   int B, Bp, T, K, R, Rp;
@@ -65,6 +66,7 @@ struct RecBars {   // all mbarriers, laid out at off_bar
   uint64_t w_full[8], w_free[8];             // 16 KB weight chunks (32 K-columns x 128 rows) staged in smem by TMA
   uint32_t tmem_slot;
   int abort;
+  long long dbg_ts[2];                       // debug: clock of the first satisfied h_full / of the last MMA issue of an item
 };
 
 // named-barrier AND-reduction over the 128 owner threads (barrier id 1): uniform agreement on a predicate
@@ -113,7 +115,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     if (threadIdx.x == 0) atomicCAS(a.dev_error, 0, 299);
     return;
   }
-  const bool dbg_on = (a.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool dbg_on = (a.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == a.dbg_m;
   long long dbg_acc[7] = {0, 0, 0, 0, 0, 0, 0};
   const long long dbg_t0 = clock64();
   const int s = blockIdx.x;            // K-split == rank in cluster
@@ -197,6 +199,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
               tma_load_2d(dst + (2 * at) * H_ATOM_BYTES, &tmH_hi, &bars->h_full[hs][at], c0, c1);
               tma_load_2d(dst + (2 * at + 1) * H_ATOM_BYTES, &tmH_lo, &bars->h_full[hs][at], c0, c1);
             }
+            if (dbg_on) {   // acc3..6: delivery time of slabs 0..3 after the TMA issue (a second, passive waiter)
+              const long long _t0 = clock64();
+              for (int at = 0; at < ATOMS && at < 4; ++at) {
+                mbar_wait(&bars->h_full[hs][at], (it / a.HST) & 1, err, RT_WATCHDOG);
+                dbg_acc[3 + at] += clock64() - _t0;
+              }
+            }
           }
         }
     }
@@ -227,6 +236,40 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
               if (!okm) { atomicCAS(a.dev_error, 0, 206); break; }
               tc_fence_after();
             }
+            if (a.KCH == 128 && a.NCH == 1) {
+              // Common shape (K-slice of 128 atoms): fully unrolled, every descriptor is the item's base descriptor
+              // plus a compile-time constant and every TMEM address a constant offset.  The generic loop below spent
+              // ~85 cycles per MMA on address arithmetic; the tensor pipe needs 32 (M128 x N64 x K8 tf32, measured with
+              // scripts/microbench/mma_rate.cu: 34 per MMA in a dependent chain).
+              constexpr uint32_t HB = NB * 128;
+              const uint64_t dh = umma_desc_k128(hbase);
+              // The slabs land within ~300 cycles of each other (TMA delivers the 64 KB in ~550 cycles) while 12 MMAs take
+              // ~410: two bursts of 24 back-to-back MMAs keep the tensor pipe at its rate (34 cycles per MMA); a barrier
+              // probe between every 12 MMAs let the short MMA queue run dry (60 per MMA).  No tcgen05.fence after these
+              // waits: the barriers are completed by TMA bytes, not by tcgen05 work of other threads.
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int at = 2 * half; at < 2 * half + 2; ++at) {
+                  RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs][at], (it / a.HST) & 1, err, RT_WATCHDOG));
+                  if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
+                }
+                if (!okm) break;
+                if (dbg_on && lane == 0 && half == 0) bars->dbg_ts[0] = clock64();
+#pragma unroll
+                for (int at = 2 * half; at < 2 * half + 2; ++at) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {   // the whole warp stays convergent, the issue itself is predicated
+                    const uint32_t w_hi = tmem_base + (at * 4 + kk) * 8, w_lo = tmem_base + 128 + (at * 4 + kk) * 8;
+                    const uint64_t h_hi = dh + (uint64_t)(((2 * at) * HB + kk * 32) >> 4);
+                    const uint64_t h_lo = dh + (uint64_t)(((2 * at + 1) * HB + kk * 32) >> 4);
+                    if (leader) umma_tf32_ts(d_tmem, w_lo, h_hi, idesc, (at | kk) != 0);
+                    if (leader) umma_tf32_ts(d_tmem, w_hi, h_lo, idesc, true);
+                    if (leader) umma_tf32_ts(d_tmem, w_hi, h_hi, idesc, true);
+                  }
+                }
+              }
+            } else
 #pragma unroll 4
             for (int ks = 0; ks < nks; ++ks) {
               const int at = ch2 * (a.KCH / 32) + (ks >> 2), kk = ks & 3;
@@ -234,6 +277,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
                 RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs][at], (it / a.HST) & 1, err, RT_WATCHDOG));
                 if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
                 tc_fence_after();
+                if (dbg_on && ch2 == 0 && lane == 0) {   // acc4..6: when slabs 1..3 could start, relative to slab 0
+                  const long long _n = clock64();
+                  if (ks == 0) bars->dbg_ts[0] = _n;
+                  else if (ks == 4) dbg_acc[4] += _n - bars->dbg_ts[0];
+                  else if (ks == 8) dbg_acc[5] += _n - bars->dbg_ts[0];
+                  else if (ks == 12) dbg_acc[6] += _n - bars->dbg_ts[0];
+                }
               }
               const uint32_t w_hi = tmem_base + ks * 8, w_lo = tmem_base + a.KCH + ks * 8;
               const uint64_t h_hi = umma_desc_k128(hbase + (2 * at) * H_ATOM_BYTES + kk * 32);
@@ -256,6 +306,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             tc_commit(&bars->t_full[as]);
           }
           __syncwarp();
+          if (dbg_on && lane == 0) {   // acc3: first slab ready -> last MMA issued (the product phase)
+            const long long _n = clock64(); dbg_acc[3] += _n - bars->dbg_ts[0]; bars->dbg_ts[1] = _n;
+          }
         }
       }
     }
@@ -280,6 +333,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         RT_TIMED(0, okp = mbar_wait(&bars->t_full[as], (it / RT_AST) & 1, err, RT_WATCHDOG));
         if (!okp) atomicCAS(a.dev_error, 0, 207);
         tc_fence_after();
+        if (dbg_on) dbg_acc[2] += clock64() - *reinterpret_cast<volatile long long*>(&bars->dbg_ts[1]);   // issue -> completion
         float v[NB];
 #pragma unroll
         for (int c = 0; c < NB; c += 16) tmem_ld16(trow + ACC_COL0 + as * NB + c, v + c);
@@ -1197,6 +1251,8 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   const bool want_dbg = getenv("DRNMF_REC_DEBUG") != nullptr;
   if (want_dbg && !dbg_dev) DRNMF_CUDA(cudaMalloc(&dbg_dev, 16 * 8 * sizeof(long long)));
   a.dbg = want_dbg ? dbg_dev : nullptr;
+  a.dbg_m = want_dbg ? atoi(getenv("DRNMF_REC_DEBUG")) - 1 : 0;      // DRNMF_REC_DEBUG=1 observes CTA (0,0), =2 CTA (0,1) ...
+  if (a.dbg_m < 0 || a.dbg_m >= p.MT) a.dbg_m = 0;
   if (want_dbg) DRNMF_CUDA(cudaMemsetAsync(dbg_dev, 0, 16 * 8 * sizeof(long long), st));
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = h->u0_d - h->u0_o; a.u0_off = h->u0_o; a.uk_dmo = h->uk_d - h->uk_o; a.uk_off = h->uk_o;
