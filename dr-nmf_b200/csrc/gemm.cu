@@ -164,16 +164,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       for (int kb = 0; kb < num_kb && ok; ++kb) {
         const int s = kb % Cfg::STAGES;
         const uint32_t ph = (kb / Cfg::STAGES) & 1;
+        // (no tcgen05.fence after this wait: the barrier is completed by TMA bytes, and a fence per k-block drains the
+        //  MMA queue; all descriptors of a stage are its base descriptor plus compile-time constants)
         if (!mbar_wait(&full[s], ph)) { atomicExch(dev_error, 102); ok = false; break; }
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint64_t d0 = umma_desc_k128(smem_u32(smem + s * Cfg::STAGE_BYTES));
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
-          const uint32_t koff = ks * 32;     // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-          const uint64_t a_hi = umma_desc_k128(st + 0 * TC_TILE_BYTES + koff);
-          const uint64_t a_lo = umma_desc_k128(st + 1 * TC_TILE_BYTES + koff);
-          const uint64_t b_hi = umma_desc_k128(st + 2 * TC_TILE_BYTES + koff);
-          const uint64_t b_lo = umma_desc_k128(st + 3 * TC_TILE_BYTES + koff);
+          constexpr uint32_t T16 = TC_TILE_BYTES >> 4;   // descriptor address field counts 16-byte units
+          const uint32_t koff = ks * 2;                 // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+          const uint64_t a_hi = d0 + (uint64_t)(0 * T16 + koff);
+          const uint64_t a_lo = d0 + (uint64_t)(1 * T16 + koff);
+          const uint64_t b_hi = d0 + (uint64_t)(2 * T16 + koff);
+          const uint64_t b_lo = d0 + (uint64_t)(3 * T16 + koff);
           const bool first = (kb < Cfg::NACC && ks == 0);          // first MMA into this accumulator overwrites
           const uint32_t acc_t = tmem_base + (uint32_t)(kb % Cfg::NACC) * Cfg::ACC_COLS;
           if (leader) {
@@ -182,8 +184,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             umma_tf32(acc_t, a_hi, b_hi, idesc, true);
           }
           if (Cfg::DUAL) {
-            const uint64_t c_hi = umma_desc_k128(st + 4 * TC_TILE_BYTES + koff);
-            const uint64_t c_lo = umma_desc_k128(st + 5 * TC_TILE_BYTES + koff);
+            const uint64_t c_hi = d0 + (uint64_t)(4 * T16 + koff);
+            const uint64_t c_lo = d0 + (uint64_t)(5 * T16 + koff);
             if (leader) {
               umma_tf32(acc_t + TC_BN, a_lo, c_hi, idesc, !first);
               umma_tf32(acc_t + TC_BN, a_hi, c_lo, idesc, true);
