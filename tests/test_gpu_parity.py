@@ -200,6 +200,39 @@ def test_stft_roundtrip_full_size():
     np.testing.assert_allclose(yh[0].cpu().numpy(), 0.5 * ys[0].cpu().numpy(), atol=1e-6)
 
 
+@pytest.mark.parametrize("N,hop", [(128, 32), (256, 128), (512, 128), (1024, 256), (1024, 512), (2048, 512), (4096, 1024)])
+def test_stft_sizes_vs_oracle(N, hop):
+    """Every FFT path (four-step register transform for N = 512 / 1024, tiled radix-2, one-frame-per-CTA fallback for
+    N = 4096) against the numpy oracle: stack, magnitude and masked synthesis, ragged batch incl. an odd frame count."""
+    rng = np.random.default_rng(N + hop)
+    lens = [int(3.3 * N) + 17, 9 * N + 5, 6 * N]
+    sigs = [rng.standard_normal(n).astype(np.float32) for n in lens]
+    offs = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    audio = torch.as_tensor(np.concatenate(sigs), device="cuda")
+    stack, mag, fidx = engine.stft_mag(audio, list(offs), lens, N, hop)
+    win = O.sqrt_hann(N)
+    F = N // 2 + 1
+    col = 0
+    masks = []
+    for s_ in sigs:
+        ref = O.stack_reim(O.stft_mc(s_.reshape(1, -1), N, hop, win))
+        T = ref.shape[1]
+        got = stack[:, col:col + T].cpu().numpy()
+        assert np.max(np.abs(got - ref)) < 3e-5 * max(1.0, np.abs(ref).max())
+        np.testing.assert_allclose(mag[col:col + T].cpu().numpy().T, np.sqrt(ref[:F] ** 2 + ref[F:] ** 2), atol=1e-4, rtol=1e-5)
+        masks.append(rng.random((T, F)).astype(np.float32))
+        col += T
+    assert col == stack.shape[1]
+    m = torch.as_tensor(np.concatenate(masks), device="cuda")
+    ys = engine.mask_istft(stack, m, fidx, N, hop)
+    for s_, mk, y in zip(sigs, masks, ys):
+        ref_stack = O.stack_reim(O.stft_mc(s_.reshape(1, -1), N, hop, win)).astype(np.float64)
+        want = O.reconstruct_x(ref_stack, hop, win.astype(np.float64), mask=mk.T.astype(np.float64), dtype=np.float64)[0]
+        got = y.cpu().numpy()
+        assert got.size == want.size and got.size > 0
+        np.testing.assert_allclose(got, want, atol=5e-6 * max(1.0, np.abs(want).max()))
+
+
 # ---- end to end: SDR parity ---------------------------------------------------------------------
 @pytest.mark.parametrize("impl", IMPLS)
 def test_enhance_sdr_parity(impl):
