@@ -486,6 +486,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
           float sacc = 0.f;
           const float* ps = a.psum + (size_t)((t - 1) & 1) * 256 * a.Bp + i * NB + b;
+#pragma unroll 16                                  // independent L2 loads in flight, summed in index order
           for (int c = part; c < n_cta; c += nparts) sacc += __ldcg(ps + (size_t)c * a.Bp);
           out_s[part * NB + b] = sacc;
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -752,6 +753,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
           float s0 = 0.f, s1 = 0.f;
           const float* ps = a.psum2 + (size_t)((fi - 1) & 1) * 256 * 2 * a.Bp + i * NB + b;
+#pragma unroll 8
           for (int c = part; c < n_cta; c += nparts) { s0 += __ldcg(ps + (size_t)c * 2 * a.Bp); s1 += __ldcg(ps + (size_t)c * 2 * a.Bp + a.Bp); }
           part_s[part * NB + b] = a.o0_b * s0 + a.ok_b * s1;
           asm volatile("bar.sync 1, 128;" ::: "memory");
