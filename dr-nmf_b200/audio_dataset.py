@@ -1,6 +1,8 @@
-"""Host-side mirror of the part of the reference's audio_dataset.py that is on the hot path: the [Re;Im] STFT stack
-with its fidx table and reconstruct_x (audio_dataset.py:267-278).  The CHiME2 file handling (taskfiles, HDF5 cache,
-MATLAB scoring) is out of scope; AudioDataset here is built from in-memory waveforms."""
+"""Host-side mirror of the reference's audio_dataset.py around the hot path: the [Re;Im] STFT stack with its fidx
+table, reconstruct_x (audio_dataset.py:267-278), and the data format the network consumes - padded (n_sequences,
+maxlen, d) tensors with a mask (reshape_and_pad_stacks, :116-169; get_padded_data_matrix, :369-383; the 'mag' /
+'logmag' feature maps and the pad value of load_data, :11-37).  The CHiME2 file handling (taskfiles, HDF5 cache, MATLAB
+scoring) is out of scope; AudioDataset here is built from in-memory waveforms."""
 from __future__ import annotations
 
 import numpy as np
@@ -8,6 +10,67 @@ import torch
 
 from . import engine as _engine
 from .util import sqrt_hann
+
+
+def get_mask_value(config):
+    """audio_dataset.py:11-17."""
+    if config.get("transform_x") == "mag" or config.get("transform_y") == "logmag":
+        return -1.0
+    return 0.0
+
+
+def data_transform(kind):
+    """audio_dataset.py:22-37: feature map applied to a [Re;Im] stack (2F, frames) -> (F, frames); identity otherwise."""
+    def _mag(x):
+        F = x.shape[0] // 2
+        return np.sqrt(x[:F] ** 2 + x[F:] ** 2)
+    if kind == "mag":
+        return _mag
+    if kind == "logmag":
+        return lambda x: np.log(np.float32(1.0) + _mag(x))
+    return lambda x: x
+
+
+def sequence_table(fidx, maxlen=None):
+    """Chunk table behind reshape_and_pad_stacks: rows (start frame, end frame) of every output sequence.  A file longer
+    than maxlen is cut into consecutive pieces of maxlen frames; pieces never span two files (audio_dataset.py:120-167)."""
+    fidx = np.asarray(fidx, dtype=np.int64)
+    maxseq = int((fidx[:, 1] - fidx[:, 0]).max())
+    if maxlen is None or maxlen > maxseq:
+        maxlen = maxseq
+    maxlen = int(maxlen)
+    rows = []
+    for s, e in fidx:
+        if maxlen == maxseq:
+            rows.append((s, e))
+        else:
+            rows.extend((t, min(t + maxlen, e)) for t in range(int(s), int(e), maxlen))
+    return np.asarray(rows, dtype=np.int64).reshape(-1, 2), maxlen
+
+
+def reshape_and_pad_stacks(x_stack, y_stack, fidx, transform_x=(lambda x: x), transform_y=(lambda y: y), pad_value=0.0,
+                           maxlen=None, verbose=False):
+    """audio_dataset.py:116-169: (2F, total frames) stacks -> x, y of shape (n_sequences, maxlen, d) filled with
+    pad_value beyond each sequence, and mask (n_sequences, maxlen, 1) = 1 on data frames."""
+    table, maxlen = sequence_table(fidx, maxlen)
+    d = transform_x(x_stack[:, 0:1]).shape[0]
+    n = table.shape[0]
+    x = np.full((n, maxlen, d), pad_value, dtype=x_stack.dtype)
+    y = np.full((n, maxlen, d), pad_value, dtype=y_stack.dtype)
+    mask = np.zeros((n, maxlen, 1), dtype=x_stack.dtype)
+    for i, (t0, t1) in enumerate(table):
+        if verbose:
+            print("Sequence %d of %d: t0=%d, t1=%d, duration=%d" % (i + 1, n, t0, t1, t1 - t0))
+        x[i, :t1 - t0] = transform_x(x_stack[:, t0:t1]).T
+        y[i, :t1 - t0] = transform_y(y_stack[:, t0:t1]).T
+        mask[i, :t1 - t0] = 1.0
+    return x, y, mask
+
+
+def clip_x_to_y(x, y, xfidx, yfidx):
+    """audio_dataset.py:90-104: keep, per utterance, the first len(y_utt) frames of x; returns a (d, frames_of_y) array."""
+    keep = [x[:, xs:xs + (ye - ys)] for (xs, _), (ys, ye) in zip(np.asarray(xfidx), np.asarray(yfidx))]
+    return np.concatenate(keep, axis=1)[:, :y.shape[1]]
 
 
 class AudioDataset:
@@ -47,3 +110,24 @@ class AudioDataset:
 
     def reconstruct_y(self, idx, mask=None):
         return self._reconstruct(self.y_stack_dev, idx, mask)
+
+    def get_data_stacks(self):
+        """audio_dataset.py:342-366 (without the HDF5 cache): (x_stack, y_stack, fidx)."""
+        return self.x_stack, getattr(self, "y_stack", None), self.fidx
+
+    def get_padded_data_matrix(self, transform_x=(lambda x: x), transform_y=(lambda y: y), pad_value=0.0, maxlen=None):
+        """audio_dataset.py:369-383."""
+        y_stack = getattr(self, "y_stack", None)
+        if y_stack is None:
+            y_stack = self.x_stack
+        return reshape_and_pad_stacks(self.x_stack, y_stack, self.fidx, transform_x=transform_x, transform_y=transform_y,
+                                      pad_value=pad_value, maxlen=maxlen)
+
+
+def load_data(config, dataset):
+    """audio_dataset.py:20-87 for an in-memory AudioDataset: feature maps + pad value from the data config
+    ('transform_x', 'transform_y', optional 'maxlen'), returns (x, y, mask) ready for the network."""
+    pad = get_mask_value(config)
+    return dataset.get_padded_data_matrix(transform_x=data_transform(config.get("transform_x")),
+                                          transform_y=data_transform(config.get("transform_y")), pad_value=pad,
+                                          maxlen=config.get("maxlen"))

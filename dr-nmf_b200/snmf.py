@@ -9,6 +9,9 @@ an array init_h is sliced per chunk (the reference would hand MATLAB a mis-sized
 from __future__ import annotations
 
 import copy
+import hashlib
+import json
+import os
 
 import numpy as np
 import torch
@@ -95,10 +98,55 @@ def sparse_nmf_matlab_on_chunk(V, params, verbose=True, useGPU=True, gpuIndex=1,
     return W, H, {"cost": cost, "div": div}
 
 
-def train_snmf(clean_frames, noisy_frames, params_snmf, noise_init=None, verbose=False, save_H=True):
-    """enhance.py:81-135 without the hickle cache: stage 1 learns r clean atoms, stage 2 learns [W_clean, W_noise] on
-    the noisy frames with the clean atoms frozen (w_update_ind).  noise_init replaces np.random.rand(*W.shape)."""
-    W, H, obj = sparse_nmf_matlab(clean_frames, params_snmf, verbose=verbose, save_H=save_H)
+class _NumpyEncoder(json.JSONEncoder):
+    """enhance.py:60-71 (MyEncoder)."""
+    def default(self, obj):
+        if isinstance(obj, np.integer):
+            return int(obj)
+        if isinstance(obj, np.floating):
+            return float(obj)
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        return super().default(obj)
+
+
+def get_snmf_savefile(params_snmf, path_dicts=""):
+    """enhance.py:74-79: path_dicts + 'W_noisy_<md5 of the sorted-key JSON of the parameters>_sparsity%.3f', with '.npz'
+    in place of the reference's '.hkl' (hickle is not available; same stem, so caches are found by the same key)."""
+    h = hashlib.md5(json.dumps(params_snmf, sort_keys=True, cls=_NumpyEncoder).encode()).hexdigest()
+    return path_dicts + "W_noisy_" + h + ("_sparsity%.3f.npz" % params_snmf["sparsity"])
+
+
+def _load_or_none(path, flag_recompute):
+    if path is None or flag_recompute or not os.path.exists(path):
+        return None
+    z = np.load(path, allow_pickle=True)
+    H = z["H"] if "H" in z.files and z["H"].ndim == 2 else None
+    return z["W"], H, {"cost": z["cost"], "div": z["div"]}
+
+
+def _dump(path, W, H, obj, save_H):
+    if path is None:
+        return
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    np.savez(path, W=W, H=(H if (save_H and H is not None) else np.zeros(0)), cost=np.asarray(obj["cost"]),
+             div=np.asarray(obj["div"]))
+
+
+def train_snmf(clean_frames, noisy_frames, params_snmf, noise_init=None, verbose=False, save_H=True, flag_recompute=False,
+               path_dicts=None):
+    """enhance.py:81-135: stage 1 learns r clean atoms, stage 2 learns [W_clean, W_noise] on the noisy frames with the
+    clean atoms frozen (w_update_ind).  noise_init replaces np.random.rand(*W.shape).  With path_dicts the two
+    dictionaries are cached under the reference's names (get_snmf_savefile; 'noisy' -> 'clean' for stage 1) and
+    reloaded unless flag_recompute."""
+    f_noisy = get_snmf_savefile(params_snmf, path_dicts) if path_dicts is not None else None
+    f_clean = f_noisy.replace("noisy", "clean") if f_noisy else None
+    got = _load_or_none(f_clean, flag_recompute)
+    if got is None:
+        W, H, obj = sparse_nmf_matlab(clean_frames, params_snmf, verbose=verbose, save_H=save_H)
+        _dump(f_clean, W, H, obj, save_H)
+    else:
+        W, H, obj = got
     r = int(params_snmf["r"])
     if noise_init is None:
         noise_init = np.random.default_rng(7654).random(W.shape)
@@ -106,7 +154,34 @@ def train_snmf(clean_frames, noisy_frames, params_snmf, noise_init=None, verbose
     idx_update = np.concatenate((np.zeros(r, dtype=bool), np.ones(r, dtype=bool)))
     p2 = copy.deepcopy(params_snmf)
     p2.update({"r": 2 * r, "init_w": W_init, "w_update_ind": idx_update})
-    W_noisy, H_noisy, obj_noisy = sparse_nmf_matlab(noisy_frames, p2, verbose=verbose, save_H=save_H)
+    got = _load_or_none(f_noisy, flag_recompute)
+    if got is None:
+        W_noisy, H_noisy, obj_noisy = sparse_nmf_matlab(noisy_frames, p2, verbose=verbose, save_H=save_H)
+        _dump(f_noisy, W_noisy, H_noisy, obj_noisy, save_H)
+    else:
+        W_noisy, H_noisy, obj_noisy = got
     obj_noisy["cost"] = np.squeeze(obj_noisy["cost"])
     obj_noisy["div"] = np.squeeze(obj_noisy["div"])
     return W_noisy, H_noisy, obj_noisy
+
+
+def snmf_infer(x_frames, W_noisy, params_snmf, max_iter=200, verbose=False):
+    """enhance.py:836-845: activations of a FIXED dictionary on new frames (w_update_ind all false, conv_eps 0,
+    max_iter 200).  x_frames (F, n); returns H (2r, n) and the objective trace."""
+    p = copy.deepcopy(params_snmf)
+    R = W_noisy.shape[1]
+    p.update({"r": R, "init_w": np.asarray(W_noisy), "w_update_ind": np.zeros(R, dtype=bool), "conv_eps": 0.0,
+              "max_iter": float(max_iter)})
+    _, H, obj = sparse_nmf_matlab(x_frames, p, verbose=verbose)
+    return H, obj
+
+
+def snmf_irm(W_noisy, H, r):
+    """enhance.py:847-852: irm = S^ / (1e-9 + S^ + N^) with S^ = W_clean H_clean, N^ = W_noise H_noise (two plain
+    GEMMs on the device).  W_noisy (F, 2r), H (2r, n) -> (F, n) float32 numpy array."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Wd = torch.as_tensor(np.ascontiguousarray(W_noisy, dtype=np.float32), device=dev)
+    Hd = torch.as_tensor(np.ascontiguousarray(H, dtype=np.float32), device=dev)
+    clean = Wd[:, :r] @ Hd[:r]
+    noise = Wd[:, r:] @ Hd[r:]
+    return (clean / (1e-9 + clean + noise)).cpu().numpy()

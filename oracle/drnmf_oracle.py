@@ -19,6 +19,7 @@ __all__ = [
     "drnmf_forward", "training_loss", "ista_ed", "sparse_nmf_ed", "sparse_nmf_chunked", "train_snmf",
     "snmf_irm", "sqrt_hann", "stft_mc", "stack_reim", "magnitude", "istft_no_div", "istft_mc",
     "reconstruct_x", "wav_quantize", "sdr_db", "masked_seqs_to_frames", "param_count_notebook",
+    "reshape_and_pad_stacks", "clip_x_to_y", "get_mask_value", "data_transform", "snr_db", "snmf_savefile_stem",
 ]
 
 EPS = 1e-7  # the reference's ubiquitous guard (enhance.py:147, custom_layers.py:44)
@@ -474,3 +475,103 @@ def masked_seqs_to_frames(x, mask):
     mask_reshape = np.reshape(mask, (n_examples * time_steps,))
     idx = np.where(mask_reshape == mask_reshape[0])[0]
     return x_reshape[:, idx]
+
+
+# --------------------------------------------------------------------------------------------
+# A.6  data formats either side of the path (audio_dataset.py, enhance.py:74-79)
+# --------------------------------------------------------------------------------------------
+def get_mask_value(config):
+    """audio_dataset.py:11-17: -1 pads magnitude (or log-magnitude-target) data, 0 otherwise."""
+    if config.get("transform_x") == "mag":
+        return -1.0
+    if config.get("transform_y") == "logmag":
+        return -1.0
+    return 0.0
+
+
+def data_transform(kind):
+    """audio_dataset.py:22-37: feature maps applied to a [Re;Im] stack (2F, frames) -> (F, frames)."""
+    if kind == "mag":
+        return lambda x: np.sqrt(x[:x.shape[0] // 2, :] ** 2 + x[x.shape[0] // 2:, :] ** 2)
+    if kind == "logmag":
+        return lambda x: np.log(np.float32(1.0) + np.sqrt(x[:x.shape[0] // 2, :] ** 2 + x[x.shape[0] // 2:, :] ** 2))
+    return lambda x: x
+
+
+def reshape_and_pad_stacks(x_stack, y_stack, fidx, transform_x=(lambda x: x), transform_y=(lambda y: y), pad_value=0.0,
+                           maxlen=None):
+    """audio_dataset.py:116-169: (2F, total frames) stacks -> (n_sequences, maxlen, d) padded with pad_value, plus a
+    (n_sequences, maxlen, 1) mask.  With maxlen < longest file, files are cut into consecutive chunks of maxlen
+    frames (:126-132, :149-167); chunks never span two files."""
+    fidx = np.asarray(fidx)
+    maxseq = int(np.max(fidx[:, 1] - fidx[:, 0]))
+    if maxlen is None or maxlen > maxseq:
+        maxlen = maxseq
+    maxlen = int(maxlen)
+    d = transform_x(x_stack[:, 0:1]).shape[0]
+    if maxlen == maxseq:
+        n_sequences = fidx.shape[0]
+    else:
+        n_sequences = 0
+        for i in range(fidx.shape[0]):
+            t = 0
+            while t < (fidx[i, 1] - fidx[i, 0]):
+                n_sequences += 1
+                t += maxlen
+    x = (pad_value * np.ones((n_sequences, maxlen, d))).astype(x_stack.dtype)
+    y = (pad_value * np.ones((n_sequences, maxlen, d))).astype(y_stack.dtype)
+    mask = np.zeros((n_sequences, maxlen, 1)).astype(x_stack.dtype)
+    t = 0
+    i_wavfile = 0
+    for i in range(n_sequences):
+        t_end = t + maxlen
+        increment = False
+        if t_end >= fidx[i_wavfile, 1]:
+            t_end = int(fidx[i_wavfile, 1])
+            increment = True
+        x[i, :t_end - t, :] = transform_x(x_stack[:, t:t_end]).T
+        y[i, :t_end - t, :] = transform_y(y_stack[:, t:t_end]).T
+        mask[i, :t_end - t, :] = 1.0
+        if increment and i < n_sequences - 1:
+            i_wavfile += 1
+            t = int(fidx[i_wavfile, 0])
+        else:
+            t += maxlen
+    return x, y, mask
+
+
+def clip_x_to_y(x, y, xfidx, yfidx):
+    """audio_dataset.py:90-104: per utterance keep the first len(y_utt) frames of x (in place, then truncated)."""
+    ylens = yfidx[:, 1] - yfidx[:, 0]
+    idx = 0
+    for iutt in range(xfidx.shape[0]):
+        xcur = x[:, xfidx[iutt, 0]:xfidx[iutt, 1]]
+        x[:, idx:idx + ylens[iutt]] = xcur[:, 0:ylens[iutt]]
+        idx += ylens[iutt]
+    return x[:, 0:y.shape[1]]
+
+
+def snr_db(est, ref):
+    """score_audio.m:209: raw SNR = 10 log10(sum(ref^2) / sum((ref - est)^2)) after truncation to the shorter (:199-204)."""
+    n = min(len(est), len(ref))
+    est, ref = np.asarray(est[:n], np.float64), np.asarray(ref[:n], np.float64)
+    return 10.0 * np.log10(np.sum(ref ** 2) / np.sum((ref - est) ** 2))
+
+
+def snmf_savefile_stem(params_snmf, path_dicts=""):
+    """enhance.py:74-79 get_snmf_savefile without the extension: path_dicts + 'W_noisy_' + md5(json.dumps(params,
+    sort_keys=True, cls=MyEncoder)) + '_sparsity%.3f'  (MyEncoder, :60-71, turns numpy scalars/arrays into python)."""
+    import hashlib
+    import json
+
+    class _Enc(json.JSONEncoder):
+        def default(self, obj):
+            if isinstance(obj, np.integer):
+                return int(obj)
+            if isinstance(obj, np.floating):
+                return float(obj)
+            if isinstance(obj, np.ndarray):
+                return obj.tolist()
+            return super().default(obj)
+    h = hashlib.md5(json.dumps(params_snmf, sort_keys=True, cls=_Enc).encode()).hexdigest()
+    return path_dicts + "W_noisy_" + h + ("_sparsity%.3f" % params_snmf["sparsity"])

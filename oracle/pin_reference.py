@@ -463,6 +463,59 @@ def pin_snmf_driver():
     print("pinned snmf chunk driver (solver itself = oracle restatement of sparse_nmf_gpu.m, UNPINNED: no MATLAB)")
 
 
+def pin_dataset():
+    """audio_dataset.py reshape_and_pad_stacks / clip_x_to_y / get_mask_value and enhance.py get_snmf_savefile, run from
+    the reference's own source (pure numpy / hashlib code)."""
+    rng = np.random.default_rng(116)
+    um, ag = load_util_and_dataset()
+    F2 = 10
+    lens = [7, 3, 12, 5]
+    fidx = np.zeros((len(lens), 2), np.int32)
+    fidx[:, 1] = np.cumsum(lens)
+    fidx[1:, 0] = fidx[:-1, 1]
+    xs = rng.standard_normal((F2, fidx[-1, 1])).astype(np.float32)
+    ys = rng.standard_normal((F2, fidx[-1, 1])).astype(np.float32)
+    mag = O.data_transform("mag")
+    out = {"x_stack": xs, "y_stack": ys, "fidx": fidx}
+    import io
+    import contextlib
+    for tag, maxlen in (("full", None), ("m5", 5), ("m4", 4), ("big", 100)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            xr, yr, mr = ag["reshape_and_pad_stacks"](xs.copy(), ys.copy(), fidx, transform_x=mag, transform_y=mag, pad_value=-1.0,
+                                                      maxlen=maxlen)
+        xo, yo, mo = O.reshape_and_pad_stacks(xs.copy(), ys.copy(), fidx, transform_x=mag, transform_y=mag, pad_value=-1.0,
+                                              maxlen=maxlen)
+        for a, b in ((xr, xo), (yr, yo), (mr, mo)):
+            assert a.shape == b.shape and np.array_equal(a, b), tag
+        out[tag + "_x"], out[tag + "_y"], out[tag + "_mask"] = xr, yr, mr
+    # clip_x_to_y: x has 2 extra frames per utterance
+    xlens = [l + 2 for l in lens]
+    xf = np.zeros((len(lens), 2), np.int32)
+    xf[:, 1] = np.cumsum(xlens)
+    xf[1:, 0] = xf[:-1, 1]
+    xl = rng.standard_normal((F2, xf[-1, 1])).astype(np.float32)
+    cr = ag["clip_x_to_y"](xl.copy(), ys, xf, fidx)
+    co = O.clip_x_to_y(xl.copy(), ys, xf, fidx)
+    assert np.array_equal(cr, co)
+    out["clip_x"], out["clip_xfidx"], out["clip_out"] = xl, xf, cr
+    for cfg in ({"transform_x": "mag", "transform_y": "mag"}, {"transform_x": "none", "transform_y": "logmag"},
+                {"transform_x": "none", "transform_y": "none"}):
+        assert ag["get_mask_value"](cfg) == O.get_mask_value(cfg)
+    # get_snmf_savefile (enhance.py:60-79), extracted verbatim by line range; py2 md5 accepts str -> feed bytes under py3
+    import hashlib
+    import json
+    eg = {"__name__": "ref_enhance_part", "np": np, "json": json, "hashlib": types.SimpleNamespace(
+        md5=lambda s_: hashlib.md5(s_.encode() if isinstance(s_, str) else s_))}
+    _load_py2(_read("enhance.py", 60, 79), "enhance.py", eg)
+    prm = {"cf": "ed", "sparsity": np.float32(5.0), "max_iter": 200., "conv_eps": 1e-4, "display": 0., "random_seed": 2016.,
+           "r": np.int64(100)}
+    ref_name = eg["get_snmf_savefile"](prm, path_dicts="dicts/")
+    assert ref_name == O.snmf_savefile_stem(prm, "dicts/") + ".hkl", (ref_name, O.snmf_savefile_stem(prm, "dicts/"))
+    out["savefile_name"] = np.array(ref_name)
+    np.savez_compressed(os.path.join(GOLD, "dataset.npz"), **out)
+    print("pinned reshape_and_pad_stacks / clip_x_to_y / get_mask_value / get_snmf_savefile against the reference's code")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s (this script only runs in the build container)" % REF)
@@ -471,4 +524,5 @@ if __name__ == "__main__":
     pin_ista()
     pin_stft()
     pin_snmf_driver()
+    pin_dataset()
     print("golden fixtures written to", GOLD)

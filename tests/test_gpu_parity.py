@@ -532,3 +532,58 @@ def test_snmf_frame_sharded():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "replicas identical: True" in p.stdout
+
+
+@pytest.mark.gpu
+def test_snmf_inference_irm_and_cache(tmp_path):
+    """two-stage dictionary training with the reference's cache naming, inference of the activations of the
+    frozen dictionary on new frames (enhance.py:836-845) and the SNMF ratio mask (:847-852) against the oracle."""
+    from drnmf_b200 import snmf
+    rng = np.random.default_rng(11)
+    F, r, n = 65, 12, 300
+    clean = np.abs(rng.standard_normal((F, n))).astype(np.float32)
+    noisy = clean + np.abs(rng.standard_normal((F, n))).astype(np.float32)
+    prm = {"cf": "ed", "sparsity": 0.5, "max_iter": 20.0, "conv_eps": 0.0, "display": 0.0, "random_seed": 2016.0, "r": r,
+           "init_w": (np.abs(rng.standard_normal((F, r))) + 0.1).astype(np.float32), "init_h": "ones"}
+    noise_init = rng.random((F, r)).astype(np.float32)
+    d = str(tmp_path) + "/"
+    W1, H1, obj1 = snmf.train_snmf(clean, noisy, prm, noise_init=noise_init, path_dicts=d)
+    names = sorted(os.listdir(d))
+    assert len(names) == 2 and names[0].startswith("W_clean_") and names[1].startswith("W_noisy_") and names[1].endswith("_sparsity0.500.npz")
+    W2, H2, obj2 = snmf.train_snmf(clean, noisy, prm, noise_init=noise_init + 1.0, path_dicts=d)     # served from the cache
+    np.testing.assert_array_equal(W1, W2)
+    Wo, Ho, _ = O.train_snmf(clean, noisy, prm, noise_init=noise_init)
+    assert rel_err(W1, Wo)[0] < 1e-4
+    x_new = np.abs(rng.standard_normal((F, 90))).astype(np.float32) + 0.05
+    H, obj = snmf.snmf_infer(x_new, W1, prm, max_iter=30)
+    po = dict(prm); po.update({"r": 2 * r, "init_w": W1.astype(np.float64), "w_update_ind": np.zeros(2 * r, bool), "conv_eps": 0.0,
+                               "max_iter": 30.0})
+    _, Href, oref = O.sparse_nmf_ed(x_new, po)
+    assert rel_err(H, Href)[0] < 1e-4 and abs(obj["cost"][-1] - oref["cost"][-1]) < 2e-5 * abs(oref["cost"][-1])
+    irm = snmf.snmf_irm(W1, H, r)
+    assert rel_err(irm, O.snmf_irm(W1.astype(np.float64), Href, r))[0] < 1e-4
+    assert irm.shape == x_new.shape and (irm >= 0).all() and (irm <= 1).all()
+
+
+@pytest.mark.gpu
+def test_dataset_padded_tensors_feed_the_network():
+    """AudioDataset -> load_data ('mag' features, -1 padding, maxlen chunking) -> the forward pass masks
+    exactly the padded frames."""
+    from drnmf_b200 import audio_dataset as ad
+    N, hop = 128, 32
+    waves = [synth.utterance(i, seconds=s)[0] for i, s in enumerate((0.20, 0.11, 0.16))]
+    ds = ad.AudioDataset(waves, waves, params_stft={"N": N, "hop": hop, "nch": 1})
+    cfg = {"transform_x": "mag", "transform_y": "mag", "maxlen": 40}
+    x, y, mask = ad.load_data(cfg, ds)
+    T_all = int((ds.fidx[:, 1] - ds.fidx[:, 0]).sum())
+    assert x.shape[1] == 40 and int(mask.sum()) == T_all and np.all(x[mask[..., 0] == 0] == -1.0)
+    xo, yo, mo = O.reshape_and_pad_stacks(ds.x_stack, ds.y_stack, ds.fidx, O.data_transform("mag"), O.data_transform("mag"), -1.0, 40)
+    np.testing.assert_allclose(x, xo, atol=1e-6)
+    np.testing.assert_array_equal(mask, mo)
+    F, R, K = N // 2 + 1, 32, 3
+    p = synth.model_params(F, R, K, alph=40.0)
+    eng = engine.DrnmfEngine(F, R, K)
+    eng.set_params(p)
+    H, irm = eng.forward(torch.as_tensor(x, device="cuda"))
+    Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+    assert max(rel_err(H.cpu().numpy(), Ho)) < TOL and max(rel_err(irm.cpu().numpy(), irmo)) < TOL

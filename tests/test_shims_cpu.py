@@ -56,3 +56,50 @@ def test_layer_rejects_what_the_kernel_cannot_do():
         custom_layers.DenseNonNegW(5, use_bias=True)
     with pytest.raises(ValueError):
         custom_layers.divide_A_by_AplusB([1, 2, 3])
+
+
+# ---- data formats either side of the path: pinned against the reference's own code -----------------------
+@pytest.mark.parametrize("tag,maxlen", [("full", None), ("m5", 5), ("m4", 4), ("big", 100)])
+def test_reshape_and_pad_stacks_golden(golden_dir, tag, maxlen):
+    """tests/golden/dataset.npz holds the outputs of the reference's reshape_and_pad_stacks (audio_dataset.py:116-169);
+    the oracle restatement and the product mirror must both reproduce them exactly, chunking included."""
+    import os
+    from drnmf_b200 import audio_dataset as ad
+    g = np.load(os.path.join(golden_dir, "dataset.npz"))
+    for impl, mag in ((O.reshape_and_pad_stacks, O.data_transform("mag")), (ad.reshape_and_pad_stacks, ad.data_transform("mag"))):
+        x, y, m = impl(g["x_stack"].copy(), g["y_stack"].copy(), g["fidx"], transform_x=mag, transform_y=mag, pad_value=-1.0,
+                       maxlen=maxlen)
+        np.testing.assert_array_equal(x, g[tag + "_x"])
+        np.testing.assert_array_equal(y, g[tag + "_y"])
+        np.testing.assert_array_equal(m, g[tag + "_mask"])
+    # the pad value is what Masking(-1) keys on, the mask marks exactly the data frames
+    assert np.all(g[tag + "_x"][g[tag + "_mask"][..., 0] == 0] == -1.0)
+    assert int(g[tag + "_mask"].sum()) == int(g["fidx"][-1, 1])
+
+
+def test_clip_mask_value_and_savefile_golden(golden_dir):
+    import os
+    from drnmf_b200 import audio_dataset as ad, snmf
+    g = np.load(os.path.join(golden_dir, "dataset.npz"))
+    for impl in (O.clip_x_to_y, ad.clip_x_to_y):
+        np.testing.assert_array_equal(impl(g["clip_x"].copy(), g["y_stack"], g["clip_xfidx"], g["fidx"]), g["clip_out"])
+    for cfg, want in (({"transform_x": "mag", "transform_y": "mag"}, -1.0), ({"transform_x": "x", "transform_y": "logmag"}, -1.0),
+                      ({"transform_x": "x", "transform_y": "y"}, 0.0)):
+        assert O.get_mask_value(cfg) == want and ad.get_mask_value(cfg) == want
+    prm = {"cf": "ed", "sparsity": np.float32(5.0), "max_iter": 200., "conv_eps": 1e-4, "display": 0., "random_seed": 2016.,
+           "r": np.int64(100)}
+    ref_name = str(g["savefile_name"])                        # produced by the reference's get_snmf_savefile
+    assert O.snmf_savefile_stem(prm, "dicts/") + ".hkl" == ref_name
+    assert snmf.get_snmf_savefile(prm, "dicts/") == ref_name[:-4] + ".npz"
+
+
+def test_scoring_snr_and_table():
+    from drnmf_b200 import scoring
+    rng = np.random.default_rng(3)
+    ref = rng.standard_normal(4000)
+    est = ref + 0.1 * rng.standard_normal(4000)
+    assert abs(scoring.snr_db(est, ref) - O.snr_db(est, ref)) < 1e-12
+    assert 19.0 < scoring.snr_db(est, ref) < 21.0
+    row, labels = scoring.compute_scores(est[:3900], ref)
+    assert labels[:2] == ["SDR", "SNR"] and len(row) == len(labels) == 6
+    assert abs(row[0] - O.sdr_db(est[:3900], ref)) < 1e-9 and np.isnan(row[2:]).all()
