@@ -6,21 +6,28 @@
 // its share of the weights each step: the step is tiled as
 //       M-tile m (128 output atoms)  x  K-split s (a slice of <=128 input atoms),   grid = (KS, MT), cluster = the KS
 // K-splits of one M-tile.
-//   * weights: a warpgroup loads the CTA's 128 x KSLICE block of S_k^T straight from L2 into registers, splits it into
-//     tf32 hi + remainder lo and writes both into TENSOR MEMORY (tcgen05.st).  The MMA takes its A operand from TMEM,
-//     which removes the per-instruction shared-memory read of A that dominates skinny-N tcgen05 products (measured:
-//     ~114 cycles per MMA with A in smem regardless of N) and frees 160 KB of smem.
+//   * weights: the CTA's 128 x KSLICE block of S_k^T - I goes to registers, is split into tf32 hi + remainder lo and
+//     written into TENSOR MEMORY (tcgen05.st).  The MMA takes its A operand from TMEM, which removes the per-instruction
+//     shared-memory read of A (with both operands in smem a skinny-N product is bound by the smem port) and frees smem.
+//     Latency mode (one batch tile): a producer thread TMA-prefetches the NEXT step's block into a 4 x 16 KB smem ring
+//     while the current step runs; for a symmetric S_k the CTAs below the diagonal fetch the mirrored block and read
+//     it transposed (only 54 of 96 MB of weights are touched per frame -> they stay in L2).  Throughput mode: straight
+//     from L2, two chunks in flight, loaded once per step and reused by every batch tile.
 //   * hidden state: B operand, Kslice x NB tile (hi and lo) TMA-loaded with 128B swizzle from a ping-pong global buffer.
-//   * product: tcgen05.mma kind::tf32, 3xTF32 compensation (W_lo.h_hi + W_hi.h_lo + W_hi.h_hi), fp32 accumulators in TMEM.
-//   * split-K reduction INSIDE the cluster over distributed shared memory (st.async + mbarrier complete_tx): CTA o owns
-//     rows [o*RO, (o+1)*RO) of the M-tile, sums the KS partials in a fixed order (deterministic), applies the fused
-//     epilogue (input projection, bias, rank-1 leak, relu, Keras mask carry) and writes hi/lo of the new hidden rows;
-//     a publisher thread issues one gpu-scope release per (step, tile); consumers acquire the flag and TMA their slice.
+//   * product: tcgen05.mma kind::tf32, 3xTF32 compensation (W_lo.h_hi + W_hi.h_lo + W_hi.h_hi), fp32 accumulators in
+//     TMEM, issued as back-to-back bursts from constant-offset descriptors (34 cycles per MMA = the pipe's rate).
+//   * split-K reduction INSIDE the cluster over distributed shared memory (staging + cp.async.bulk + mbarrier
+//     complete_tx): CTA o owns rows [o*RO, (o+1)*RO) of the M-tile, sums the KS partials in a fixed order
+//     (deterministic), applies the fused epilogue (identity part, input projection, bias, rank-1 leak, relu, Keras mask
+//     carry) and writes hi/lo of the new hidden rows; the owner warps release their stores with red.release.gpu
+//     (latency mode) or hand them to a publisher thread that batches the gpu-scope fences (throughput mode);
+//     consumers acquire the flag and TMA their slice.
 //   * utterances are cut into independent batch tiles of NB columns that are software-pipelined through the same
 //     TMEM-resident weights (hides the exchange latency when B is large, reuses every weight n_tiles times).
 //
-// Warp roles (512 threads): 1 hidden-state TMA (+flag acquire) | 2 MMA issuer / TMEM owner | 3 publisher |
-//     4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue) | 12-15 weight loaders (L2 -> regs -> TMEM).
+// Warp roles (512 threads): 0 weight producer (TMA ring) | 1 hidden-state TMA (+flag acquire) | 2 MMA issuer / TMEM
+//     owner | 3 publisher | 4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue) | 12-15 weight loaders
+//     (smem ring or L2 -> regs -> TMEM).
 #include "internal.h"
 
 #include <cstdio>
