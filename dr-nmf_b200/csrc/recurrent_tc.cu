@@ -47,6 +47,7 @@ struct RecArgs {
   float *actT_hi, *actT_lo;                  // training: K x Rp x (T*Bp) activations, time-major frames; else null
   // backward chain (BWD instantiation): dL/dH from the head, dL/dz^k out, state-gradient carry, partial row sums
   const float* dH; float *deltaT_hi, *deltaT_lo, *G, *psum2;
+  const float* alph_vec;                     // K x Rp step sizes for vector alph (untie_alph) in the backward chain, else null
   float d0mo_b, o0_b, ok_b;
   unsigned int* flags;
   int* dev_error;
@@ -730,6 +731,17 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         fetch_act(f2, u2, i2, act_next);
       }
       // ---- loads that do not depend on this item's product (this thread wrote them itself, or they are inputs) ----
+      // Vector alph: S_k^T = I - diag(1/alph_k) G (G symmetric) is not symmetric, but
+      //   sum_j delta_j S_k[i][j] = alph_k,i * sum_j (delta_j / alph_k,j) S_k^T[i][j],
+      // so the stored matrix still serves: the operand is written pre-scaled by 1/alph and the product is scaled back.
+      float4 a_post = make_float4(1.f, 1.f, 1.f, 1.f), a_pre = a_post;   // alph of the product's layer / 1/alph of the next one
+      if (a.alph_vec && mine) {
+        if (u > 0) a_post = __ldg(reinterpret_cast<const float4*>(a.alph_vec + (size_t)(K - u) * Rp + rowq));
+        if (la > 0) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.alph_vec + (size_t)la * Rp + rowq));
+          a_pre = make_float4(1.f / t4.x, 1.f / t4.y, 1.f / t4.z, 1.f / t4.w);
+        }
+      }
       float4 pre[CB];                                         // u > 0: own rows of delta^k (identity of S_k); u == 0: G
       float4 dh4[CB];                                         // u == 0: head gradient
       float mvt[CB], mvn[CB];                                 // mask of frame t / t+1
@@ -832,8 +844,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);
         ++it;
 #pragma unroll
-        for (int bi = 0; bi < CB; ++bi) {   // identity part of S_k: this owner's rows of delta^k
-          d[0][bi] += pre[bi].x; d[1][bi] += pre[bi].y; d[2][bi] += pre[bi].z; d[3][bi] += pre[bi].w;
+        for (int bi = 0; bi < CB; ++bi) {   // identity part of S_k: this owner's rows of the operand; scale back (vector alph)
+          d[0][bi] = (d[0][bi] + pre[bi].x) * a_post.x; d[1][bi] = (d[1][bi] + pre[bi].y) * a_post.y;
+          d[2][bi] = (d[2][bi] + pre[bi].z) * a_post.z; d[3][bi] = (d[3][bi] + pre[bi].w) * a_post.w;
         }
       }
       // ---- mask with the stored activation, store both layouts, row-sum partials ----
@@ -867,10 +880,11 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 #pragma unroll
         for (int bi = 0; bi < CB; ++bi) {
           const int b = i * NB + col0b + bi;
-          if (la > 0) {                                        // operand of the next product
+          if (la > 0) {                                        // operand of the next product (pre-scaled for vector alph)
             const size_t o2 = ((size_t)(u & 1) * a.Bp + b) * Rp + rowq;
-            __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(d[0][bi], d[1][bi], d[2][bi], d[3][bi]));
-            __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(d[0][bi]), tf32_lo(d[1][bi]), tf32_lo(d[2][bi]), tf32_lo(d[3][bi])));
+            const float o0v = d[0][bi] * a_pre.x, o1v = d[1][bi] * a_pre.y, o2v = d[2][bi] * a_pre.z, o3v = d[3][bi] * a_pre.w;
+            __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(o0v, o1v, o2v, o3v));
+            __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(o0v), tf32_lo(o1v), tf32_lo(o2v), tf32_lo(o3v)));
           } else if (b < a.B && mvt[bi] != 0.f) {
             // delta^0: start of the new state gradient  G = (d0-o0) delta^0 (+ rank-1 terms added at the next frame start)
             __stcg(reinterpret_cast<float4*>(a.G + (size_t)b * Rp + rowq),
@@ -1222,7 +1236,7 @@ static RecPlan choose_plan(const drnmf_handle* h, int B) {
 int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,
                             float* deltaT_lo, float* G, float* psum2, cudaStream_t st) {
   const int K = h->K, Rp = h->Rp;
-  if (K < 2 || h->alph_dim != 1) return 1;
+  if (K < 2) return 1;
   RecPlan p = choose_plan(h, B);
   if (!p.ok) return 1;
   RecArgs& a = p.a;
@@ -1231,6 +1245,7 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
   a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo;
   a.dH = dH; a.deltaT_hi = deltaT_hi; a.deltaT_lo = deltaT_lo; a.G = G; a.psum2 = psum2;
+  a.alph_vec = (h->alph_dim > 1) ? h->alph : nullptr;
   a.d0mo_b = h->u0_d - h->u0_o; a.o0_b = h->u0_o; a.ok_b = h->uk_o;
   a.dbg = nullptr;
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;

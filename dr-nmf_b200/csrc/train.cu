@@ -168,6 +168,7 @@ __global__ void k_xT(const float* __restrict__ xp, int B, int T, int Bp, int F, 
 // ---- backward chain (CUDA-core steps; the chain has the same all-to-all structure as the forward recurrence) -------
 struct BwdArgs {
   const float *ST, *actT, *mvalid, *dH;
+  const float* alph;   // K x Rp step sizes when alph is a vector (untie_alph), else null: see k_bwd_step
   float *deltaT_hi, *deltaT_lo, *G, *dbuf, *rs_part;
   int B, Bp, T, K, R, Rp, t, k, nc;
   size_t TB;
@@ -188,7 +189,8 @@ __global__ void k_bwd_frame_begin(BwdArgs a) {
       const float act = a.actT[((size_t)(a.K - 1) * a.Rp + j) * a.TB + col];
       if (act > 0.f) d = a.dH[bt * a.Rp + j] + a.G[(size_t)b * a.Rp + j];
     }
-    a.dbuf[(size_t)b * a.Rp + j] = d;                                   // slot 0
+    // slot 0: operand of the first product (pre-scaled by 1/alph for vector alph, see k_bwd_step)
+    a.dbuf[(size_t)b * a.Rp + j] = (a.alph && a.K > 1) ? d / a.alph[(size_t)(a.K - 1) * a.Rp + j] : d;
     const size_t o = ((size_t)(a.K - 1) * a.Rp + j) * a.TB + col;
     a.deltaT_hi[o] = d; a.deltaT_lo[o] = tf32_lo(d);
     local += d;
@@ -205,7 +207,9 @@ __global__ void k_bwd_frame_begin(BwdArgs a) {
 }
 
 // layer k -> k-1:  dg^{k-1}[b][i] = sum_j delta^k[b][j] S_k[i][j] ;  delta^{k-1} = dg .* 1[act^{k-1} > 0]
-// (S_k is symmetric for scalar alph: the stored S_k^T serves both directions.)
+// S_k is symmetric for scalar alph: the stored S_k^T serves both directions.  For vector alph (untie_alph)
+// S_k^T = I - diag(1/alph) G with G symmetric, hence  sum_j delta_j S_k[i][j] = alph_i * sum_j (delta_j / alph_j) S_k^T[i][j]:
+// the same stored matrix serves if the operand is pre-scaled by 1/alph_k and the product post-scaled by alph_k.
 __global__ void __launch_bounds__(SIMT_THREADS) k_bwd_step(BwdArgs a) {
   float acc[4][4], acc2[4][4];
   const int m0 = blockIdx.y * SIMT_BM, n0 = blockIdx.x * SIMT_BN;      // m = utterance, n = input atom i
@@ -227,9 +231,9 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_bwd_step(BwdArgs a) {
         float d = 0.f;
         if (j < a.R) {
           const float act = a.actT[((size_t)(a.k - 1) * a.Rp + j) * a.TB + col];
-          if (act > 0.f) d = acc[i][jj];
+          if (act > 0.f) d = a.alph ? acc[i][jj] * a.alph[(size_t)a.k * a.Rp + j] : acc[i][jj];
         }
-        dout[(size_t)b * a.Rp + j] = d;
+        dout[(size_t)b * a.Rp + j] = (a.alph && a.k > 1) ? d / a.alph[(size_t)(a.k - 1) * a.Rp + j] : d;
         const size_t o = ((size_t)(a.k - 1) * a.Rp + j) * a.TB + col;
         a.deltaT_hi[o] = d; a.deltaT_lo[o] = tf32_lo(d);
         part += d;
@@ -401,8 +405,6 @@ static int gemm(const drnmf_handle* h, GemmEpi epi, const GemmArgs& a, cudaStrea
 int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value, float* g_log_D,
                          float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
                          double* loss_host, float* irm_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  DRNMF_CHECK(h->alph_dim == 1, "training with untie_alph (vector alph) is not built: S_k is then asymmetric and the "
-                                "backward chain needs its transpose");
   DRNMF_CHECK(h->uk_d == h->uk_o, "training assumes U_k = c*11^T for k >= 1 (what build_alt creates)");
   TrainWs w = carve_train(h, B, T, ws);
   if (ws_bytes < w.bytes) { set_error("training workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
@@ -462,6 +464,7 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   ba.actT = w.fwd.actT_hi; ba.mvalid = w.fwd.mvalid; ba.dH = w.dH; ba.deltaT_hi = w.deltaT_hi; ba.deltaT_lo = w.deltaT_lo;
   ba.G = w.G; ba.dbuf = w.dbuf; ba.rs_part = w.rs_part; ba.B = B; ba.Bp = Bp; ba.T = T; ba.K = K; ba.R = R; ba.Rp = Rp; ba.TB = TB;
   ba.d0mo = h->u0_d - h->u0_o; ba.o0 = h->u0_o; ba.ok = h->uk_o; ba.nc = Rp / SIMT_BN;
+  ba.alph = (h->alph_dim > 1) ? h->alph : nullptr;
   const dim3 gstep(Rp / SIMT_BN, (B + SIMT_BM - 1) / SIMT_BM);
   int bwd_rc = 1;
   {
@@ -523,7 +526,7 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
     k_param_chain<<<(R + 7) / 8, 256, 0, st>>>(w.dDt, k >= 1, w.part, w.splits_x, w.Fx, h->Dt_hi + (size_t)k * Rp * Fp,
                                                 h->Wt_hi + (size_t)k * Rp * Fp, h->bias + (size_t)k * Rp, h->alph + (size_t)k * Rp,
                                                 F, R, Rp, Fp, gD, (tied_D && k > 0) ? 1 : 0, w.rowacc);
-    k_scalar_grads<<<1, 256, 0, st>>>(w.rowacc, w.rowS, k >= 1 ? Rp / 32 : 0, R, h->alph_dim, g_log_alph + (tied_a ? 0 : k), g_log_lam1 + (tied_l ? 0 : k),
+    k_scalar_grads<<<1, 256, 0, st>>>(w.rowacc, w.rowS, k >= 1 ? Rp / 32 : 0, R, h->alph_dim, g_log_alph + (tied_a ? 0 : (size_t)k * h->alph_dim), g_log_lam1 + (tied_l ? 0 : k),
                                       (tied_a && k > 0) ? 1 : 0, (tied_l && k > 0) ? 1 : 0);
     count_launch(2);
   }

@@ -392,7 +392,8 @@ def test_snmf_python_mirror_chunk_driver(golden_dir):
 # ---- training: loss + hand-written BPTT against torch.autograd on the float64 oracle ---------------------------
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("case", [dict(F=33, R=16, K=3, B=3, T=6, tied=False), dict(F=65, R=40, K=4, B=5, T=8, tied=False),
-                                  dict(F=40, R=24, K=3, B=2, T=5, tied=True)])
+                                  dict(F=40, R=24, K=3, B=2, T=5, tied=True),
+                                  dict(F=33, R=24, K=4, B=3, T=6, tied=False, vec=True)])     # untie_alph (enhance.py:225-226)
 def test_loss_and_grads_vs_autograd(case, impl):
     from oracle import torch_oracle as TO
     F, R, K, B, T = (case[k] for k in "FRKBT")
@@ -400,6 +401,8 @@ def test_loss_and_grads_vs_autograd(case, impl):
     p = synth.model_params(F, R, K, alph=15.0, lam1=0.3, untied=not case["tied"])
     if not case["tied"]:
         p["log_alph"] = (p["log_alph"] + 0.05 * rng.standard_normal(K)).astype(np.float32)
+    if case.get("vec"):   # one step size per atom: S_k is no longer symmetric, the backward chain must cope
+        p["log_alph"] = (p["log_alph"][:, None] + 0.15 * rng.standard_normal((K, R))).astype(np.float32)
     x = (np.abs(rng.standard_normal((B, T, F))) * 2).astype(np.float32)
     y = (x * rng.uniform(0.2, 0.9, size=x.shape)).astype(np.float32)
     lens = rng.integers(2, T + 1, size=B); lens[0] = T
