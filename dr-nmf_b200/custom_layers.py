@@ -81,9 +81,17 @@ class SimpleDeepRNN:
                 return self.alt_params[labels[0]][None]
             return torch.stack([self.alt_params[l] for l in labels])
 
+        # log_U1 / log_Uk are R x R constants of the a*I + b*11^T form (enhance.py:163-167); verifying that structure
+        # means a pass over both matrices on the host, so the (diag, off) pairs are cached until the tensors change
+        # (a training step rebuilds the parameter set every iteration)
+        key = tuple((id(self.alt_params[n]), getattr(self.alt_params[n], "_version", 0)) for n in ("log_U1", "log_Uk"))
+        if getattr(self, "_u_key", None) != key:
+            from .engine import structured_u
+            self._u_pairs = (structured_u(self.alt_params["log_U1"], "log_U1"), structured_u(self.alt_params["log_Uk"], "log_Uk"))
+            self._u_key = key
         return {"log_D": stack("log_D"), "log_alph": stack("log_alph").reshape(len(set(lab["log_alph"])), -1),
-                "log_lam1": stack("log_lam1").reshape(-1), "log_U1": self.alt_params["log_U1"],
-                "log_Uk": self.alt_params["log_Uk"], "log_h0": self.log_h0, "k_clean": k_clean, "k_noise": k_noise}
+                "log_lam1": stack("log_lam1").reshape(-1), "log_U1": self._u_pairs[0], "log_Uk": self._u_pairs[1],
+                "log_h0": self.log_h0, "k_clean": k_clean, "k_noise": k_noise}
 
     @property
     def weights(self):
