@@ -156,19 +156,20 @@ __global__ void k_mu_h(float* __restrict__ Ht_hi, float* __restrict__ Ht_lo, flo
 
 // W update for a block of 32 columns (all F rows): reduce split-K partials in split order, column sums, multiplicative
 // update of the updated columns, renormalisation of every column (:262), both layouts + remainders.
-// grid ceil(R/32), block (32, 8).  W is read from / written to Wm (F x Rk).
-__global__ void k_mu_w(float* __restrict__ Wm_hi, float* __restrict__ Wm_lo, float* __restrict__ WT_hi,
+// grid ceil(R/32), block (32, ny <= 32).  W is read from / written to Wm (F x Rk).
+__global__ void __launch_bounds__(1024) k_mu_w(float* __restrict__ Wm_hi, float* __restrict__ Wm_lo, float* __restrict__ WT_hi,
                        float* __restrict__ WT_lo, float* __restrict__ VHp, float* __restrict__ LHp, int splits, int F, int R,
                        int Rk, int Fk, float flr, const uint8_t* __restrict__ w_update) {
-  __shared__ float red_v[8][33], red_l[8][33];
+  __shared__ float red_v[32][33], red_l[32][33];
   __shared__ float sv[32], sl[32], nrm[32];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const int ny = blockDim.y;                                 // rows are dealt to the ny thread rows (<= 32)
   const size_t sstride = (size_t)F * Rk;
   const bool upd = (c < R) && (!w_update || w_update[c]);
   // pass 1: VH, LH = sum over splits (stored back into split 0), column sums of VH.*W and LH.*W
   float a_v = 0.f, a_l = 0.f;
   if (c < R)
-    for (int f = threadIdx.y; f < F; f += 8) {
+    for (int f = threadIdx.y; f < F; f += ny) {
       const size_t o = (size_t)f * Rk + c;
       float vh = 0.f, lh = 0.f;
       for (int s = 0; s < splits; ++s) { vh += VHp[s * sstride + o]; lh += LHp[s * sstride + o]; }
@@ -180,14 +181,14 @@ __global__ void k_mu_w(float* __restrict__ Wm_hi, float* __restrict__ Wm_lo, flo
   __syncthreads();
   if (threadIdx.y == 0) {
     float tv = 0.f, tl = 0.f;
-    for (int y = 0; y < 8; ++y) { tv += red_v[y][threadIdx.x]; tl += red_l[y][threadIdx.x]; }
+    for (int y = 0; y < ny; ++y) { tv += red_v[y][threadIdx.x]; tl += red_l[y][threadIdx.x]; }
     sv[threadIdx.x] = tv; sl[threadIdx.x] = tl;
   }
   __syncthreads();
   // pass 2: multiplicative update, accumulate the new column norm
   float a_n = 0.f;
   if (c < R)
-    for (int f = threadIdx.y; f < F; f += 8) {
+    for (int f = threadIdx.y; f < F; f += ny) {
       const size_t o = (size_t)f * Rk + c;
       float w = Wm_hi[o];
       if (upd) {
@@ -202,13 +203,13 @@ __global__ void k_mu_w(float* __restrict__ Wm_hi, float* __restrict__ Wm_lo, flo
   __syncthreads();
   if (threadIdx.y == 0) {
     float t = 0.f;
-    for (int y = 0; y < 8; ++y) t += red_v[y][threadIdx.x];
+    for (int y = 0; y < ny; ++y) t += red_v[y][threadIdx.x];
     nrm[threadIdx.x] = sqrtf(t);
   }
   __syncthreads();
   // pass 3: normalise, write both layouts and remainders
   if (c < Rk)
-    for (int f = threadIdx.y; f < F; f += 8) {
+    for (int f = threadIdx.y; f < F; f += ny) {
       const size_t o = (size_t)f * Rk + c;
       const float w = (c < R) ? Wm_hi[o] / nrm[threadIdx.x] : 0.f;
       Wm_hi[o] = w; Wm_lo[o] = tf32_lo(w);
@@ -327,16 +328,18 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
     if (any_w_update) {
       if ((rc = corr_gemm(w.Vm_hi, w.Vm_lo, w.VHp))) return rc;
       if ((rc = corr_gemm(w.Lm_hi, w.Lm_lo, w.LHp))) return rc;
-      int splits_w = w.splits;
-      if (allreduce) {   // frames are sharded over ranks: V H^T and L H^T are sums over ALL frames (SURVEY 8e)
-        const size_t ne = (size_t)F * Rk;
+      // split-K partials -> split 0 with one thread per element (fixed split order): the update kernel below has only
+      // ceil(R/32) CTAs, and summing the partials there made it the largest item of an iteration (830 us of 2.2 ms)
+      const size_t ne = (size_t)F * Rk;
+      if (w.splits > 1) {
         k_reduce_splits<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(w.VHp, w.splits, ne);
         k_reduce_splits<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(w.LHp, w.splits, ne);
         count_launch(2);
-        if (allreduce(user, w.VHp, ne, 0, st) || allreduce(user, w.LHp, ne, 0, st)) { set_error("all-reduce callback failed"); return DRNMF_ERR_CUDA; }
-        splits_w = 1;
       }
-      k_mu_w<<<(Rk + 31) / 32, tb, 0, st>>>(w.Wm_hi, w.Wm_lo, w.WT_hi, w.WT_lo, w.VHp, w.LHp, splits_w, F, R, Rk, Fk, flr, w_update);
+      if (allreduce) {   // frames are sharded over ranks: V H^T and L H^T are sums over ALL frames (SURVEY 8e)
+        if (allreduce(user, w.VHp, ne, 0, st) || allreduce(user, w.LHp, ne, 0, st)) { set_error("all-reduce callback failed"); return DRNMF_ERR_CUDA; }
+      }
+      k_mu_w<<<(Rk + 31) / 32, dim3(32, 32), 0, st>>>(w.Wm_hi, w.Wm_lo, w.WT_hi, w.WT_lo, w.VHp, w.LHp, 1, F, R, Rk, Fk, flr, w_update);
       count_launch();
       if ((rc = lambda_gemm())) return rc;
     }
