@@ -467,7 +467,10 @@ int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const float* stack_
   k_enh_tables<<<(B + 127) / 128, 128, 0, st>>>(e.frames, B, T, L, e.fidx, e.out_offs);
   count_launch();
   DRNMF_CUDA(cudaMemsetAsync(e.audio, 0, (size_t)B * L * 4, st));
-  if ((rc = drnmf_forward(h, e.x, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream))) return rc;
+  if ((rc = drnmf_forward(h, e.x, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream))) {
+    cudaStreamSynchronize(h->side);      // the caller may release the workspace: let the side copy land first
+    return rc;
+  }
   DRNMF_CUDA(cudaStreamWaitEvent(st, h->ev_side[1], 0));
   if ((rc = launch_mask_istft(e.stack, e.irm, e.fidx, e.out_offs, B, T, N, hop, (int64_t)BT, e.frames_tmp, e.audio, st))) return rc;
   DRNMF_CUDA(cudaMemcpyAsync(audio_out_host, e.audio, (size_t)B * L * 4, cudaMemcpyDeviceToHost, st));
