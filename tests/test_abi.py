@@ -49,3 +49,24 @@ def test_structured_u_detection():
     assert abs(d - 1.0) < 1e-6 and abs(o - 1e-7) < 1e-12
     with pytest.raises(NotImplementedError):
         engine.structured_u(np.random.default_rng(0).standard_normal((R, R)))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's baseline arm) runs without a GPU and prints ONE JSON line with the
+    contract keys; it is the only bench leg allowed to execute oracle/."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-utts", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-1500:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
