@@ -590,3 +590,42 @@ def test_dataset_padded_tensors_feed_the_network():
     H, irm = eng.forward(torch.as_tensor(x, device="cuda"))
     Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
     assert max(rel_err(H.cpu().numpy(), Ho)) < TOL and max(rel_err(irm.cpu().numpy(), irmo)) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", IMPLS)
+def test_edge_cases_fully_masked_single_frame_single_utterance(impl):
+    """Edge cases of the masked scan: an utterance without any valid frame (outputs stay zero, its state never moves),
+    T = 1, B = 1, and a batch whose only valid frame is the last one."""
+    F, R, K = 33, 24, 3
+    rng = np.random.default_rng(2)
+    p = synth.model_params(F, R, K, alph=12.0)
+    eng = engine.DrnmfEngine(F, R, K, impl=impl)
+    eng.set_params(p)
+    # (a) one fully masked utterance next to a normal one
+    x = (np.abs(rng.standard_normal((2, 5, F))) * 2).astype(np.float32)
+    x[1] = -1.0
+    H, irm = eng.forward(torch.as_tensor(x, device="cuda"))
+    Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+    assert np.all(H[1].cpu().numpy() == 0.0) and np.all(Ho[1] == 0.0)
+    assert max(rel_err(H.cpu().numpy(), Ho)) < TOL and max(rel_err(irm[0].cpu().numpy(), irmo[0])) < TOL
+    # (b) T = 1, B = 1
+    x1 = (np.abs(rng.standard_normal((1, 1, F))) * 2).astype(np.float32)
+    H1, irm1 = eng.forward(torch.as_tensor(x1, device="cuda"))
+    Ho1, irmo1 = O.drnmf_forward(x1, p, dtype=np.float64)
+    assert max(rel_err(H1.cpu().numpy(), Ho1)) < TOL and max(rel_err(irm1.cpu().numpy(), irmo1)) < TOL
+    # (c) only the last frame valid: everything before is zero, the last frame starts from h0
+    x2 = np.full((3, 4, F), -1.0, np.float32)
+    x2[:, -1] = (np.abs(rng.standard_normal((3, F))) * 2).astype(np.float32)
+    H2, _ = eng.forward(torch.as_tensor(x2, device="cuda"))
+    Ho2 = O.rnn_forward(x2, p)
+    assert np.all(H2[:, :-1].cpu().numpy() == 0.0)
+    assert max(rel_err(H2.cpu().numpy(), Ho2)) < TOL
+    # gradients with a fully masked utterance in the batch: finite, and equal to the batch without it
+    y = (x * 0.5).astype(np.float32); y[1] = -1.0
+    ls, ms, g = eng.loss_and_grads(torch.as_tensor(x, device="cuda"), torch.as_tensor(y, device="cuda"))
+    ls0, ms0, g0 = eng.loss_and_grads(torch.as_tensor(x[:1], device="cuda"), torch.as_tensor(y[:1], device="cuda"))
+    assert ms == ms0 == 5.0 and abs(ls - ls0) < 1e-5 * abs(ls0)
+    for key in ("log_D", "log_alph", "log_h0", "k_clean"):
+        a, b = g[key].cpu().numpy(), g0[key].cpu().numpy()
+        assert np.isfinite(a).all() and rel_err(a, b)[0] < 1e-5, key
