@@ -56,6 +56,8 @@ def load():
         "drnmf_forward": (i32, [vp, vp, i32, i32, f32, vp, vp, vp, sz, vp]),
         "drnmf_stage_times": (i32, [vp, C.POINTER(f32)]),
         "drnmf_recurrent_config": (i32, [vp, C.POINTER(i32)]),
+        "drnmf_recurrent_config2": (i32, [vp, i32, C.POINTER(i32)]),
+        "drnmf_debug_inject_error": (i32, [vp, i32, vp]),
         "drnmf_get_derived": (i32, [vp, i32, i32, vp, vp]),
         "drnmf_padded_dims": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
         "drnmf_stft_frames": (i32, [i32, i32, i32]),

@@ -62,6 +62,8 @@ static int check_dev_error(drnmf_handle* h, cudaStream_t st, const char* what) {
   DRNMF_CUDA(cudaStreamSynchronize(st));
   int g = gemm_device_error(st);
   if (v != 0 || g != 0) {
+    // report once, then clear: a transient failure (e.g. a watchdog expiry under SM contention) must not latch
+    if (v != 0) cudaMemsetAsync(h->dev_error, 0, sizeof(int), st);
     set_error("%s: device-side failure code %d (gemm %d): a kernel watchdog expired or a protocol check failed", what, v, g);
     return DRNMF_ERR_DEVICE;
   }
@@ -259,6 +261,24 @@ int drnmf_recurrent_config(const drnmf_handle* h, int* cfg9) {
   DRNMF_CHECK(h && cfg9, "NULL argument");
   cfg9[0] = h->last_rec_impl;
   for (int i = 0; i < 8; ++i) cfg9[1 + i] = h->rec_cfg[i];
+  return DRNMF_OK;
+}
+
+int drnmf_recurrent_config2(const drnmf_handle* h, int which, int* cfg10) {
+  DRNMF_CHECK(h && cfg10, "NULL argument");
+  DRNMF_CHECK(which == 0 || which == 1, "which must be 0 (forward) or 1 (backward chain)");
+  cfg10[0] = which ? h->last_bwd_impl : h->last_rec_impl;
+  for (int i = 0; i < 8; ++i) cfg10[1 + i] = which ? h->bwd_cfg[i] : h->rec_cfg[i];
+  cfg10[9] = which ? h->bwd_groups : h->rec_groups;
+  return DRNMF_OK;
+}
+
+int drnmf_debug_inject_error(drnmf_handle* h, int code, void* stream) {
+  DRNMF_CHECK(h, "NULL handle");
+  int rc = check_device(h);
+  if (rc) return rc;
+  DRNMF_CUDA(cudaMemcpyAsync(h->dev_error, &code, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  DRNMF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return DRNMF_OK;
 }
 

@@ -322,10 +322,14 @@ static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
     if ((rc = make_tmap_2d(&tB2_hi, a.B2_hi, a.Kd, a.N, a.ldb, TC_BK, TC_BN))) return rc;
     if ((rc = make_tmap_2d(&tB2_lo, a.B2_lo, a.Kd, a.N, a.ldb, TC_BK, TC_BN))) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per context: keep one flag per device
+  static bool attr_set[DRNMF_MAX_DEVICES] = {};
+  int dev = 0;
+  DRNMF_CUDA(cudaGetDevice(&dev));
+  DRNMF_CHECK(dev >= 0 && dev < DRNMF_MAX_DEVICES, "device ordinal %d out of range", dev);
+  if (!attr_set[dev]) {
     DRNMF_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid((a.M + TC_BM - 1) / TC_BM, (a.N + TC_BN - 1) / TC_BN, a.splits > 1 ? a.splits : 1);
   k_gemm_tc<EPI><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo, a, dev_error);
@@ -334,30 +338,48 @@ static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
   return DRNMF_OK;
 }
 
-static int* g_gemm_dev_error = nullptr;   // lazily allocated error word for handle-less GEMM users
+// lazily allocated error word for handle-less GEMM users, one per device (device memory is per device)
+static int* g_gemm_dev_error[DRNMF_MAX_DEVICES] = {};
+
+static int gemm_error_word(int** out) {
+  int dev = 0;
+  DRNMF_CUDA(cudaGetDevice(&dev));
+  DRNMF_CHECK(dev >= 0 && dev < DRNMF_MAX_DEVICES, "device ordinal %d out of range", dev);
+  if (!g_gemm_dev_error[dev]) {
+    DRNMF_CUDA(cudaMalloc(&g_gemm_dev_error[dev], sizeof(int)));
+    DRNMF_CUDA(cudaMemset(g_gemm_dev_error[dev], 0, sizeof(int)));
+  }
+  *out = g_gemm_dev_error[dev];
+  return DRNMF_OK;
+}
 
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
   DRNMF_CHECK(a.lda % 4 == 0 && a.ldb % 4 == 0, "tcgen05 GEMM needs row strides that are multiples of 4 floats");
   if (epi == EPI_STORE || epi == EPI_GRAM) DRNMF_CHECK(a.ldc % 4 == 0 && a.N_valid % 16 == 0, "tcgen05 GEMM store needs ldc%%4==0, N%%16==0");
   if (epi == EPI_LAMBDA) DRNMF_CHECK(a.ldc % 4 == 0 && a.ldv % 4 == 0, "EPI_LAMBDA needs ldc%%4==0 and ldv%%4==0");
-  if (!g_gemm_dev_error) {
-    DRNMF_CUDA(cudaMalloc(&g_gemm_dev_error, sizeof(int)));
-    DRNMF_CUDA(cudaMemset(g_gemm_dev_error, 0, sizeof(int)));
-  }
+  int* errw = nullptr;
+  int rc = gemm_error_word(&errw);
+  if (rc) return rc;
   switch (epi) {
-    case EPI_STORE: return launch_tc_impl<EPI_STORE>(a, st, g_gemm_dev_error);
-    case EPI_GRAM:  return launch_tc_impl<EPI_GRAM>(a, st, g_gemm_dev_error);
-    case EPI_RECON: return launch_tc_impl<EPI_RECON>(a, st, g_gemm_dev_error);
-    case EPI_LAMBDA: return launch_tc_impl<EPI_LAMBDA>(a, st, g_gemm_dev_error);
+    case EPI_STORE: return launch_tc_impl<EPI_STORE>(a, st, errw);
+    case EPI_GRAM:  return launch_tc_impl<EPI_GRAM>(a, st, errw);
+    case EPI_RECON: return launch_tc_impl<EPI_RECON>(a, st, errw);
+    case EPI_LAMBDA: return launch_tc_impl<EPI_LAMBDA>(a, st, errw);
   }
   return DRNMF_ERR_INVALID;
 }
 
+// Reads the current device's GEMM error word and, when it is set, clears it again (on the stream): a transient
+// watchdog expiry is reported once and does not poison every later call of the process.
 int gemm_device_error(cudaStream_t st) {
-  if (!g_gemm_dev_error) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DRNMF_MAX_DEVICES) return -1;
+  int* w = g_gemm_dev_error[dev];
+  if (!w) return 0;
   int v = 0;
-  if (cudaMemcpyAsync(&v, g_gemm_dev_error, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaMemcpyAsync(&v, w, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  if (v != 0) cudaMemsetAsync(w, 0, sizeof(int), st);
   return v;
 }
 

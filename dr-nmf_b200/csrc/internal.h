@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#define DRNMF_MAX_DEVICES 64
+
 struct drnmf_handle {
   int F, R, K, r;      // bins, atoms (speech+noise), layers, atoms per source
   int Rp, Fp, Fq;      // R padded to 128, F padded to 32 (GEMM K dim), F padded to 128 (GEMM N dim rows)
@@ -30,7 +32,10 @@ struct drnmf_handle {
   cudaEvent_t ev_side[2];  // [0] main stream reached the call, [1] side copy done
   bool side_ready;
   int last_rec_impl;       // 0 = persistent tcgen05 kernel, 1 = SIMT per-step kernels (last drnmf_forward)
+  int last_bwd_impl;       // the same for the backward chain of the last drnmf_loss_and_grads
   int rec_cfg[8];          // NB, KS, MT, ATOMS, n_tiles, WST, HST, RST of the last persistent launch
+  int rec_groups;          // batch groups (grid.z) of the last persistent launch
+  int bwd_cfg[8], bwd_groups;   // the same for the backward chain of the last drnmf_loss_and_grads
 };
 
 namespace drnmf {

@@ -32,6 +32,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace drnmf {
 
@@ -55,7 +56,8 @@ struct RecArgs {
   long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
   // shapes
   int B, Bp, T, K, R, Rp;
-  int MT, KS, RO, ATOMS, KSLICE, n_tiles;
+  int MT, KS, RO, ATOMS, KSLICE, n_tiles;      // n_tiles = batch tiles per batch group (grid.z groups run on disjoint SMs)
+  int n_tiles_total;                         // batch tiles of the whole batch
   int sym;                                   // S_k symmetric and square blocks: CTAs below the diagonal read the mirrored block
   int pub_unit;                              // flag increments per (CTA, item): 1 = publisher thread, 4 = each owner warp releases its own stores
   int KCH, NCH;                              // weight chunk held in TMEM at a time (<= 128 K-columns), chunks per K-slice
@@ -109,7 +111,28 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int ta
 template <int NB, bool BWD, int CB>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
-               const __grid_constant__ CUtensorMap tmW, RecArgs a) {
+               const __grid_constant__ CUtensorMap tmW, const RecArgs a_in) {
+  // Batch groups: utterances are independent, so grid.z groups of (KS x MT) CTAs each run the whole chain on their own
+  // contiguous range of batch tiles (disjoint SMs, own flags, no interaction).  Everything indexed by the utterance is
+  // re-based once here; below, tile i / utterance b are group-local.
+  RecArgs a = a_in;
+  const int tile0 = blockIdx.z * a_in.n_tiles;
+  const int boff = tile0 * NB;
+  if (gridDim.z > 1) {
+    const size_t bo = (size_t)boff;
+    a.n_tiles = min(a_in.n_tiles, a_in.n_tiles_total - tile0);
+    a.B = min(a_in.B - boff, a.n_tiles * NB);
+    a.mvalid += bo * a.T; a.flags += (size_t)tile0 * a.MT;
+    a.hb_hi += bo * a.Rp; a.hb_lo += bo * a.Rp;
+    if (!BWD) {
+      a.XW += bo * a.T * a.K * a.Rp; a.state += bo * a.Rp; a.psum += bo;
+      a.Hp_hi += bo * a.T * a.Rp; a.Hp_lo += bo * a.T * a.Rp;
+      if (a.H_user) a.H_user += bo * a.T * a.R;
+    } else {
+      a.dH += bo * a.T * a.Rp; a.deltaT_hi += bo; a.deltaT_lo += bo; a.G += bo * a.Rp; a.psum2 += bo;
+    }
+    if (a.actT_hi) { a.actT_hi += bo; a.actT_lo += bo; }
+  }
   // No static shared memory in this kernel: the dynamic window starts 1024-aligned (checked below).  Keeping `smem`
   // a plain __shared__ array (no integer round-trip) lets the compiler emit LDS/STS instead of generic LD/ST.
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -123,7 +146,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     if (threadIdx.x == 0) atomicCAS(a.dev_error, 0, 299);
     return;
   }
-  const bool dbg_on = (a.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == a.dbg_m;
+  const bool dbg_on = (a.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == a.dbg_m && blockIdx.z == 0;
   long long dbg_acc[7] = {0, 0, 0, 0, 0, 0, 0};
   const long long dbg_t0 = clock64();
   const int s = blockIdx.x;            // K-split == rank in cluster
@@ -202,7 +225,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             RT_TIMED(2, fence_proxy_async_global());   // generic-proxy writes of the owners -> async-proxy (TMA) reads   // generic-proxy writes of the owners -> async-proxy (TMA) reads
             uint8_t* dst = smem + a.off_h + hs * a.h_stage_bytes;
             for (int at = 0; at < ATOMS; ++at) {   // one barrier per 32-atom slab: the MMA starts on the first to land
-              const int c0 = s * a.KSLICE + at * 32, c1 = slot * a.Bp + i * NB;
+              const int c0 = s * a.KSLICE + at * 32, c1 = slot * a.Bp + boff + i * NB;   // the tensor map covers all groups
               mbar_expect_tx(&bars->h_full[hs][at], 2 * H_ATOM_BYTES);
               tma_load_2d(dst + (2 * at) * H_ATOM_BYTES, &tmH_hi, &bars->h_full[hs][at], c0, c1);
               tma_load_2d(dst + (2 * at + 1) * H_ATOM_BYTES, &tmH_lo, &bars->h_full[hs][at], c0, c1);
@@ -1101,19 +1124,28 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct RecPlan { int NB, KS, MT, RO, ATOMS, KSLICE, n_tiles, WST, HST, RST, CB; size_t smem; RecArgs a; bool ok; const char* why; };
+// n_tiles = batch tiles per group, G = batch groups (grid.z), n_tiles_total = tiles of the whole batch
+struct RecPlan { int NB, KS, MT, RO, ATOMS, KSLICE, n_tiles, n_tiles_total, G, WST, HST, RST, CB; size_t smem; RecArgs a; bool ok; const char* why; };
 
-static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
+static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int G) {
   RecPlan p{};
   p.ok = false;
   const int Rp = h->Rp;
   p.MT = Rp / 128;
   p.NB = NB;
-  p.n_tiles = (B + p.NB - 1) / p.NB;
+  p.n_tiles_total = (B + p.NB - 1) / p.NB;
+  if (G < 1) G = 1;
+  if (G > p.n_tiles_total) G = p.n_tiles_total;
+  p.n_tiles = (p.n_tiles_total + G - 1) / G;
+  p.G = (p.n_tiles_total + p.n_tiles - 1) / p.n_tiles;      // no empty group
   if (Rp % (KS * 32) != 0 || p.MT * KS > h->num_sms) { p.why = "no (M-tile x K-split) grid fits the device"; return p; }
   p.KS = KS; p.RO = 128 / KS; p.KSLICE = Rp / KS; p.ATOMS = p.KSLICE / 32;
   if (p.KSLICE > 512 || (p.KSLICE > 128 && p.KSLICE % 128 != 0)) { p.why = "K-slice wider than 512 atoms (four TMEM weight chunks)"; return p; }
-  p.a.pub_unit = (p.n_tiles == 1 && !getenv("DRNMF_REC_PUBLISHER")) ? 4 : 1;
+  {   // who publishes: every owner warp with its own red.release (default for one tile per group) or a publisher thread
+    const char* e = getenv("DRNMF_REC_PUB");
+    const bool direct = e ? !strcmp(e, "direct") : (p.n_tiles == 1);
+    p.a.pub_unit = direct ? 4 : 1;
+  }
   p.a.KCH = p.KSLICE > 128 ? 128 : p.KSLICE;
   p.a.NCH = p.KSLICE / p.a.KCH;
   if (p.RO * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
@@ -1155,6 +1187,7 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB) {
   p.smem = (size_t)off + 1024;
   p.a.h_stage_bytes = h_stage; p.a.red_slot_bytes = red_slot;
   p.a.MT = p.MT; p.a.KS = p.KS; p.a.RO = p.RO; p.a.ATOMS = p.ATOMS; p.a.KSLICE = p.KSLICE; p.a.n_tiles = p.n_tiles;
+  p.a.n_tiles_total = p.n_tiles_total;
   p.a.WST = p.WST; p.a.HST = p.HST; p.a.RST = p.RST;
   p.ok = true;
   return p;
@@ -1173,21 +1206,30 @@ static RecKernel rec_kernel(const RecPlan& p, bool bwd) {
 
 static void rec_launch_config(const RecPlan& p, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, cudaStream_t st) {
   cfg = cudaLaunchConfig_t{};
-  cfg.gridDim = dim3(p.KS, p.MT, 1);
+  cfg.gridDim = dim3(p.KS, p.MT, p.G);
   cfg.blockDim = dim3(RT_THREADS, 1, 1);
   cfg.dynamicSmemBytes = p.smem;
   cfg.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.KS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  // The CTAs spin on flags written by other clusters, so the whole grid must be co-resident.  A cooperative launch
+  // makes the driver check that at launch time (SMs taken by another stream / process / NCCL kernel -> the launch
+  // fails cleanly with cudaErrorCooperativeLaunchTooLarge instead of running into the device-side watchdog).
+  static const bool coop = getenv("DRNMF_REC_COOP") && !strcmp(getenv("DRNMF_REC_COOP"), "1");   // TODO default on once verified
+  if (coop) {
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.numAttrs = 2;
+  }
 }
 
 // co-resident clusters the device offers for this plan (the kernel spins on peers: all CTAs must be resident)
-static int rec_max_clusters(const RecPlan& p, int* out) {
-  RecKernel kern = rec_kernel(p, false);
+static int rec_max_clusters(const RecPlan& p, bool bwd, int* out) {
+  RecKernel kern = rec_kernel(p, bwd);          // the instantiation that will be launched (register use differs)
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
-  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
   rec_launch_config(p, cfg, attr, nullptr);
   *out = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(out, kern, &cfg);
@@ -1200,7 +1242,7 @@ static int launch_rec(const RecPlan& p, bool bwd, const CUtensorMap& tH_hi, cons
   RecKernel kern = rec_kernel(p, bwd);
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
-  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
   rec_launch_config(p, cfg, attr, st);
   DRNMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tH_hi, tH_lo, tW, p.a));
   count_launch();
@@ -1208,26 +1250,43 @@ static int launch_rec(const RecPlan& p, bool bwd, const CUtensorMap& tH_hi, cons
 }
 
 // Candidate tilings, preferred first: more K-splits = more SMs streaming the weights; the cluster (= the K-splits of
-// one M-tile) must be co-resident MT times, which depends on the board's GPC layout -> ask the occupancy API.
-static RecPlan choose_plan(const drnmf_handle* h, int B) {
+// one M-tile) must be co-resident MT times per batch group, which depends on the board's GPC layout -> ask the
+// occupancy API.  Batch groups: utterances are independent, so when the device can host G x MT clusters the batch is
+// cut into G groups on disjoint SMs (B = 64 at R = 1000: two groups of one 32-utterance tile on 128 SMs; a 32-column
+// step is shorter than a 64-column one, and throughput batches use twice the tensor pipes).  The batch tile is the
+// widest one that still leaves a tile for every group.
+static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
   RecPlan p{};
   p.ok = false; p.why = "no candidate tiling";
   const char* env_ks = getenv("DRNMF_REC_KS");
   const char* env_nb = getenv("DRNMF_REC_NB");
+  const char* env_g = getenv("DRNMF_REC_G");
   for (int KS = 16; KS >= 1 && !p.ok; KS >>= 1) {
     if (env_ks && atoi(env_ks) != KS) continue;
+    // co-resident clusters for this cluster size (probe with the smallest tile: shared memory is at the limit anyway)
+    RecPlan probe = plan_recurrent(h, B, KS, 16, 1);
+    if (!probe.ok) { p.why = probe.why; continue; }
+    int mc = 0;
+    rec_max_clusters(probe, bwd, &mc);
+    if (mc < probe.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
+    const int g_max = env_g ? atoi(env_g) : mc / probe.MT;
     for (int NB = 64; NB >= 16 && !p.ok; NB >>= 1) {
       if (env_nb && atoi(env_nb) != NB) continue;
+      // default: the widest tile that still gives every group a tile (NB = 16 is the floor)
+      if (!env_nb && NB > 16 && (B + NB - 1) / NB < g_max && B > NB / 2) continue;
       if (!env_nb && ((NB == 64 && B <= 32) || (NB == 32 && B <= 16))) continue;
-      RecPlan c = plan_recurrent(h, B, KS, NB);
-      if (!c.ok) { if (!p.why || !p.ok) p.why = c.why; continue; }
-      int mc = 0;
-      rec_max_clusters(c, &mc);
-      if (mc < c.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
-      p = c;
+      for (int G = g_max; G >= 1 && !p.ok; --G) {
+        RecPlan c = plan_recurrent(h, B, KS, NB, G);
+        if (!c.ok) { p.why = c.why; continue; }
+        if (c.G != G && G != g_max) continue;       // this group count was already tried
+        int mc2 = 0;
+        rec_max_clusters(c, bwd, &mc2);
+        if (mc2 < c.MT * c.G) { p.why = "not enough co-resident clusters for any tiling"; continue; }
+        p = c;
+      }
     }
   }
-  if (p.ok && p.n_tiles * p.MT > 16384) { p.ok = false; p.why = "too many batch tiles"; }
+  if (p.ok && p.n_tiles_total * p.MT > 16384) { p.ok = false; p.why = "too many batch tiles"; }
   return p;
 }
 
@@ -1237,8 +1296,10 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
                             float* deltaT_lo, float* G, float* psum2, cudaStream_t st) {
   const int K = h->K, Rp = h->Rp;
   if (K < 2) return 1;
-  RecPlan p = choose_plan(h, B);
-  if (!p.ok) return 1;
+  RecPlan p = choose_plan(h, B, true);
+  if (!p.ok) { set_error("persistent tcgen05 backward chain unavailable for this shape (%s)", p.why); return 1; }
+  { int c[8] = {p.NB, p.KS, p.MT, p.ATOMS, p.n_tiles, p.WST, p.HST, p.RST}; for (int i = 0; i < 8; ++i) h->bwd_cfg[i] = c[i]; }
+  h->bwd_groups = p.G;
   RecArgs& a = p.a;
   a.XW = nullptr; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.state = nullptr; a.psum = nullptr; a.Hp_hi = nullptr; a.Hp_lo = nullptr; a.H_user = nullptr;
@@ -1251,7 +1312,7 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = 0.f; a.u0_off = 0.f; a.uk_dmo = 0.f; a.uk_off = 0.f;
   a.ST = h->ST_hi;
-  DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles * p.MT, st));
+  DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
   CUtensorMap tH_hi, tH_lo, tW;
   int rc;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
@@ -1262,16 +1323,17 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
 
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
   const int K = h->K, Rp = h->Rp;
-  RecPlan p = choose_plan(h, B);
+  RecPlan p = choose_plan(h, B, false);
   if (!p.ok) {
-    // Shapes the persistent kernel does not cover yet run on the CUDA-core recurrence (still on the GPU).
-    static bool warned = false;
-    if (!warned) { fprintf(stderr, "[libdrnmf] persistent tcgen05 recurrence unavailable (%s); using the SIMT recurrence\n", p.why); warned = true; }
-    h->last_rec_impl = 1;
-    return launch_recurrent_simt(h, w, B, T, H_user, st);
+    // No silent second backend: a shape the persistent kernel cannot tile is an error.  The CUDA-core recurrence only
+    // runs when it is asked for (DRNMF_IMPL_SIMT handle, or DRNMF_RECURRENT=simt for debugging).
+    set_error("persistent tcgen05 recurrence unavailable for R=%d (padded %d), B=%d: %s; the CUDA-core recurrence must be "
+              "requested explicitly (DRNMF_IMPL_SIMT)", h->R, h->Rp, B, p.why);
+    return DRNMF_ERR_INVALID;
   }
   h->last_rec_impl = 0;
   { int c[8] = {p.NB, p.KS, p.MT, p.ATOMS, p.n_tiles, p.WST, p.HST, p.RST}; for (int i = 0; i < 8; ++i) h->rec_cfg[i] = c[i]; }
+  h->rec_groups = p.G;
   RecArgs& a = p.a;
   a.XW = w.XW; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.state = w.state; a.psum = w.psum; a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;
@@ -1286,7 +1348,7 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   if (want_dbg) DRNMF_CUDA(cudaMemsetAsync(dbg_dev, 0, 16 * 8 * sizeof(long long), st));
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = h->u0_d - h->u0_o; a.u0_off = h->u0_o; a.uk_dmo = h->uk_d - h->uk_o; a.uk_off = h->uk_o;
-  DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles * p.MT, st));
+  DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
   a.ST = h->ST_hi;
   CUtensorMap tH_hi, tH_lo, tW;
   int rc;

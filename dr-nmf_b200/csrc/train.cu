@@ -467,15 +467,19 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   ba.alph = (h->alph_dim > 1) ? h->alph : nullptr;
   const dim3 gstep(Rp / SIMT_BN, (B + SIMT_BM - 1) / SIMT_BM);
   int bwd_rc = 1;
+  h->last_bwd_impl = 1;
   {
     bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
     const char* e = getenv("DRNMF_RECURRENT");
     if (e && !strcmp(e, "simt")) rec_simt = true;
     if (!rec_simt) {
-      bwd_rc = launch_recurrent_bwd_tc(h, w.fwd, B, T, w.dH, w.deltaT_hi, w.deltaT_lo, w.G, w.psum2, st);
+      // K == 1 has no layer-to-layer product at all: the per-frame kernels below are the whole chain
+      bwd_rc = (K < 2) ? 1 : launch_recurrent_bwd_tc(h, w.fwd, B, T, w.dH, w.deltaT_hi, w.deltaT_lo, w.G, w.psum2, st);
+      if (bwd_rc == 1 && K >= 2) return DRNMF_ERR_INVALID;      // no silent CUDA-core fallback (error text set by the planner)
       if (bwd_rc != 0 && bwd_rc != 1) return bwd_rc;
       if (bwd_rc == 0) {
-        const int KSx = h->rec_cfg[1], MTx = h->rec_cfg[2];
+        h->last_bwd_impl = 0;
+        const int KSx = h->bwd_cfg[1], MTx = h->bwd_cfg[2];
         k_bwd_finalize_G<<<B, 128, 0, st>>>(w.G, w.psum2, w.fwd.mvalid, T, Bp, R, Rp, KSx * MTx, (T - 1) & 1, h->u0_o, h->uk_o);
         count_launch();
       }

@@ -189,14 +189,22 @@ class DrnmfEngine:
         _lib.check(self.lib.drnmf_stage_times(self.h, ms))
         return [float(v) for v in ms]
 
-    def recurrent_config(self):
-        """dict describing how the last forward's recurrence ran (impl 'tcgen05' | 'simt' + tiling)."""
-        c = (C.c_int * 9)()
-        _lib.check(self.lib.drnmf_recurrent_config(self.h, c))
-        keys = ("NB", "KS", "MT", "ATOMS", "n_tiles", "WST", "HST", "RST")
+    def recurrent_config(self, backward=False):
+        """dict describing how the recurrence of the last forward (or the backward chain of the last loss_and_grads) ran:
+        impl 'tcgen05' | 'simt' + tiling; n_tiles = batch tiles per group, groups = batch groups on disjoint SMs."""
+        c = (C.c_int * 10)()
+        _lib.check(self.lib.drnmf_recurrent_config2(self.h, 1 if backward else 0, c))
+        keys = ("NB", "KS", "MT", "ATOMS", "n_tiles", "WST", "HST", "RST", "groups")
         d = {"impl": "tcgen05" if c[0] == 0 else "simt"}
         d.update({k: int(c[1 + i]) for i, k in enumerate(keys)})
         return d
+
+    def last_backward_impl(self):
+        return self.recurrent_config(backward=True)["impl"]
+
+    def inject_device_error(self, code):
+        """Test hook (drnmf_debug_inject_error): latch `code` in the device-side error word."""
+        _lib.check(self.lib.drnmf_debug_inject_error(self.h, int(code), _stream()))
 
     def derived(self, which, k=0):
         n = {0: self.Rp * self.Rp, 1: self.Rp * self.Fp, 2: self.Rp, 3: self.Rp}[which]

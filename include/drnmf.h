@@ -88,6 +88,15 @@ DRNMF_API int drnmf_stage_times(drnmf_handle* h, float* ms4);
  * weight / hidden / reduction ring depths of the persistent kernel. */
 DRNMF_API int drnmf_recurrent_config(const drnmf_handle* h, int* cfg9);
 
+/* Extended form: which = 0 the recurrence of the last drnmf_forward, 1 the backward chain of the last
+ * drnmf_loss_and_grads; cfg10[0..8] as above, cfg10[9] = batch groups (independent utterance ranges that run the chain
+ * on disjoint SMs; the grid is KS x MT x groups CTAs).  Replaces nothing in the reference (introspection only). */
+DRNMF_API int drnmf_recurrent_config2(const drnmf_handle* h, int which, int* cfg10);
+
+/* Test hook: writes `code` into the handle's device-side error word, as a kernel watchdog would.  The next compute
+ * call reports DRNMF_ERR_DEVICE once and clears the word (errors do not latch). */
+DRNMF_API int drnmf_debug_inject_error(drnmf_handle* h, int code, void* stream);
+
 /* Debug/inspection: copy a derived tensor to a caller device buffer.  which: 0 = S_k^T (Rp x Rp, k>=1),
  * 1 = W_k^T (Rp x Fp), 2 = b_k (Rp), 3 = h0 (Rp).  Rp/Fp via drnmf_padded_dims. */
 DRNMF_API int drnmf_get_derived(const drnmf_handle* h, int which, int k, float* out, void* stream);
@@ -152,7 +161,8 @@ DRNMF_API size_t drnmf_ista_workspace_bytes(int F, int n, int R);
  * loss_host[1] = sum m; the training loss is loss_host[0]/loss_host[1] and every gradient returned is the gradient of
  * loss_host[0] (divide by the -- possibly all-reduced -- frame count).  Gradient shapes follow drnmf_set_params:
  * g_log_D (n_log_D,F,R), g_log_alph (n_log_alph), g_log_lam1 (n_log_lam1), g_log_h0 (R), g_k_clean/g_k_noise (R/2,F);
- * tied parameters receive the sum over layers.  irm (B,T,F) optional output.  Scalar alph per layer only. */
+ * tied parameters receive the sum over layers.  irm (B,T,F) optional output.  log_alph may be one scalar per layer or one value per atom
+ * (alph_dim = R, 'untie_alph'); g_log_alph then has n_log_alph * alph_dim entries. */
 DRNMF_API int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value,
                          float* g_log_D, float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean,
                          float* g_k_noise, double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream);

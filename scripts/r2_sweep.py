@@ -1,0 +1,83 @@
+"""Round-2 operating-point sweep of the persistent recurrence: batch tile NB x batch groups G x publish mode, at the
+bench batch (B=64), the training batch (B=32) and throughput batches.  The plan is chosen per launch from the
+DRNMF_REC_* environment variables, so one process can walk the whole table.  Every configuration is compared with the
+first one of its batch size (fixed reduction order -> bitwise equality expected)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from drnmf_b200 import engine, synth
+
+F, R, K = 513, int(os.environ.get("SWEEP_R", "1000")), 25
+T = int(os.environ.get("SWEEP_T", "193"))
+p = synth.model_params(F, R, K)
+p["log_U1"], p["log_Uk"] = synth.structured_u_init()
+eng = engine.DrnmfEngine(F, R, K)
+eng.set_params(p)
+fl_rec = 2.0 * R * R * (K - 1)
+
+
+def setenv(**kw):
+    for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS"):
+        os.environ.pop(k, None)
+    for k, v in kw.items():
+        if v is not None:
+            os.environ["DRNMF_REC_" + k] = str(v)
+
+
+def run(B, Tn, reps=3, **kw):
+    g = torch.Generator(device="cuda").manual_seed(B)
+    x = torch.rand(B, Tn, F, device="cuda", generator=g) * 4
+    setenv(**kw)
+    best = None
+    H = None
+    try:
+        for _ in range(reps):
+            H, _ = eng.forward(x, want_irm=False)
+            torch.cuda.synchronize()
+            ms = eng.stage_times()[2]
+            best = ms if best is None else min(best, ms)
+    except Exception as e:
+        print("B=%d %s FAILED: %s" % (B, kw, e), flush=True)
+        return None
+    cfg = eng.recurrent_config()
+    steps = Tn * (K - 1)
+    tf = fl_rec * B * Tn / (best / 1e3) / 1e12
+    print("B=%4d T=%3d req=%-32s plan=NB%d G%d tiles%d W%d H%d R%d | rec %8.3f ms  %6.2f us/step  %7.1f kframes/s  %6.1f TF/s useful" % (
+        B, Tn, kw, cfg["NB"], cfg["groups"], cfg["n_tiles"], cfg["WST"], cfg["HST"], cfg["RST"], best, 1e3 * best / steps,
+        B * Tn / best, tf), flush=True)
+    return H
+
+
+def sweep(B, Tn, configs):
+    ref = None
+    for kw in configs:
+        H = run(B, Tn, **kw)
+        if H is None:
+            continue
+        if ref is None:
+            ref = H.clone()
+        else:
+            same = torch.equal(H, ref)
+            err = float((H - ref).abs().max() / ref.abs().max())
+            print("      vs first config: bitwise %s, max rel %.2e" % (same, err), flush=True)
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "b64"):
+    sweep(64, T, [dict(NB=64, G=1), dict(NB=32, G=2), dict(NB=32, G=1), dict(NB=32, G=1, PUB="direct"),
+                  dict(NB=16, G=2), dict(NB=16, G=2, PUB="direct"), dict(NB=16, G=1), dict(NB=16, G=1, PUB="direct"), dict()])
+if which in ("all", "b32"):
+    sweep(32, T, [dict(NB=32, G=1), dict(NB=16, G=2), dict(NB=16, G=1), dict(NB=16, G=1, PUB="direct"), dict()])
+if which in ("all", "thr"):
+    sweep(512, 48, [dict(NB=64, G=1), dict(NB=64, G=2), dict(NB=64, G=2, PUB="direct"), dict(NB=32, G=2), dict()])
+    sweep(2048, 12, [dict(NB=64, G=1), dict(NB=64, G=2)])
+    sweep(128, 96, [dict(NB=64, G=1), dict(NB=64, G=2), dict(NB=32, G=2), dict(NB=32, G=2, PUB="direct")])
+if which in ("all", "dbg"):
+    print("---- per-role cycle counters (stderr) ----", flush=True)
+    for kw in (dict(NB=64, G=1), dict(NB=32, G=2), dict(NB=32, G=1), dict(NB=16, G=2)):
+        sys.stderr.write("\n## B=64 %s\n" % kw); sys.stderr.flush()
+        run(64, 40, reps=1, DEBUG=1, **kw)
+    for kw in (dict(NB=64, G=1), dict(NB=64, G=2)):
+        sys.stderr.write("\n## B=512 %s\n" % kw); sys.stderr.flush()
+        run(512, 12, reps=1, DEBUG=1, **kw)
+setenv()
