@@ -1268,6 +1268,7 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
     if (!probe.ok) { p.why = probe.why; continue; }
     int mc = 0;
     rec_max_clusters(probe, bwd, &mc);
+    if (getenv("DRNMF_REC_VERBOSE")) fprintf(stderr, "[libdrnmf] plan probe KS=%d MT=%d smem=%zu: %d co-resident clusters\n", KS, probe.MT, probe.smem, mc);
     if (mc < probe.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
     const int g_max = env_g ? atoi(env_g) : mc / probe.MT;
     for (int NB = 64; NB >= 16 && !p.ok; NB >>= 1) {
@@ -1281,6 +1282,7 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
         if (c.G != G && G != g_max) continue;       // this group count was already tried
         int mc2 = 0;
         rec_max_clusters(c, bwd, &mc2);
+        if (getenv("DRNMF_REC_VERBOSE")) fprintf(stderr, "[libdrnmf]   candidate KS=%d NB=%d G=%d tiles/group=%d smem=%zu: %d co-resident clusters (need %d)\n", KS, NB, c.G, c.n_tiles, c.smem, mc2, c.MT * c.G);
         if (mc2 < c.MT * c.G) { p.why = "not enough co-resident clusters for any tiling"; continue; }
         p = c;
       }

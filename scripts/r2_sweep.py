@@ -17,7 +17,7 @@ fl_rec = 2.0 * R * R * (K - 1)
 
 
 def setenv(**kw):
-    for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS"):
+    for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS", "DRNMF_REC_VERBOSE"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         if v is not None:
@@ -72,6 +72,10 @@ if which in ("all", "thr"):
     sweep(512, 48, [dict(NB=64, G=1), dict(NB=64, G=2), dict(NB=64, G=2, PUB="direct"), dict(NB=32, G=2), dict()])
     sweep(2048, 12, [dict(NB=64, G=1), dict(NB=64, G=2)])
     sweep(128, 96, [dict(NB=64, G=1), dict(NB=64, G=2), dict(NB=32, G=2), dict(NB=32, G=2, PUB="direct")])
+if which in ("ks4",):
+    sweep(64, T, [dict(NB=64, G=1, VERBOSE=1), dict(KS=4, NB=64, G=1, VERBOSE=1), dict(KS=4, NB=32, G=2), dict(KS=4, NB=16, G=4),
+                  dict(KS=4, NB=16, G=2), dict(KS=16, NB=64, G=1, VERBOSE=1), dict(KS=2, NB=16, G=4, VERBOSE=1)])
+    sweep(512, 24, [dict(NB=64, G=1), dict(KS=4, NB=64, G=4), dict(KS=4, NB=64, G=2), dict(KS=4, NB=32, G=4)])
 if which in ("all", "dbg"):
     print("---- per-role cycle counters (stderr) ----", flush=True)
     for kw in (dict(NB=64, G=1), dict(NB=32, G=2), dict(NB=32, G=1), dict(NB=16, G=2)):
