@@ -78,18 +78,9 @@ int drnmf_version(void) { return 100; }
 const char* drnmf_last_error(void) { return drnmf::last_error(); }
 unsigned long long drnmf_launch_count(void) { return drnmf::launch_count(); }
 
-// R is padded with zero atoms (exact: a zero atom never activates, prep.cu) to the next multiple of 128 for which the
-// persistent recurrence has a tiling: K-splits of at most 128 atoms, or of 256/384/512 streamed through TMEM in
-// 128-column chunks (plan_recurrent, recurrent_tc.cu).  Beyond 2048 atoms nothing fits and the pad stays minimal.
-static int padded_atoms(int R, int num_sms) {
-  const int m0 = (R + 127) / 128;
-  for (int m = m0; m <= 16; ++m)
-    for (int KS = 16; KS >= 1; KS >>= 1) {
-      const int ksl = 128 * m / KS;
-      if ((128 * m) % (32 * KS) == 0 && KS * m <= num_sms && (ksl <= 128 || (ksl <= 512 && ksl % 128 == 0))) return 128 * m;
-    }
-  return 128 * m0;
-}
+// R is padded with zero atoms (exact: a zero atom never activates, prep.cu) to the next multiple of 128: the persistent
+// recurrence tiles the atoms into 128-row M-tiles and K-slices of Rp/KS atoms (multiples of 32 for every cluster size).
+static int padded_atoms(int R, int /*num_sms*/) { return 128 * ((R + 127) / 128); }
 
 int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags) {
   DRNMF_CHECK(out != nullptr, "drnmf_create: out is NULL");

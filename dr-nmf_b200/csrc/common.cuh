@@ -35,6 +35,9 @@ static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * 
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
                  uint32_t box_cols, uint32_t box_rows);
 
+int make_tmap_slabs(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
+                    uint32_t box_rows, uint32_t box_slabs);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // small device utilities
@@ -121,15 +124,17 @@ __device__ __forceinline__ bool mbar_try_wait_cluster_park(uint64_t* bar, uint32
   return ok != 0;
 }
 // Bounded wait: returns false if the watchdog expires (caller records an error and bails out) so that a
-// protocol bug can never hang the GPU.  `budget` is in try_wait rounds (each is a HW-suspended wait).
+// protocol bug can never hang the GPU.  The abort flag lives in global memory (a system-scope load costs ~700 cycles):
+// it is only looked at after a parked wait has timed out, never on the way into the wait - a waiter that is woken 200
+// cycles after its first probe must not sit behind that load (it did: every hop of the recurrence paid for it).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag = nullptr,
                                           long long budget_cycles = 4000000000LL) {
   if (mbar_try_wait(bar, parity)) return true;
-  if (abort_flag && *abort_flag) return false;
+  if (mbar_try_wait_park(bar, parity)) return true;
   long long t0 = clock64();
   uint32_t it = 0;
   while (!mbar_try_wait_park(bar, parity)) {
-    if ((++it & 0x3FF) == 0) {
+    if ((++it & 0x3) == 0) {
       if (clock64() - t0 > budget_cycles) return false;
       if (abort_flag && *abort_flag) return false;
     }
@@ -139,11 +144,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
 __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity, volatile int* abort_flag = nullptr,
                                                   long long budget_cycles = 4000000000LL) {
   if (mbar_try_wait_cluster(bar, parity)) return true;
-  if (abort_flag && *abort_flag) return false;
+  if (mbar_try_wait_cluster_park(bar, parity)) return true;
   long long t0 = clock64();
   uint32_t it = 0;
   while (!mbar_try_wait_cluster_park(bar, parity)) {
-    if ((++it & 0x3FF) == 0) {
+    if ((++it & 0x3) == 0) {
       if (clock64() - t0 > budget_cycles) return false;
       if (abort_flag && *abort_flag) return false;
     }
@@ -161,6 +166,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,

@@ -2,32 +2,38 @@
 //
 // Problem shape: per utterance the chain is T x K_layers strictly serial steps (layer 0 of frame t+1 starts from the
 // last layer of frame t); per step the work is  g^k = relu(g^{k-1} . S_k + x~W_k + b_k + leak),  a (B x R).(R x R)
-// product with a SKINNY batch dimension.  S_k (4 MB at R=1000) must be re-streamed every step, so every SM has to pull
-// its share of the weights each step: the step is tiled as
-//       M-tile m (128 output atoms)  x  K-split s (a slice of <=128 input atoms),   grid = (KS, MT), cluster = the KS
-// K-splits of one M-tile.
-//   * weights: the CTA's 128 x KSLICE block of S_k^T - I goes to registers, is split into tf32 hi + remainder lo and
-//     written into TENSOR MEMORY (tcgen05.st).  The MMA takes its A operand from TMEM, which removes the per-instruction
-//     shared-memory read of A (with both operands in smem a skinny-N product is bound by the smem port) and frees smem.
-//     Latency mode (one batch tile): a producer thread TMA-prefetches the NEXT step's block into a 4 x 16 KB smem ring
-//     while the current step runs; for a symmetric S_k the CTAs below the diagonal fetch the mirrored block and read
-//     it transposed (only 54 of 96 MB of weights are touched per frame -> they stay in L2).  Throughput mode: straight
-//     from L2, two chunks in flight, loaded once per step and reused by every batch tile.
-//   * hidden state: B operand, Kslice x NB tile (hi and lo) TMA-loaded with 128B swizzle from a ping-pong global buffer.
+// product with a SKINNY batch dimension.  S_k (4 MB at R=1000) must be re-streamed every step, so many SMs have to
+// pull a share of the weights each step: the step is tiled as
+//       M-tile m (128 output atoms)  x  K-split s (a slice of Rp/KS input atoms)  x  batch group g,
+//       grid = (KS, MT, G), cluster = the KS K-splits of one M-tile.
+// What bounds a step (measured, profiles/r2_*): the split-K exchange inside the cluster moves a 128 x NB fp32 partial
+// tile per CTA through distributed shared memory at ~13 B/clk (700 + 40 NB cycles), the hop to the consumers through
+// L2 costs ~2.5k cycles, while the 3xTF32 product of a 128-atom slice takes 26 NB cycles.  Hence
+//   * K-splits of 4 (cluster of 4 CTAs, 33 clusters are co-resident on a B200; only 15 clusters of 8): a CTA multiplies
+//     a 128 x (Rp/4) block, i.e. twice the tensor work per exchanged byte of the round-1 tiling (KS = 8);
+//   * batch groups: utterances are independent, so the batch is cut into G = (co-resident clusters) / MT groups that
+//     run the whole chain on disjoint SMs with their own flags (R = 1000: 4 groups x 32 CTAs = 128 SMs).  At B = 64
+//     a group steps 16 utterances: a quarter of the exchange bytes per step; at B >= 512 every group pipelines
+//     64-column batch tiles through the same weights.
+//   * weights: the CTA's block of S_k^T - I streams through a shared-memory ring (TMA, 16 KB pieces of 32 K-columns),
+//     is split into tf32 hi + remainder lo by the loader warps and lands in TENSOR MEMORY in 64-column sub-chunks
+//     (3 buffers of hi|lo = 384 TMEM columns).  The MMA takes A from TMEM (no per-instruction smem read of A).  With
+//     more sub-chunks than buffers (K-slice >= 256) consecutive batch tiles walk the K-slice in alternating direction,
+//     so the sub-chunks resident at the turn are reused and only the rest is re-streamed (slot = sub-chunk mod 3);
+//     the schedule (sub-chunk, slot, first use, last use per position) is built on the host and passed as a table.
+//   * hidden state: B operand, 64-atom x NB sub-chunk tiles (hi and lo) TMA-loaded with 128B swizzle from a
+//     ping-pong global buffer into a ring of stages; consumers acquire the producers' flags lazily per M-tile.
 //   * product: tcgen05.mma kind::tf32, 3xTF32 compensation (W_lo.h_hi + W_hi.h_lo + W_hi.h_hi), fp32 accumulators in
-//     TMEM, issued as back-to-back bursts from constant-offset descriptors (34 cycles per MMA = the pipe's rate).
+//     TMEM, bursts of 24 back-to-back MMAs per sub-chunk from constant-offset descriptors.
 //   * split-K reduction INSIDE the cluster over distributed shared memory (staging + cp.async.bulk + mbarrier
 //     complete_tx): CTA o owns rows [o*RO, (o+1)*RO) of the M-tile, sums the KS partials in a fixed order
 //     (deterministic), applies the fused epilogue (identity part, input projection, bias, rank-1 leak, relu, Keras mask
 //     carry) and writes hi/lo of the new hidden rows; the owner warps release their stores with red.release.gpu
-//     (latency mode) or hand them to a publisher thread that batches the gpu-scope fences (throughput mode);
-//     consumers acquire the flag and TMA their slice.
-//   * utterances are cut into independent batch tiles of NB columns that are software-pipelined through the same
-//     TMEM-resident weights (hides the exchange latency when B is large, reuses every weight n_tiles times).
+//     (one tile per group) or hand them to a publisher thread that batches the gpu-scope fences (several tiles).
 //
 // Warp roles (512 threads): 0 weight producer (TMA ring) | 1 hidden-state TMA (+flag acquire) | 2 MMA issuer / TMEM
 //     owner | 3 publisher | 4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue) | 12-15 weight loaders
-//     (smem ring or L2 -> regs -> TMEM).
+//     (smem ring -> regs -> TMEM).
 #include "internal.h"
 
 #include <cstdio>
@@ -38,8 +44,18 @@ namespace drnmf {
 
 constexpr int RT_THREADS = 512;
 constexpr int RT_AST = 2;                    // TMEM accumulator stages
+constexpr int RT_WB = 3;                     // TMEM weight buffers: 64 K-columns hi | 64 lo = 128 TMEM columns each
 constexpr int RT_PST = 4;                    // owner -> publisher hand-off slots
+constexpr int RT_MAXSC = 16;                 // sub-chunks (64 K-columns) per K-slice: K-slices of up to 1024 atoms
+constexpr int RT_MAXH = 8;                   // hidden-state ring depth
+constexpr int RT_MAXW = 16;                  // weight ring depth (16 KB pieces)
 constexpr long long RT_WATCHDOG = 3000000000LL;
+
+// Per-step schedule of a CTA: which 64-column sub-chunk of the K-slice each (batch tile, position) multiplies, in
+// which TMEM weight buffer it lives, whether that buffer is filled for this use (first use) and whether it may be
+// overwritten afterwards (last use).  Tile classes: 0 first tile, 1 odd tile, 2 even tile > 0; +3 when the tile is the
+// last of the step.  Entry bits: [3:0] sub-chunk, [5:4] buffer, 6 first use, 7 last use.
+struct RecSched { uint8_t e[6][RT_MAXSC]; };
 
 struct RecArgs {
   // tensors
@@ -54,15 +70,17 @@ struct RecArgs {
   int* dev_error;
   int dbg_m;                                 // M-tile of the observed CTA (K-split 0)
   long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
+  long long* trace;                          // optional event trace of CTA (0,0): [0] = count, then (tag, clock) pairs
+  int trace_lo, trace_hi;                    // items [lo, hi) of the observed CTA are traced
+  int h3d;                                   // hidden-state tensor maps are 3-D slab maps (two 32-atom tiles per TMA instruction)
   // shapes
   int B, Bp, T, K, R, Rp;
-  int MT, KS, RO, ATOMS, KSLICE, n_tiles;      // n_tiles = batch tiles per batch group (grid.z groups run on disjoint SMs)
+  int MT, KS, RO, KSLICE, n_tiles;           // n_tiles = batch tiles per batch group (grid.z groups run on disjoint SMs)
   int n_tiles_total;                         // batch tiles of the whole batch
-  int sym;                                   // S_k symmetric and square blocks: CTAs below the diagonal read the mirrored block
+  int NSC;                                   // 64-column sub-chunks per K-slice (the last one may be 32 wide)
+  int rot;                                   // NSC <= RT_WB: the buffers rotate by NSC per step (next step's weights prefetch)
   int pub_unit;                              // flag increments per (CTA, item): 1 = publisher thread, 4 = each owner warp releases its own stores
-  int KCH, NCH;                              // weight chunk held in TMEM at a time (<= 128 K-columns), chunks per K-slice
-  int WST, HST, RST;                         // WST unused (weights live in TMEM); hidden-tile / reduction-slot ring depths
-  const float* ST;                           // (K-1) x Rp x Rp  S_k^T
+  int WST, HST, RST;                         // weight-piece / hidden-sub-chunk / reduction-slot ring depths
   float u0_dmo, u0_off, uk_dmo, uk_off;
   // smem offsets (bytes from the 1024-aligned base)
   int off_w, off_h, off_red, off_push, off_leak, off_out, off_bar;
@@ -70,10 +88,10 @@ struct RecArgs {
 };
 
 struct RecBars {   // all mbarriers, laid out at off_bar
-  uint64_t h_full[4][16], h_empty[4], t_full[RT_AST], t_empty[RT_AST], red_full[4], red_free[4];
+  uint64_t h_full[RT_MAXH], h_empty[RT_MAXH], t_full[RT_AST], t_empty[RT_AST], red_full[4], red_free[4];
   uint64_t pub_full[RT_PST], pub_empty[RT_PST];
-  uint64_t wt_full, wt_empty;                // weights of the current step are in TMEM / may be overwritten
-  uint64_t w_full[8], w_free[8];             // 16 KB weight chunks (32 K-columns x 128 rows) staged in smem by TMA
+  uint64_t wb_full[RT_WB], wb_empty[RT_WB];  // TMEM weight buffer holds its sub-chunk / may be overwritten
+  uint64_t w_full[RT_MAXW], w_free[RT_MAXW]; // 16 KB weight pieces (32 K-columns x 128 rows) staged in smem by TMA
   uint32_t tmem_slot;
   int abort;
   long long dbg_ts[2];                       // debug: clock of the first satisfied h_full / of the last MMA issue of an item
@@ -108,10 +126,35 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int ta
     else { stmt; }                                             \
   } while (0)
 
+// event trace (debug): every tracing thread appends (tag, clock) pairs to its role's region of a.trace with a private
+// counter (plain stores, no atomics: the probe must not move what it measures).  tag = event << 16 | item (low 16 bits)
+constexpr int RT_TRC_PER_ROLE = 256;
+#define RT_TRACE(role, ev, item)                                                                    \
+  do {                                                                                              \
+    if (dbg_on && a.trace && (long long)(item) >= a.trace_lo && (long long)(item) < a.trace_hi && trc < RT_TRC_PER_ROLE) { \
+      long long* _p = a.trace + 8 + ((role) * RT_TRC_PER_ROLE + trc) * 2;                           \
+      _p[0] = ((long long)(ev) << 16) | (long long)((item) & 0xFFFF); _p[1] = clock64(); ++trc;     \
+      a.trace[role] = trc;                                                                          \
+    }                                                                                               \
+  } while (0)
+
+// ring position without runtime division (a 64-bit % and / per use cost ~100 cycles each on the critical path)
+struct RtRing {
+  int idx; uint32_t ph;
+  __device__ __forceinline__ RtRing() : idx(0), ph(0) {}
+  __device__ __forceinline__ void next(int depth) { if (++idx == depth) { idx = 0; ph ^= 1u; } }
+};
+
+// schedule entry of (tile i of n, position p)
+__device__ __forceinline__ uint32_t sched_at(const RecSched& sc, int i, int n, int p) {
+  const int cls = (i == 0 ? 0 : ((i & 1) ? 1 : 2)) + (i == n - 1 ? 3 : 0);
+  return sc.e[cls][p];
+}
+
 template <int NB, bool BWD, int CB>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
-               const __grid_constant__ CUtensorMap tmW, const RecArgs a_in) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ RecSched sch, const RecArgs a_in) {
   // Batch groups: utterances are independent, so grid.z groups of (KS x MT) CTAs each run the whole chain on their own
   // contiguous range of batch tiles (disjoint SMs, own flags, no interaction).  Everything indexed by the utterance is
   // re-based once here; below, tile i / utterance b are group-local.
@@ -148,19 +191,20 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
   }
   const bool dbg_on = (a.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == a.dbg_m && blockIdx.z == 0;
   long long dbg_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  int trc = 0;
   const long long dbg_t0 = clock64();
   const int s = blockIdx.x;            // K-split == rank in cluster
   const int m = blockIdx.y;            // M-tile
-  const int K = a.K, T = a.T, Rp = a.Rp, n_tiles = a.n_tiles, ATOMS = a.ATOMS;
-  constexpr uint32_t TMEM_COLS = 512;    // [0,KSLICE) W hi | [KSLICE,2 KSLICE) W lo | [256, 256 + AST*NB) accumulators
-  constexpr uint32_t ACC_COL0 = 256;
-  const uint32_t H_ATOM_BYTES = NB * 128;
+  const int K = a.K, T = a.T, Rp = a.Rp, n_tiles = a.n_tiles, NSC = a.NSC;
+  constexpr uint32_t TMEM_COLS = 512;    // [128 b, 128 b + 64) W hi | [+64, +128) W lo of buffer b | [384, 384 + AST*NB) accumulators
+  constexpr uint32_t ACC_COL0 = RT_WB * 128;
+  constexpr uint32_t HB = NB * 128;      // one 32-atom x NB tile (hi or lo) of the hidden state
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo); tma_prefetch_desc(&tmW);
-    mbar_init(&bars->wt_full, 128); mbar_init(&bars->wt_empty, 1);
-    for (int i = 0; i < 8; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], 4); }
-    for (int i = 0; i < 4; ++i) { for (int a2 = 0; a2 < 16; ++a2) mbar_init(&bars->h_full[i][a2], 1); mbar_init(&bars->h_empty[i], 1); }
+    for (int i = 0; i < RT_WB; ++i) { mbar_init(&bars->wb_full[i], 128); mbar_init(&bars->wb_empty[i], 1); }
+    for (int i = 0; i < RT_MAXW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], 4); }
+    for (int i = 0; i < RT_MAXH; ++i) { mbar_init(&bars->h_full[i], 1); mbar_init(&bars->h_empty[i], 1); }
     for (int i = 0; i < RT_AST; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
     for (int i = 0; i < 4; ++i) { mbar_init(&bars->red_full[i], 1); mbar_init(&bars->red_free[i], 4 * a.KS); }
     for (int i = 0; i < RT_PST; ++i) { mbar_init(&bars->pub_full[i], 4); mbar_init(&bars->pub_empty[i], 1); }
@@ -170,180 +214,175 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
   if (warp == 2) tmem_alloc<TMEM_COLS>(&bars->tmem_slot);
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();                  // every CTA's barriers exist before any remote arrive / st.async
+  cluster_sync_all();                  // every CTA's barriers exist before any remote arrive / bulk copy
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
   const int n_mma_steps = T * (K - 1);
 
   if (warp == 0) {
-    // ================= weight producer: TMA S_k^T[m*128 .. +128][32 K-columns] chunks into the smem ring ===============
-    // The weights do not depend on the recurrence, so the ring runs up to WST chunks (a whole step when one batch
-    // tile is in flight) ahead of the loaders that move them into TMEM.
-    if (lane == 0 && a.WST > 0) {
+    // ================= weight producer: TMA S_k^T[m*128 .. +128][32 K-columns] pieces into the smem ring ===============
+    // The weights do not depend on the recurrence, so the ring runs ahead of the loaders that move them into TMEM
+    // (a whole step ahead when one batch tile is in flight and the K-slice fits the ring).
+    if (lane == 0) {
       const uint64_t pol_w = l2_policy_evict_last();
-      const int nchunk = a.KCH / 32;
-      long long wc = 0;
+      RtRing wr;
       bool okw = true;
       for (int ms = 0; ms < n_mma_steps && okw; ++ms) {
         const int k = BWD ? (K - 1 - ms % (K - 1)) : (ms % (K - 1) + 1);
-        const int reps = (a.NCH > 1) ? n_tiles : 1;
-        for (int rep = 0; rep < reps && okw; ++rep)
-          for (int ch2 = 0; ch2 < a.NCH && okw; ++ch2)
-            for (int ch = 0; ch < nchunk; ++ch, ++wc) {
-              const int ws = (int)(wc % a.WST);
-              RT_TIMED(0, okw = mbar_wait(&bars->w_free[ws], (uint32_t)(((wc / a.WST) & 1) ^ 1), err, RT_WATCHDOG));
+        for (int i = 0; i < n_tiles && okw; ++i)
+          for (int p = 0; p < NSC && okw; ++p) {
+            const uint32_t e = sched_at(sch, i, n_tiles, p);
+            if (!(e & 64u)) continue;                                   // resident: nothing to load
+            const int col0 = s * a.KSLICE + (int)(e & 15u) * 64;
+            const int npc = (a.KSLICE - (int)(e & 15u) * 64 >= 64) ? 2 : 1;
+            for (int pc = 0; pc < npc; ++pc, wr.next(a.WST)) {
+              const int ws = wr.idx;
+              RT_TIMED(0, okw = mbar_wait(&bars->w_free[ws], wr.ph ^ 1u, err, RT_WATCHDOG));
               if (!okw) { atomicCAS(a.dev_error, 0, 214); break; }
               mbar_expect_tx(&bars->w_full[ws], 16384u);
-              // block (m, s) of S_k^T - or, below the diagonal of a symmetric S_k, the mirrored block (s, m), cut
-              // into 32-row slabs of the M-tile: only 36 of the 64 blocks of a layer are ever fetched (54 of 96 MB at
-              // R = 1000, K = 25), which is what fits in L2 across a frame
-              const bool tr = a.sym && s < m;
-              const int c0 = tr ? m * 128 + ch * 32 : s * a.KSLICE + ch2 * a.KCH + ch * 32;
-              const int c1 = (k - 1) * Rp + (tr ? s * 128 : m * 128);
-              tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW, &bars->w_full[ws], c0, c1, pol_w);
+              tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW, &bars->w_full[ws], col0 + pc * 32, (k - 1) * Rp + m * 128, pol_w);
             }
+          }
       }
     }
   } else if (warp == 1) {
-    // ================= hidden-state loader: acquire the producers' flag, then TMA the K-slice of tile i =================
-    if (lane == 0) {
-      const int m_lo = (s * a.KSLICE) / 128, m_hi = ((s + 1) * a.KSLICE - 1) / 128;
-      int it = 0;
-      for (int t = 0; t < T; ++t)
-        for (int k = 1; k < K; ++k) {
+    // ================= hidden-state loader: acquire the producers' flags, then TMA the sub-chunks of tile i ============
+    // Flags are acquired lazily, right before the first sub-chunk that needs a producer M-tile (the M-tiles of a step
+    // finish up to ~2k cycles apart): the lanes poll the (at most two) M-tiles a sub-chunk overlaps in parallel - a
+    // satisfied poll still costs an L2 round trip -, then lane 0 issues one slab TMA per hi / lo.
+    {
+      const int m_lo = (s * a.KSLICE) >> 7;
+      RtRing hr;
+      long long item = 0;
+      bool okh = true;
+      for (int t = 0; t < T && okh; ++t)
+        for (int k = 1; k < K && okh; ++k) {
           const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(t * K + k);   // step (t,k-1) published
           const int slot = (k - 1) & 1;
-          for (int i = 0; i < n_tiles; ++i, ++it) {
-            const int hs = it % a.HST;
-            bool okh;
-            RT_TIMED(0, okh = mbar_wait(&bars->h_empty[hs], ((it / a.HST) & 1) ^ 1, err, RT_WATCHDOG));
-            if (!okh) { atomicCAS(a.dev_error, 0, 202); goto h_done; }
-            for (int mm = m_lo; mm <= m_hi; ++mm) {
-              RT_TIMED(1, okh = poll_flag(a.flags + i * a.MT + mm, target, err));
-              if (!okh) { atomicCAS(a.dev_error, 0, 203); goto h_done; }
-            }
-            RT_TIMED(2, fence_proxy_async_global());   // generic-proxy writes of the owners -> async-proxy (TMA) reads   // generic-proxy writes of the owners -> async-proxy (TMA) reads
-            uint8_t* dst = smem + a.off_h + hs * a.h_stage_bytes;
-            for (int at = 0; at < ATOMS; ++at) {   // one barrier per 32-atom slab: the MMA starts on the first to land
-              const int c0 = s * a.KSLICE + at * 32, c1 = slot * a.Bp + boff + i * NB;   // the tensor map covers all groups
-              mbar_expect_tx(&bars->h_full[hs][at], 2 * H_ATOM_BYTES);
-              tma_load_2d(dst + (2 * at) * H_ATOM_BYTES, &tmH_hi, &bars->h_full[hs][at], c0, c1);
-              tma_load_2d(dst + (2 * at + 1) * H_ATOM_BYTES, &tmH_lo, &bars->h_full[hs][at], c0, c1);
-            }
-            if (dbg_on) {   // acc3..6: delivery time of slabs 0..3 after the TMA issue (a second, passive waiter)
-              const long long _t0 = clock64();
-              for (int at = 0; at < ATOMS && at < 4; ++at) {
-                mbar_wait(&bars->h_full[hs][at], (it / a.HST) & 1, err, RT_WATCHDOG);
-                dbg_acc[3 + at] += clock64() - _t0;
+          for (int i = 0; i < n_tiles && okh; ++i, ++item) {
+            unsigned int polled = 0;                 // producer M-tiles of this K-slice acquired for this item (warp-uniform)
+            for (int p = 0; p < NSC && okh; ++p, hr.next(a.HST)) {
+              const int sc = (int)(sched_at(sch, i, n_tiles, p) & 15u);
+              const int c0 = s * a.KSLICE + sc * 64;
+              const int wdt = (a.KSLICE - sc * 64 >= 64) ? 64 : 32;
+              const int mt_a = c0 >> 7, mt_b = (c0 + wdt - 1) >> 7;
+              const unsigned int need = (1u << (mt_a - m_lo)) | (1u << (mt_b - m_lo));
+              if (need & ~polled) {
+                bool mine_ok = true;
+                const long long _t0 = dbg_on ? clock64() : 0;
+                if (lane < 2) {
+                  const int mt = lane == 0 ? mt_a : mt_b;
+                  if (!((polled >> (mt - m_lo)) & 1u) && (lane == 0 || mt_b != mt_a))
+                    mine_ok = poll_flag(a.flags + i * a.MT + mt, target, err);
+                }
+                okh = __all_sync(0xffffffffu, mine_ok);
+                if (dbg_on) dbg_acc[1] += clock64() - _t0;
+                if (!okh) { if (lane == 0) atomicCAS(a.dev_error, 0, 203); break; }
+                polled |= need;
+                if (lane == 0) fence_proxy_async_global();          // generic-proxy writes of the owners -> async-proxy (TMA) reads
+                if (lane == 0) RT_TRACE(1, 1 + p, item);
               }
+              if (lane == 0) {
+                const int hs = hr.idx;
+                RT_TIMED(0, okh = mbar_wait(&bars->h_empty[hs], hr.ph ^ 1u, err, RT_WATCHDOG));
+                if (!okh) atomicCAS(a.dev_error, 0, 202);
+                else {
+                  uint8_t* dst = smem + a.off_h + hs * a.h_stage_bytes;
+                  const int slab = c0 >> 5;
+                  const int c1 = slot * a.Bp + boff + i * NB;          // the tensor map covers all groups
+                  // stage = [hi slab 0 | hi slab 1 | lo slab 0 | lo slab 1]; a 32-wide last sub-chunk still moves two
+                  // slabs (the second one is not multiplied; beyond the matrix it is zero-filled)
+                  if (a.h3d) {
+                    mbar_expect_tx(&bars->h_full[hs], 4u * HB);
+                    tma_load_3d(dst, &tmH_hi, &bars->h_full[hs], 0, c1, slab);
+                    tma_load_3d(dst + 2 * HB, &tmH_lo, &bars->h_full[hs], 0, c1, slab);
+                  } else {                              // 2-D maps: one 32-atom tile per instruction
+                    const int nat = wdt >> 5;
+                    mbar_expect_tx(&bars->h_full[hs], (uint32_t)(2 * nat) * HB);
+                    for (int at = 0; at < nat; ++at) {
+                      tma_load_2d(dst + at * HB, &tmH_hi, &bars->h_full[hs], (slab + at) * 32, c1);
+                      tma_load_2d(dst + (2 + at) * HB, &tmH_lo, &bars->h_full[hs], (slab + at) * 32, c1);
+                    }
+                  }
+                  RT_TRACE(1, 10 + p, item);
+                }
+              }
+              okh = __all_sync(0xffffffffu, okh);
             }
           }
         }
     }
-  h_done:;
   } else if (warp == 2) {
     // ================= MMA issuer =================
     // The whole warp runs the loop convergently (descriptor arithmetic stays in the uniform datapath); one elected
     // lane issues the tcgen05 instructions.
     {
       const uint32_t idesc = umma_idesc_tf32(128, NB);
-      int it = 0, wload = 0;
+      long long it = 0;
+      RtRing hr, ar;
+      uint32_t f0 = 0, f1 = 0, f2 = 0;               // fills of the three TMEM weight buffers seen so far
+      int rot = 0;
       bool okm = true;
+      const bool leader = elect_one();
       for (int ms = 0; ms < n_mma_steps && okm; ++ms) {
-        for (int i = 0; i < n_tiles; ++i, ++it) {
-          const int as = it % RT_AST, hs = it % a.HST;
-          RT_TIMED(0, okm = mbar_wait(&bars->t_empty[as], ((it / RT_AST) & 1) ^ 1, err, RT_WATCHDOG));
+        for (int i = 0; i < n_tiles && okm; ++i, ++it, ar.next(RT_AST)) {
+          const int as = ar.idx;
+          RT_TIMED(0, okm = mbar_wait(&bars->t_empty[as], ar.ph ^ 1u, err, RT_WATCHDOG));
           if (!okm) { atomicCAS(a.dev_error, 0, 204); break; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + ACC_COL0 + as * NB;
-          const uint32_t hbase = smem_u32(smem + a.off_h + hs * a.h_stage_bytes);
-          const bool leader = elect_one();
-          const int nks = a.KCH / 8;
-          for (int ch2 = 0; ch2 < a.NCH && okm; ++ch2) {
-            // weights: one chunk of <= 128 K-columns (hi | lo) lives in TMEM at a time.  A single-chunk slice is loaded
-            // once per step and reused by every batch tile; a two-chunk slice (R > 1024) is re-streamed per tile.
-            if (a.NCH > 1 || i == 0) {
-              RT_TIMED(2, okm = mbar_wait(&bars->wt_full, (uint32_t)(wload & 1), err, RT_WATCHDOG));
+          for (int p = 0; p < NSC; ++p, hr.next(a.HST)) {
+            const uint32_t e = sched_at(sch, i, n_tiles, p);
+            const int sc = (int)(e & 15u);
+            int wb = (int)((e >> 4) & 3u) + rot; wb = wb >= RT_WB ? wb - RT_WB : wb;
+            if (e & 64u) {                           // first use: the loaders fill the buffer for this position
+              const uint32_t f = wb == 0 ? f0 : (wb == 1 ? f1 : f2);
+              RT_TIMED(2, okm = mbar_wait(&bars->wb_full[wb], f & 1u, err, RT_WATCHDOG));
               if (!okm) { atomicCAS(a.dev_error, 0, 206); break; }
               tc_fence_after();
+              if (wb == 0) ++f0; else if (wb == 1) ++f1; else ++f2;
             }
-            if (a.KCH == 128 && a.NCH == 1) {
-              // Common shape (K-slice of 128 atoms): fully unrolled, every descriptor is the item's base descriptor
-              // plus a compile-time constant and every TMEM address a constant offset.  The generic loop below spent
-              // ~85 cycles per MMA on address arithmetic; the tensor pipe needs 32 (M128 x N64 x K8 tf32, measured with
-              // scripts/microbench/mma_rate.cu: 34 per MMA in a dependent chain).
-              constexpr uint32_t HB = NB * 128;
-              const uint64_t dh = umma_desc_k128(hbase);
-              // The slabs land within ~300 cycles of each other (TMA delivers the 64 KB in ~550 cycles) while 12 MMAs take
-              // ~410: two bursts of 24 back-to-back MMAs keep the tensor pipe at its rate (34 cycles per MMA); a barrier
-              // probe between every 12 MMAs let the short MMA queue run dry (60 per MMA).  No tcgen05.fence after these
-              // waits: the barriers are completed by TMA bytes, not by tcgen05 work of other threads.
+            const int hs = hr.idx;
+            RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs], hr.ph, err, RT_WATCHDOG));
+            if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
+            // (no tcgen05.fence after this wait: the barrier is completed by TMA bytes, not by tcgen05 work)
+            if (dbg_on && lane == 0 && p == 0) bars->dbg_ts[0] = clock64();
+            if (lane == 0) RT_TRACE(2, 1 + p, it);
+            const uint32_t wbase = tmem_base + (uint32_t)wb * 128u;
+            const uint64_t dh = umma_desc_k128(smem_u32(smem + a.off_h + hs * a.h_stage_bytes));
+            const bool two = (a.KSLICE - sc * 64 >= 64);
+            // 12 MMAs per 32-atom slab, all descriptors = base + compile-time constants (34 cycles per N=64 MMA when the
+            // queue never runs dry; address arithmetic per MMA cost 85)
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
+            for (int at = 0; at < 2; ++at) {
+              if (at == 1 && !two) break;
 #pragma unroll
-                for (int at = 2 * half; at < 2 * half + 2; ++at) {
-                  RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs][at], (it / a.HST) & 1, err, RT_WATCHDOG));
-                  if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
-                }
-                if (!okm) break;
-                if (dbg_on && lane == 0 && half == 0) bars->dbg_ts[0] = clock64();
-#pragma unroll
-                for (int at = 2 * half; at < 2 * half + 2; ++at) {
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {   // the whole warp stays convergent, the issue itself is predicated
-                    const uint32_t w_hi = tmem_base + (at * 4 + kk) * 8, w_lo = tmem_base + 128 + (at * 4 + kk) * 8;
-                    const uint64_t h_hi = dh + (uint64_t)(((2 * at) * HB + kk * 32) >> 4);
-                    const uint64_t h_lo = dh + (uint64_t)(((2 * at + 1) * HB + kk * 32) >> 4);
-                    if (leader) umma_tf32_ts(d_tmem, w_lo, h_hi, idesc, (at | kk) != 0);
-                    if (leader) umma_tf32_ts(d_tmem, w_hi, h_lo, idesc, true);
-                    if (leader) umma_tf32_ts(d_tmem, w_hi, h_hi, idesc, true);
-                  }
-                }
-              }
-            } else
-#pragma unroll 4
-            for (int ks = 0; ks < nks; ++ks) {
-              const int at = ch2 * (a.KCH / 32) + (ks >> 2), kk = ks & 3;
-              if (kk == 0) {
-                RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs][at], (it / a.HST) & 1, err, RT_WATCHDOG));
-                if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
-                tc_fence_after();
-                if (dbg_on && ch2 == 0 && lane == 0) {   // acc4..6: when slabs 1..3 could start, relative to slab 0
-                  const long long _n = clock64();
-                  if (ks == 0) bars->dbg_ts[0] = _n;
-                  else if (ks == 4) dbg_acc[4] += _n - bars->dbg_ts[0];
-                  else if (ks == 8) dbg_acc[5] += _n - bars->dbg_ts[0];
-                  else if (ks == 12) dbg_acc[6] += _n - bars->dbg_ts[0];
-                }
-              }
-              const uint32_t w_hi = tmem_base + ks * 8, w_lo = tmem_base + a.KCH + ks * 8;
-              const uint64_t h_hi = umma_desc_k128(hbase + (2 * at) * H_ATOM_BYTES + kk * 32);
-              const uint64_t h_lo = umma_desc_k128(hbase + (2 * at + 1) * H_ATOM_BYTES + kk * 32);
-              if (leader) {
-                umma_tf32_ts(d_tmem, w_lo, h_hi, idesc, !(ch2 == 0 && ks == 0));
-                umma_tf32_ts(d_tmem, w_hi, h_lo, idesc, true);
-                umma_tf32_ts(d_tmem, w_hi, h_hi, idesc, true);
+              for (int kk = 0; kk < 4; ++kk) {       // the whole warp stays convergent, the issue itself is predicated
+                const uint32_t w_hi = wbase + (at * 4 + kk) * 8, w_lo = wbase + 64 + (at * 4 + kk) * 8;
+                const uint64_t h_hi = dh + (uint64_t)((at * HB + kk * 32) >> 4);
+                const uint64_t h_lo = dh + (uint64_t)(((2 + at) * HB + kk * 32) >> 4);
+                if (leader) umma_tf32_ts(d_tmem, w_lo, h_hi, idesc, (p | at | kk) != 0);
+                if (leader) umma_tf32_ts(d_tmem, w_hi, h_lo, idesc, true);
+                if (leader) umma_tf32_ts(d_tmem, w_hi, h_hi, idesc, true);
               }
             }
-            if (!okm) break;
-            if (a.NCH > 1 || i == n_tiles - 1) {
-              if (leader) tc_commit(&bars->wt_empty);                  // this chunk of weights has been consumed
-              ++wload;
+            if (leader) {
+              tc_commit(&bars->h_empty[hs]);
+              if (e & 128u) tc_commit(&bars->wb_empty[wb]);           // last use of this sub-chunk in the step
             }
+            __syncwarp();
           }
           if (!okm) break;
-          if (leader) {
-            tc_commit(&bars->h_empty[hs]);
-            tc_commit(&bars->t_full[as]);
-          }
+          if (leader) tc_commit(&bars->t_full[as]);
           __syncwarp();
-          if (dbg_on && lane == 0) {   // acc3: first slab ready -> last MMA issued (the product phase)
+          if (lane == 0) RT_TRACE(2, 20, it);
+          if (dbg_on && lane == 0) {   // acc3: first sub-chunk ready -> last MMA issued (the product phase)
             const long long _n = clock64(); dbg_acc[3] += _n - bars->dbg_ts[0]; bars->dbg_ts[1] = _n;
           }
         }
+        rot += a.rot; rot = rot >= RT_WB ? rot - RT_WB : rot;
       }
     }
-  m_done:;
   } else if (warp >= 4 && warp < 8) {
     // ================= pushers: TMEM accumulator -> staging smem -> bulk DSMEM copy into every owner's slot =========
     // Thread rho holds accumulator row rho.  Rows are staged row-major with the 16-byte chunks of a row XOR-swizzled
@@ -357,13 +396,15 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     constexpr int CHUNKS = NB / 4;                   // 16-byte chunks per row
     constexpr int SWZ = (CHUNKS >= 8) ? 7 : CHUNKS - 1;
     int it = 0;
+    RtRing ar, rr;
     for (int ms = 0; ms < n_mma_steps; ++ms) {      // on a watchdog error the loop keeps running (waits return at once)
-      for (int i = 0; i < n_tiles; ++i, ++it) {     // so that the named barrier below always sees all 128 threads
-        const int as = it % RT_AST, rs = it % a.RST;
+      for (int i = 0; i < n_tiles; ++i, ++it, ar.next(RT_AST), rr.next(a.RST)) {     // so that the named barrier below always sees all 128 threads
+        const int as = ar.idx, rs = rr.idx;
         bool okp;
-        RT_TIMED(0, okp = mbar_wait(&bars->t_full[as], (it / RT_AST) & 1, err, RT_WATCHDOG));
+        RT_TIMED(0, okp = mbar_wait(&bars->t_full[as], ar.ph, err, RT_WATCHDOG));
         if (!okp) atomicCAS(a.dev_error, 0, 207);
         tc_fence_after();
+        if (threadIdx.x == 128) RT_TRACE(4, 1, it);
         if (dbg_on) dbg_acc[2] += clock64() - *reinterpret_cast<volatile long long*>(&bars->dbg_ts[1]);   // issue -> completion
         float v[NB];
 #pragma unroll
@@ -373,8 +414,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->t_empty[as]);
         // slot rs (staging here, reduction slot in the owners) is free once every owner has consumed its previous use
-        RT_TIMED(1, okp = mbar_wait_cluster(&bars->red_free[rs], ((it / a.RST) & 1) ^ 1, err, RT_WATCHDOG));
+        RT_TIMED(1, okp = mbar_wait_cluster(&bars->red_free[rs], rr.ph ^ 1u, err, RT_WATCHDOG));
         if (!okp) atomicCAS(a.dev_error, 0, 208);
+        if (threadIdx.x == 128) RT_TRACE(4, 2, it);
         const uint32_t srow = stage0 + rs * a.red_slot_bytes + rho * (NB * 4);
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
@@ -395,6 +437,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const uint32_t bar = mapa_u32(smem_u32(&bars->red_full[rs]), o);
           dsmem_bulk_copy(dst, src, blk_bytes, bar);
         }
+        if (threadIdx.x == 128) RT_TRACE(4, 3, it);
       }
     }
   } else if (warp == 3) {
@@ -465,6 +508,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     for (int bi = 0; bi < CB; ++bi) xa_next[bi] = make_float4(0.f, 0.f, 0.f, 0.f);
     fetch_xw(0, 0, 0, xa_next);
     int it = 0;
+    RtRing rr;
     long long j = 0;
     for (int t = 0; t < T; ++t)
     for (int k = 0; k < K; ++k)
@@ -532,13 +576,14 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         asm volatile("bar.sync 1, 128;" ::: "memory");
       } else {
         // ---- wait for the KS partial tiles, sum them in rank order ----
-        const int rs = it % a.RST;
+        const int rs = rr.idx;
         if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
         bool oko;
-        RT_TIMED(0, oko = mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG));
+        RT_TIMED(0, oko = mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG));
         if (!oko) atomicCAS(a.dev_error, 0, 210);
         const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
         if (dbg_on) _ts = clock64();
+        if (otid == 0) RT_TRACE(5, 1, it);
         // address of (row r, columns CB*cq..) inside a source block: row-major, 16-byte chunk index swizzled by
         // (row & 7); the pusher's row index rho = o*RO + r has the same low 3 bits as r because RO is a multiple of 8.
         const uint32_t src_stride = (uint32_t)(RO * NB * 4);
@@ -573,7 +618,8 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         __syncwarp();                                  // this warp has consumed the slot (values are in registers):
         if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);   // 4 warps x KS owners arrivals
         if (dbg_on) { long long _n = clock64(); dbg_acc[3] += _n - _ts; _ts = _n; }
-        ++it;
+        if (otid == 0) RT_TRACE(5, 2, it);
+        ++it; rr.next(a.RST);
       }
       // ---- fused epilogue: relu(acc + x~W_k + b_k + leak terms), Keras mask carry on the last layer ----
       if (mine) {
@@ -670,7 +716,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         // latency mode (one batch tile): every owner warp releases its own stores - ONE wait for the write acks on the
         // critical path instead of release.cta arrive + the publisher's gpu fence back to back
         __syncwarp();
+        if (otid == 0 && k > 0) RT_TRACE(5, 3, it - 1);
         if (lane == 0) RT_TIMED(1, flag_add_release(a.flags + i * a.MT + m, 1u));
+        if (otid == 0 && k > 0) RT_TRACE(5, 4, it - 1);
       } else {
         // ---- hand the item to the publisher (release.cta arrive; the publisher's fence makes it gpu-visible) ----
         const int ps_ = (int)(j % RT_PST);
@@ -737,6 +785,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       for (int bi = 0; bi < CB; ++bi) act_next[e][bi] = 0.f;
     fetch_act(0, 0, 0, act_next);
     int it = 0;
+    RtRing rr;
     long long j = 0;
     for (int fi = 0; fi < T; ++fi)
     for (int u = 0; u < K; ++u)
@@ -826,9 +875,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           d[0][bi] = dg[0]; d[1][bi] = dg[1]; d[2][bi] = dg[2]; d[3][bi] = dg[3];
         }
       } else {
-        const int rs = it % a.RST;
+        const int rs = rr.idx;
         if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
-        if (!mbar_wait_cluster(&bars->red_full[rs], (it / a.RST) & 1, err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 220);
+        if (!mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 220);
         const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -865,7 +914,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         }
         __syncwarp();
         if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);
-        ++it;
+        ++it; rr.next(a.RST);
 #pragma unroll
         for (int bi = 0; bi < CB; ++bi) {   // identity part of S_k: this owner's rows of the operand; scale back (vector alph)
           d[0][bi] = (d[0][bi] + pre[bi].x) * a_post.x; d[1][bi] = (d[1][bi] + pre[bi].y) * a_post.y;
@@ -941,173 +990,73 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       }
     }
   }
-  if (warp >= 12 && a.WST == 0) {
-    // ================= weight loaders, direct variant (throughput mode: no shared memory left for a weight ring) =======
-    // S_k^T[m*128 + row][s*KSLICE ..] : L2 -> registers -> (hi | lo) in TMEM; the weights are loaded once per step and
-    // reused by every batch tile, so their latency is amortised.
+  if (warp >= 12) {
+    // ================= weight loaders: smem ring -> registers -> (hi | lo) in a TMEM weight buffer =================
+    // Thread = row of the M-tile = TMEM lane.  A piece is 128 rows x 128 bytes in the TMA 128B-swizzle layout (16-byte
+    // chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)): eight consecutive rows read eight different chunks, so the
+    // LDS.128 of a quarter-warp are conflict-free.  The loaders walk the same schedule as the MMA warp and fill a buffer
+    // whenever a position is a first use.
     const int q = warp - 12;                          // TMEM lane quarter (warp % 4)
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int nchunk = a.KCH / 32;
-    const uint64_t pol_w = l2_policy_evict_last();
-    int wl = 0;
+    RtRing wr;
+    uint32_t f0 = 0, f1 = 0, f2 = 0;
+    int rot = 0;
     bool okl = true;
     for (int ms = 0; ms < n_mma_steps && okl; ++ms) {
-      // forward walks the layers 1..K-1 of every frame, backward K-1..1 (S_k is symmetric for scalar alph)
-      const int k = BWD ? (K - 1 - ms % (K - 1)) : (ms % (K - 1) + 1);
-      const int reps = (a.NCH > 1) ? n_tiles : 1;      // multi-chunk slices are re-streamed for every batch tile
-      for (int rep = 0; rep < reps && okl; ++rep)
-      for (int ch2 = 0; ch2 < a.NCH; ++ch2, ++wl) {
-      const int col0 = s * a.KSLICE + ch2 * a.KCH;
-      const float* src = a.ST + ((size_t)(k - 1) * Rp + (size_t)m * 128 + row) * Rp + (size_t)col0;
-      // Two register buffers: chunks 0 and 1 are fetched before waiting for the TMEM buffer, chunk c + 2 right after
-      // chunk c has been converted, so two L2 round trips are always in flight behind the conversion work.
-      float va[32], vb[32];
-      auto fetch = [&](float (&v)[32], int ch) {
+      for (int i = 0; i < n_tiles && okl; ++i)
+        for (int p = 0; p < NSC && okl; ++p) {
+          const uint32_t e = sched_at(sch, i, n_tiles, p);
+          if (!(e & 64u)) continue;
+          const int sc = (int)(e & 15u);
+          int wb = (int)((e >> 4) & 3u) + rot; wb = wb >= RT_WB ? wb - RT_WB : wb;
+          const int col0 = s * a.KSLICE + sc * 64;
+          const int npc = (a.KSLICE - sc * 64 >= 64) ? 2 : 1;
+          const uint32_t tb = trow + (uint32_t)wb * 128u;
+          for (int pc = 0; pc < npc; ++pc, wr.next(a.WST)) {
+            const int ws = wr.idx;
+            RT_TIMED(1, okl = mbar_wait(&bars->w_full[ws], wr.ph, err, RT_WATCHDOG));
+            if (!okl) { atomicCAS(a.dev_error, 0, 215); break; }
+            const uint32_t rbase = smem_u32(smem + a.off_w + ws * 16384) + (uint32_t)row * 128u;
+            float v[32];
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 f = ldg_hint4(src + ch * 32 + 4 * c4, pol_w);
-          v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
-        }
-      };
-      // The tensor core multiplies by S_k^T - I = -(G_k)^T only; the identity part of the product (the operand itself)
-      // is added exactly, in fp32, by the row owner.  tcgen05 accumulates with round-toward-zero, and with the identity
-      // inside the product that bias (relative to |h|) piles up over the K_layers x T chain (measured 1.1e-4 on H at
-      // R=1000, K=25 against 5e-6 for this form).
-      auto convert = [&](float (&v)[32], int ch) {
-        if (col0 + ch * 32 == m * 128 + q * 32) {       // warp-uniform: this chunk holds the diagonal, in column `lane`
+            for (int c4 = 0; c4 < 8; ++c4)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * c4]), "=f"(v[4 * c4 + 1]), "=f"(v[4 * c4 + 2]),
+                           "=f"(v[4 * c4 + 3]) : "r"(rbase + (uint32_t)((c4 ^ (row & 7)) << 4)));
+            if (pc == 0) {
+              const uint32_t f = wb == 0 ? f0 : (wb == 1 ? f1 : f2);
+              RT_TIMED(0, okl = mbar_wait(&bars->wb_empty[wb], (f & 1u) ^ 1u, err, RT_WATCHDOG));
+              if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
+              tc_fence_after();
+            }
+            // The tensor core multiplies by S_k^T - I = -(G_k)^T only; the identity part of the product (the operand
+            // itself) is added exactly, in fp32, by the row owner.  tcgen05 accumulates with round-toward-zero, and with
+            // the identity inside the product that bias (relative to |h|) piles up over the K_layers x T chain (measured
+            // 1.1e-4 on H at R=1000, K=25 against 5e-6 for this form).
+            if (col0 + pc * 32 == m * 128 + q * 32) {     // warp-uniform: this piece holds the diagonal, in column `lane`
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] -= (e == lane) ? 1.0f : 0.0f;     // select, not a branch (a 32-way jump table otherwise)
-        }
-        float lo[32];
+              for (int e2 = 0; e2 < 32; ++e2) v[e2] -= (e2 == lane) ? 1.0f : 0.0f;   // select, not a branch (a 32-way jump table otherwise)
+            }
+            float lo[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(v[e]);
-        tmem_st32(trow + ch * 32, v);
-        tmem_st32(trow + a.KCH + ch * 32, lo);
-      };
-      fetch(va, 0);
-      if (nchunk > 1) fetch(vb, 1);
-      RT_TIMED(0, okl = mbar_wait(&bars->wt_empty, (uint32_t)((wl & 1) ^ 1), err, RT_WATCHDOG));
-      if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
-      tc_fence_after();
-      for (int ch = 0; ch < nchunk; ch += 2) {
-        convert(va, ch);
-        if (ch + 2 < nchunk) fetch(va, ch + 2);
-        if (ch + 1 < nchunk) {
-          convert(vb, ch + 1);
-          if (ch + 3 < nchunk) fetch(vb, ch + 3);
-        }
-      }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(&bars->wt_full);
-      }
-    }
-  }
-  if (warp >= 12 && a.WST > 0 && a.sym && s < m) {
-    // ================= weight loaders, mirrored block (symmetric S_k, CTA below the diagonal) =================
-    // The ring holds block (s, m): stage ch = [K index c (128 rows)] x [output rows 32*ch .. +32 of the M-tile (128
-    // bytes)].  Warp q owns TMEM lanes = output rows 32q..32q+31, i.e. exactly stage q, and reads it transposed: for a
-    // fixed c the 32 lanes read one 128-byte row (conflict-free).  No diagonal in these blocks.  The four stages are
-    // handed back after the last piece (every warp waits for and arrives on every stage so that the arrival counts of
-    // consecutive steps cannot mix).
-    const int q = warp - 12;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    int wl = 0;
-    long long wc = 0;
-    bool okl = true;
-    for (int ms = 0; ms < n_mma_steps && okl; ++ms, ++wl, wc += 4) {
-      for (int ch = 0; ch < 4 && okl; ++ch) {
-        const long long w2 = wc + ch;
-        RT_TIMED(1, okl = mbar_wait(&bars->w_full[(int)(w2 % a.WST)], (uint32_t)((w2 / a.WST) & 1), err, RT_WATCHDOG));
-        if (!okl) atomicCAS(a.dev_error, 0, 215);
-      }
-      if (!okl) break;
-      RT_TIMED(0, okl = mbar_wait(&bars->wt_empty, (uint32_t)((wl & 1) ^ 1), err, RT_WATCHDOG));
-      if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
-      tc_fence_after();
-      const uint32_t tile = smem_u32(smem + a.off_w + (int)((wc + q) % a.WST) * 16384);
-      const uint32_t lcol = (uint32_t)(lane & 3) * 4u, lchunk = (uint32_t)(lane >> 2);
-      for (int pc = 0; pc < 4; ++pc) {                  // 32 K-columns at a time
-        float v[32], lo[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const uint32_t c = (uint32_t)(pc * 32 + e);
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[e]) : "r"(tile + c * 128u + ((lchunk ^ (c & 7u)) << 4) + lcol));
-        }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(v[e]);
-        tmem_st32(trow + pc * 32, v);
-        tmem_st32(trow + a.KCH + pc * 32, lo);
-      }
-      fence_proxy_async_smem();                          // all values have been consumed by the arithmetic above
-      __syncwarp();
-      if (lane < 4) mbar_arrive(&bars->w_free[(int)((wc + lane) % a.WST)]);
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(&bars->wt_full);
-    }
-  } else if (warp >= 12 && a.WST > 0) {
-    // ================= weight loaders: smem ring -> registers -> (hi | lo) in TMEM =================
-    // Thread = row of the M-tile = TMEM lane.  A chunk is 128 rows x 128 bytes in the TMA 128B-swizzle layout (16-byte
-    // piece c of row r sits at r*128 + ((c ^ (r & 7)) << 4)): eight consecutive rows read eight different pieces, so the
-    // LDS.128 of a quarter-warp are conflict-free.
-    const int q = warp - 12;                          // TMEM lane quarter (warp % 4)
-    const int row = q * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int nchunk = a.KCH / 32;
-    int wl = 0;
-    long long wc = 0;
-    bool okl = true;
-    for (int ms = 0; ms < n_mma_steps && okl; ++ms) {
-      const int reps = (a.NCH > 1) ? n_tiles : 1;      // multi-chunk slices are re-streamed for every batch tile
-      for (int rep = 0; rep < reps && okl; ++rep)
-      for (int ch2 = 0; ch2 < a.NCH && okl; ++ch2, ++wl) {
-        const int col0 = s * a.KSLICE + ch2 * a.KCH;
-        for (int ch = 0; ch < nchunk; ++ch, ++wc) {
-          const int ws = (int)(wc % a.WST);
-          RT_TIMED(1, okl = mbar_wait(&bars->w_full[ws], (uint32_t)((wc / a.WST) & 1), err, RT_WATCHDOG));
-          if (!okl) { atomicCAS(a.dev_error, 0, 215); break; }
-          const uint32_t rbase = smem_u32(smem + a.off_w + ws * 16384) + (uint32_t)row * 128u;
-          long long _tl = dbg_on ? clock64() : 0;
-          float v[32];
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * c4]), "=f"(v[4 * c4 + 1]), "=f"(v[4 * c4 + 2]),
-                         "=f"(v[4 * c4 + 3]) : "r"(rbase + (uint32_t)((c4 ^ (row & 7)) << 4)));
-          if (ch == 0) {
-            RT_TIMED(0, okl = mbar_wait(&bars->wt_empty, (uint32_t)((wl & 1) ^ 1), err, RT_WATCHDOG));
-            if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
-            tc_fence_after();
+            for (int e2 = 0; e2 < 32; ++e2) lo[e2] = tf32_lo(v[e2]);
+            // Hand the piece back only now: the arithmetic above depends on every loaded value, so the LDS have really
+            // completed (an arrive issued right behind the loads let the refill overtake them: measured, non-repeatable
+            // results), and the generic-proxy reads are fenced against the async-proxy (TMA) refill.
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->w_free[ws]);
+            tmem_st32(tb + pc * 32, v);
+            tmem_st32(tb + 64 + pc * 32, lo);
           }
-          // The tensor core multiplies by S_k^T - I = -(G_k)^T only; the identity part of the product (the operand
-          // itself) is added exactly, in fp32, by the row owner.  tcgen05 accumulates with round-toward-zero, and with
-          // the identity inside the product that bias (relative to |h|) piles up over the K_layers x T chain (measured
-          // 1.1e-4 on H at R=1000, K=25 against 5e-6 for this form).
-          if (col0 + ch * 32 == m * 128 + q * 32) {     // warp-uniform: this chunk holds the diagonal, in column `lane`
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] -= (e == lane) ? 1.0f : 0.0f;   // select, not a branch (a 32-way jump table otherwise)
-          }
-          float lo[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) lo[e] = tf32_lo(v[e]);
-          // Hand the stage back only now: the arithmetic above depends on every loaded value, so the LDS have really
-          // completed (an arrive issued right behind the loads let the refill overtake them: measured, non-repeatable
-          // results), and the generic-proxy reads are fenced against the async-proxy (TMA) refill.
-          if (dbg_on) { long long _n = clock64(); dbg_acc[2] += _n - _tl; _tl = _n; }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->w_free[ws]);
-          if (dbg_on) { long long _n = clock64(); dbg_acc[3] += _n - _tl; _tl = _n; }
-          tmem_st32(trow + ch * 32, v);
-          tmem_st32(trow + a.KCH + ch * 32, lo);
-          if (dbg_on) { long long _n = clock64(); dbg_acc[4] += _n - _tl; _tl = _n; }
+          if (!okl) break;
+          RT_TIMED(5, tc_wait_st());
+          tc_fence_before();
+          mbar_arrive(&bars->wb_full[wb]);
+          if (threadIdx.x == 384) RT_TRACE(6, 1 + sc, (long long)ms * n_tiles + i);
+          if (wb == 0) ++f0; else if (wb == 1) ++f1; else ++f2;
         }
-        if (!okl) break;
-        RT_TIMED(5, tc_wait_st());
-        tc_fence_before();
-        mbar_arrive(&bars->wt_full);
-      }
+      rot += a.rot; rot = rot >= RT_WB ? rot - RT_WB : rot;
     }
   }
   if (dbg_on && (lane == 0 || warp >= 4) && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64 ||
@@ -1125,7 +1074,46 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------
 // n_tiles = batch tiles per group, G = batch groups (grid.z), n_tiles_total = tiles of the whole batch
-struct RecPlan { int NB, KS, MT, RO, ATOMS, KSLICE, n_tiles, n_tiles_total, G, WST, HST, RST, CB; size_t smem; RecArgs a; bool ok; const char* why; };
+struct RecPlan { int NB, KS, MT, RO, NSC, KSLICE, n_tiles, n_tiles_total, G, WST, HST, RST, CB; size_t smem; RecArgs a; RecSched sch; bool ok; const char* why; };
+
+// Per-step schedule (see RecSched).  NSC <= RT_WB: every sub-chunk of the step is resident, all tiles walk the K-slice
+// upwards (results do not depend on the tile an utterance lands in) and the buffers rotate from step to step so that the
+// next step's first sub-chunks are converted while this step still multiplies.  NSC > RT_WB: buffer = sub-chunk mod 3,
+// tiles walk the K-slice in alternating direction and reuse whatever the previous tile left resident.
+static void build_schedule(RecSched& sc, int NSC, int n_tiles, int* rot) {
+  memset(&sc, 0, sizeof(sc));
+  if (NSC <= RT_WB) {
+    *rot = NSC % RT_WB;
+    for (int cls = 0; cls < 6; ++cls)
+      for (int p = 0; p < NSC; ++p)
+        sc.e[cls][p] = (uint8_t)(p | (p << 4) | ((cls % 3 == 0) ? 64 : 0) | ((cls >= 3) ? 128 : 0));
+    return;
+  }
+  *rot = 0;
+  const int n = n_tiles < 6 ? n_tiles : 6 - ((n_tiles & 1) ? 1 : 0);   // the pattern has period 2: simulate a short step of the same parity
+  struct Acc { int sc, slot, fresh, last; };
+  Acc acc[6 * RT_MAXSC];
+  int resident[RT_WB] = {-1, -1, -1};
+  for (int i = 0; i < n; ++i)
+    for (int p = 0; p < NSC; ++p) {
+      Acc& x = acc[i * NSC + p];
+      x.sc = (i & 1) ? NSC - 1 - p : p;
+      x.slot = x.sc % RT_WB;
+      x.fresh = resident[x.slot] != x.sc;
+      resident[x.slot] = x.sc;
+      x.last = 1;
+    }
+  for (int j = 0; j < n * NSC; ++j)
+    for (int j2 = j + 1; j2 < n * NSC; ++j2)
+      if (acc[j2].slot == acc[j].slot) { acc[j].last = acc[j2].sc != acc[j].sc; break; }
+  for (int i = 0; i < n; ++i) {
+    const int cls = (i == 0 ? 0 : ((i & 1) ? 1 : 2)) + (i == n - 1 ? 3 : 0);
+    for (int p = 0; p < NSC; ++p) {
+      const Acc& x = acc[i * NSC + p];
+      sc.e[cls][p] = (uint8_t)(x.sc | (x.slot << 4) | (x.fresh ? 64 : 0) | (x.last ? 128 : 0));
+    }
+  }
+}
 
 static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int G) {
   RecPlan p{};
@@ -1138,44 +1126,49 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
   if (G > p.n_tiles_total) G = p.n_tiles_total;
   p.n_tiles = (p.n_tiles_total + G - 1) / G;
   p.G = (p.n_tiles_total + p.n_tiles - 1) / p.n_tiles;      // no empty group
-  if (Rp % (KS * 32) != 0 || p.MT * KS > h->num_sms) { p.why = "no (M-tile x K-split) grid fits the device"; return p; }
-  p.KS = KS; p.RO = 128 / KS; p.KSLICE = Rp / KS; p.ATOMS = p.KSLICE / 32;
-  if (p.KSLICE > 512 || (p.KSLICE > 128 && p.KSLICE % 128 != 0)) { p.why = "K-slice wider than 512 atoms (four TMEM weight chunks)"; return p; }
+  if (Rp % (KS * 32) != 0 || p.MT * KS * p.G > h->num_sms) { p.why = "no (M-tile x K-split) grid fits the device"; return p; }
+  p.KS = KS; p.RO = 128 / KS; p.KSLICE = Rp / KS; p.NSC = (p.KSLICE + 63) / 64;
+  if (p.NSC > RT_MAXSC) { p.why = "K-slice wider than 1024 atoms"; return p; }
   {   // who publishes: every owner warp with its own red.release (default for one tile per group) or a publisher thread
     const char* e = getenv("DRNMF_REC_PUB");
     const bool direct = e ? !strcmp(e, "direct") : (p.n_tiles == 1);
     p.a.pub_unit = direct ? 4 : 1;
   }
-  p.a.KCH = p.KSLICE > 128 ? 128 : p.KSLICE;
-  p.a.NCH = p.KSLICE / p.a.KCH;
   if (p.RO * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
   p.CB = p.RO * p.NB >= 2048 ? 4 : (p.RO * p.NB >= 1024 ? 2 : 1);     // batch columns per owner thread (4 rows x CB)
   if (((p.RO / 4) * (p.NB / p.CB)) % 32 != 0) { p.why = "owner tile smaller than a warp"; return p; }
-  const int h_stage = 2 * p.ATOMS * p.NB * 128, red_slot = 128 * p.NB * 4;   // slot = KS blocks of RO x NB fp32
+  const int h_stage = 4 * p.NB * 128, red_slot = 128 * p.NB * 4;      // 64 atoms (hi, lo) x NB ; KS blocks of RO x NB fp32
   const int leak_b = round_up(2 * p.n_tiles * p.NB * 4, 128), out_b = round_up(max(p.NB * (p.RO + 1), 128) * 4, 128);
   const int fixed = leak_b + out_b + (int)sizeof(RecBars) + 256;
   const int budget = 232448 - 1024 - fixed;
-  // every reduction slot has a twin staging slot on the pusher side (same index), hence 2 * red_slot per depth
-  // One batch tile in flight (latency mode): the next step's hidden state only exists after this step's MMAs, so one
-  // hidden-state stage and one reduction slot are enough and the rest of the shared memory holds the weight ring (a
-  // whole step ahead when it fits).  Several tiles (throughput mode): two hidden-state stages first, the weights are
-  // reused by every tile and need a single stage.
+  // every reduction slot has a twin staging slot on the pusher side (same index), hence 2 * red_slot per depth.
+  // One batch tile per group (latency mode): the next step's hidden state only exists after this step's exchange, so a
+  // step's worth of hidden sub-chunks and one reduction slot are enough and the rest of the shared memory holds the
+  // weight ring (a whole step ahead when it fits).  Several tiles (throughput mode): the tiles pipeline, so the
+  // reduction slots and the hidden-state ring get their second stages first.
   const int w_stage = 16384;
-  const int wst_max = getenv("DRNMF_REC_WST") ? atoi(getenv("DRNMF_REC_WST")) : 8;
-  p.WST = 0; p.HST = (p.n_tiles > 1) ? 2 : 1; p.RST = 1;
-  int rem = budget - p.HST * h_stage - p.RST * 2 * red_slot;
-  if (rem < 0) { p.why = "hidden-state and reduction rings do not fit in shared memory"; return p; }
-  // a ring shallower than a step's worth of chunks only adds the TMA round trip per chunk (measured 3.7k cycles each):
-  // in that case the loaders read the weights straight from L2 (WST = 0)
-  const int w_want = min(min(p.ATOMS, 4), wst_max);
-  if (rem >= w_want * w_stage) { p.WST = w_want; rem -= w_want * w_stage; }
-  if (p.n_tiles > 1) {
-    if (rem >= 2 * red_slot) { ++p.RST; rem -= 2 * red_slot; }
-    while (p.HST < 4 && rem >= h_stage) { ++p.HST; rem -= h_stage; }
-    while (p.RST < 4 && rem >= 2 * red_slot) { ++p.RST; rem -= 2 * red_slot; }
+  const int env_wst = getenv("DRNMF_REC_WST") ? atoi(getenv("DRNMF_REC_WST")) : 0;
+  const int env_hst = getenv("DRNMF_REC_HST") ? atoi(getenv("DRNMF_REC_HST")) : 0;
+  const int env_rst = getenv("DRNMF_REC_RST") ? atoi(getenv("DRNMF_REC_RST")) : 0;
+  const int pieces_per_step = p.KSLICE / 32;
+  p.HST = 2; p.RST = 1; p.WST = 2;
+  int rem = budget - p.HST * h_stage - p.RST * 2 * red_slot - p.WST * w_stage;
+  if (rem < 0) { p.why = "hidden-state, reduction and weight rings do not fit in shared memory"; return p; }
+  auto grow = [&](int& depth, int unit, int cap) { while (depth < cap && rem >= unit) { ++depth; rem -= unit; } };
+  if (p.n_tiles == 1) {
+    grow(p.HST, h_stage, min(p.NSC, RT_MAXH));
+    grow(p.WST, w_stage, min(pieces_per_step, RT_MAXW));
+  } else {
+    grow(p.RST, 2 * red_slot, 2);
+    grow(p.HST, h_stage, 3);
+    grow(p.WST, w_stage, 4);
+    grow(p.HST, h_stage, min(2 * p.NSC, RT_MAXH));
+    grow(p.WST, w_stage, min(pieces_per_step, RT_MAXW));
   }
-  while (p.WST > 0 && p.WST < wst_max && p.WST < p.ATOMS && rem >= w_stage) { ++p.WST; rem -= w_stage; }
-  p.a.sym = (h->alph_dim == 1 && p.KSLICE == 128 && p.a.NCH == 1 && p.KS == p.MT && p.WST >= 4 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
+  if (env_hst > 0 && env_hst <= RT_MAXH) p.HST = env_hst;
+  if (env_rst > 0 && env_rst <= 4) p.RST = env_rst;
+  if (env_wst > 0 && env_wst <= RT_MAXW) p.WST = env_wst;
+  if (p.HST * h_stage + p.RST * 2 * red_slot + p.WST * w_stage > budget) { p.why = "requested ring depths do not fit in shared memory"; return p; }
   int off = 0;
   p.a.off_w = off; off += p.WST * w_stage;
   p.a.off_h = off; off += p.HST * h_stage;
@@ -1186,14 +1179,15 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
   p.a.off_bar = off; off += (int)sizeof(RecBars);
   p.smem = (size_t)off + 1024;
   p.a.h_stage_bytes = h_stage; p.a.red_slot_bytes = red_slot;
-  p.a.MT = p.MT; p.a.KS = p.KS; p.a.RO = p.RO; p.a.ATOMS = p.ATOMS; p.a.KSLICE = p.KSLICE; p.a.n_tiles = p.n_tiles;
+  p.a.MT = p.MT; p.a.KS = p.KS; p.a.RO = p.RO; p.a.KSLICE = p.KSLICE; p.a.n_tiles = p.n_tiles; p.a.NSC = p.NSC;
   p.a.n_tiles_total = p.n_tiles_total;
   p.a.WST = p.WST; p.a.HST = p.HST; p.a.RST = p.RST;
+  build_schedule(p.sch, p.NSC, p.n_tiles, &p.a.rot);
   p.ok = true;
   return p;
 }
 
-using RecKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, RecArgs);
+using RecKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const RecSched, const RecArgs);
 
 template <int NB>
 static RecKernel rec_kernel_nb(bool bwd, int CB) {
@@ -1216,7 +1210,7 @@ static void rec_launch_config(const RecPlan& p, cudaLaunchConfig_t& cfg, cudaLau
   // The CTAs spin on flags written by other clusters, so the whole grid must be co-resident.  A cooperative launch
   // makes the driver check that at launch time (SMs taken by another stream / process / NCCL kernel -> the launch
   // fails cleanly with cudaErrorCooperativeLaunchTooLarge instead of running into the device-side watchdog).
-  static const bool coop = getenv("DRNMF_REC_COOP") && !strcmp(getenv("DRNMF_REC_COOP"), "1");   // TODO default on once verified
+  static const bool coop = !(getenv("DRNMF_REC_COOP") && !strcmp(getenv("DRNMF_REC_COOP"), "0"));
   if (coop) {
     attr[1].id = cudaLaunchAttributeCooperative;
     attr[1].val.cooperative = 1;
@@ -1231,6 +1225,7 @@ static int rec_max_clusters(const RecPlan& p, bool bwd, int* out) {
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
   rec_launch_config(p, cfg, attr, nullptr);
+  cfg.numAttrs = 1;                             // the occupancy query takes the cluster shape only
   *out = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(out, kern, &cfg);
   if (e != cudaSuccess) { cudaGetLastError(); *out = 0; }
@@ -1244,31 +1239,39 @@ static int launch_rec(const RecPlan& p, bool bwd, const CUtensorMap& tH_hi, cons
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
   rec_launch_config(p, cfg, attr, st);
-  DRNMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tH_hi, tH_lo, tW, p.a));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tH_hi, tH_lo, tW, p.sch, p.a);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("persistent recurrence launch failed (%s): grid %d x %d x %d CTAs must be co-resident; SMs in use by another "
+              "stream or process?", cudaGetErrorString(e), p.KS, p.MT, p.G);
+    return DRNMF_ERR_CUDA;
+  }
   count_launch();
   return DRNMF_OK;
 }
 
-// Candidate tilings, preferred first: more K-splits = more SMs streaming the weights; the cluster (= the K-splits of
-// one M-tile) must be co-resident MT times per batch group, which depends on the board's GPC layout -> ask the
-// occupancy API.  Batch groups: utterances are independent, so when the device can host G x MT clusters the batch is
-// cut into G groups on disjoint SMs (B = 64 at R = 1000: two groups of one 32-utterance tile on 128 SMs; a 32-column
-// step is shorter than a 64-column one, and throughput batches use twice the tensor pipes).  The batch tile is the
-// widest one that still leaves a tile for every group.
+// Candidate tilings.  K-splits (= cluster size) of 4 first: a B200 hosts 33 clusters of 4 but only 15 of 8, and a
+// 128 x (Rp/4) block per CTA does twice the tensor work per exchanged partial tile.  Batch groups: when the device can
+// host G x MT clusters the batch is cut into G groups on disjoint SMs (R = 1000: 4 groups x 32 CTAs).  The batch tile
+// is the widest one that still leaves a tile for every group (B = 64 -> four groups of one 16-utterance tile; B >= 256
+// -> 64-column tiles pipelined through the same weights).
 static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
   RecPlan p{};
   p.ok = false; p.why = "no candidate tiling";
   const char* env_ks = getenv("DRNMF_REC_KS");
   const char* env_nb = getenv("DRNMF_REC_NB");
   const char* env_g = getenv("DRNMF_REC_G");
-  for (int KS = 16; KS >= 1 && !p.ok; KS >>= 1) {
+  const bool verbose = getenv("DRNMF_REC_VERBOSE") != nullptr;
+  static const int ks_order[5] = {4, 8, 2, 1, 16};
+  for (int kq = 0; kq < 5 && !p.ok; ++kq) {
+    const int KS = ks_order[kq];
     if (env_ks && atoi(env_ks) != KS) continue;
     // co-resident clusters for this cluster size (probe with the smallest tile: shared memory is at the limit anyway)
     RecPlan probe = plan_recurrent(h, B, KS, 16, 1);
     if (!probe.ok) { p.why = probe.why; continue; }
     int mc = 0;
     rec_max_clusters(probe, bwd, &mc);
-    if (getenv("DRNMF_REC_VERBOSE")) fprintf(stderr, "[libdrnmf] plan probe KS=%d MT=%d smem=%zu: %d co-resident clusters\n", KS, probe.MT, probe.smem, mc);
+    if (verbose) fprintf(stderr, "[libdrnmf] plan probe KS=%d MT=%d smem=%zu: %d co-resident clusters\n", KS, probe.MT, probe.smem, mc);
     if (mc < probe.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
     const int g_max = env_g ? atoi(env_g) : mc / probe.MT;
     for (int NB = 64; NB >= 16 && !p.ok; NB >>= 1) {
@@ -1282,7 +1285,7 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
         if (c.G != G && G != g_max) continue;       // this group count was already tried
         int mc2 = 0;
         rec_max_clusters(c, bwd, &mc2);
-        if (getenv("DRNMF_REC_VERBOSE")) fprintf(stderr, "[libdrnmf]   candidate KS=%d NB=%d G=%d tiles/group=%d smem=%zu: %d co-resident clusters (need %d)\n", KS, NB, c.G, c.n_tiles, c.smem, mc2, c.MT * c.G);
+        if (verbose) fprintf(stderr, "[libdrnmf]   candidate KS=%d NB=%d G=%d tiles/group=%d smem=%zu: %d co-resident clusters (need %d)\n", KS, NB, c.G, c.n_tiles, c.smem, mc2, c.MT * c.G);
         if (mc2 < c.MT * c.G) { p.why = "not enough co-resident clusters for any tiling"; continue; }
         p = c;
       }
@@ -1292,16 +1295,36 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
   return p;
 }
 
-// Backward chain on the persistent kernel.  Returns 1 (no error set) when the shape is not covered and the caller
-// should use the CUDA-core chain instead.
+// Hidden-state tensor maps: 3-D slab maps (one instruction per 64-atom sub-chunk and hi/lo) when the driver accepts
+// the stride order, else 2-D maps (one instruction per 32-atom tile).
+static int make_h_maps(CUtensorMap* hi, CUtensorMap* lo, const FwdWorkspace& w, int Rp, int NB, int* h3d) {
+  static int use3d = getenv("DRNMF_REC_H2D") ? 0 : 1;
+  if (use3d) {
+    if (make_tmap_slabs(hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, NB, 2) == DRNMF_OK &&
+        make_tmap_slabs(lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, NB, 2) == DRNMF_OK) { *h3d = 1; return DRNMF_OK; }
+    fprintf(stderr, "[libdrnmf] 3-D slab tensor maps rejected (%s); using 2-D maps\n", last_error());
+    use3d = 0;
+  }
+  *h3d = 0;
+  int rc;
+  if ((rc = make_tmap_2d(hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, NB))) return rc;
+  return make_tmap_2d(lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, NB);
+}
+
+static void record_cfg(const RecPlan& p, int* cfg8, int* groups) {
+  const int c[8] = {p.NB, p.KS, p.MT, p.NSC, p.n_tiles, p.WST, p.HST, p.RST};
+  for (int i = 0; i < 8; ++i) cfg8[i] = c[i];
+  *groups = p.G;
+}
+
+// Backward chain on the persistent kernel.  Returns 1 (error text set) when no tiling covers the shape.
 int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,
                             float* deltaT_lo, float* G, float* psum2, cudaStream_t st) {
   const int K = h->K, Rp = h->Rp;
   if (K < 2) return 1;
   RecPlan p = choose_plan(h, B, true);
   if (!p.ok) { set_error("persistent tcgen05 backward chain unavailable for this shape (%s)", p.why); return 1; }
-  { int c[8] = {p.NB, p.KS, p.MT, p.ATOMS, p.n_tiles, p.WST, p.HST, p.RST}; for (int i = 0; i < 8; ++i) h->bwd_cfg[i] = c[i]; }
-  h->bwd_groups = p.G;
+  record_cfg(p, h->bwd_cfg, &h->bwd_groups);
   RecArgs& a = p.a;
   a.XW = nullptr; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.state = nullptr; a.psum = nullptr; a.Hp_hi = nullptr; a.Hp_lo = nullptr; a.H_user = nullptr;
@@ -1313,13 +1336,11 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   a.dbg = nullptr;
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = 0.f; a.u0_off = 0.f; a.uk_dmo = 0.f; a.uk_off = 0.f;
-  a.ST = h->ST_hi;
   DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
   CUtensorMap tH_hi, tH_lo, tW;
   int rc;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
-  if ((rc = make_tmap_2d(&tH_hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
-  if ((rc = make_tmap_2d(&tH_lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
+  if ((rc = make_h_maps(&tH_hi, &tH_lo, w, Rp, p.NB, &a.h3d))) return rc;
   return launch_rec(p, true, tH_hi, tH_lo, tW, st);
 }
 
@@ -1334,8 +1355,7 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
     return DRNMF_ERR_INVALID;
   }
   h->last_rec_impl = 0;
-  { int c[8] = {p.NB, p.KS, p.MT, p.ATOMS, p.n_tiles, p.WST, p.HST, p.RST}; for (int i = 0; i < 8; ++i) h->rec_cfg[i] = c[i]; }
-  h->rec_groups = p.G;
+  record_cfg(p, h->rec_cfg, &h->rec_groups);
   RecArgs& a = p.a;
   a.XW = w.XW; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.state = w.state; a.psum = w.psum; a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;
@@ -1348,15 +1368,23 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   a.dbg_m = want_dbg ? atoi(getenv("DRNMF_REC_DEBUG")) - 1 : 0;      // DRNMF_REC_DEBUG=1 observes CTA (0,0), =2 CTA (0,1) ...
   if (a.dbg_m < 0 || a.dbg_m >= p.MT) a.dbg_m = 0;
   if (want_dbg) DRNMF_CUDA(cudaMemsetAsync(dbg_dev, 0, 16 * 8 * sizeof(long long), st));
+  static long long* trace_dev = nullptr;
+  const char* tr = want_dbg ? getenv("DRNMF_REC_TRACE") : nullptr;      // "lo:hi" = items of the observed CTA to trace
+  a.trace = nullptr; a.trace_lo = a.trace_hi = 0;
+  if (tr) {
+    if (!trace_dev) DRNMF_CUDA(cudaMalloc(&trace_dev, (8 + 8 * RT_TRC_PER_ROLE * 2) * sizeof(long long)));
+    DRNMF_CUDA(cudaMemsetAsync(trace_dev, 0, (8 + 8 * RT_TRC_PER_ROLE * 2) * sizeof(long long), st));
+    a.trace = trace_dev;
+    a.trace_lo = atoi(tr);
+    a.trace_hi = strchr(tr, ':') ? atoi(strchr(tr, ':') + 1) : a.trace_lo + 2;
+  }
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = h->u0_d - h->u0_o; a.u0_off = h->u0_o; a.uk_dmo = h->uk_d - h->uk_o; a.uk_off = h->uk_o;
   DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
-  a.ST = h->ST_hi;
   CUtensorMap tH_hi, tH_lo, tW;
   int rc;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
-  if ((rc = make_tmap_2d(&tH_hi, w.hb_hi, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
-  if ((rc = make_tmap_2d(&tH_lo, w.hb_lo, Rp, 2ull * w.Bp, Rp, 32, p.NB))) return rc;
+  if ((rc = make_h_maps(&tH_hi, &tH_lo, w, Rp, p.NB, &a.h3d))) return rc;
   rc = launch_rec(p, false, tH_hi, tH_lo, tW, st);
   if (rc == DRNMF_OK && want_dbg) {
     long long d[16 * 8];
@@ -1364,7 +1392,8 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
     DRNMF_CUDA(cudaStreamSynchronize(st));
     const char* names[16] = {"w-tma", "h-loader", "mma", "publisher", "pusher", "", "", "", "owner", "", "", "", "w-loader", "", "", ""};
     const long long items = (long long)T * (K - 1) * p.n_tiles;
-    fprintf(stderr, "[libdrnmf] recurrence debug (CTA 0,0; cycles per MMA item, %lld items): NB=%d KS=%d tiles=%d\n", items, p.NB, p.KS, p.n_tiles);
+    fprintf(stderr, "[libdrnmf] recurrence debug (CTA 0,0; cycles per MMA item, %lld items): NB=%d KS=%d G=%d tiles/group=%d NSC=%d W%d H%d R%d\n",
+            items, p.NB, p.KS, p.G, p.n_tiles, p.NSC, p.WST, p.HST, p.RST);
     for (int wv = 0; wv < 16; ++wv) {
       if (!names[wv][0]) continue;
       const long long* q = d + wv * 8;
@@ -1372,6 +1401,25 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
               (double)q[0] / items, (double)q[1] / items, (double)q[2] / items, (double)q[3] / items, (double)q[4] / items,
               (double)q[5] / items, (double)q[6] / items, (double)q[7] / items);
     }
+  }
+  if (rc == DRNMF_OK && a.trace) {
+    static long long tb[8 + 8 * RT_TRC_PER_ROLE * 2];
+    DRNMF_CUDA(cudaMemcpyAsync(tb, trace_dev, sizeof(tb), cudaMemcpyDeviceToHost, st));
+    DRNMF_CUDA(cudaStreamSynchronize(st));
+    struct Ev { long long t; int role, ev, item; };
+    static Ev evs[8 * RT_TRC_PER_ROLE];
+    int n = 0;
+    for (int r = 0; r < 8; ++r)
+      for (int e = 0; e < tb[r] && e < RT_TRC_PER_ROLE; ++e) {
+        const long long tag = tb[8 + (r * RT_TRC_PER_ROLE + e) * 2];
+        evs[n++] = Ev{tb[8 + (r * RT_TRC_PER_ROLE + e) * 2 + 1], r, (int)(tag >> 16), (int)(tag & 0xFFFF)};
+      }
+    for (int i = 1; i < n; ++i)
+      for (int j = i; j > 0 && evs[j].t < evs[j - 1].t; --j) { Ev x = evs[j]; evs[j] = evs[j - 1]; evs[j - 1] = x; }
+    static const char* rn[8] = {"w-tma", "h-load", "mma", "pub", "pusher", "owner", "w-load", "?"};
+    fprintf(stderr, "[libdrnmf] trace of CTA (0,%d), items [%d,%d): role event item +cycles\n", a.dbg_m, a.trace_lo, a.trace_hi);
+    for (int i = 0; i < n; ++i)
+      fprintf(stderr, "  %-7s ev%-3d item %-5d +%lld\n", rn[evs[i].role], evs[i].ev, evs[i].item, evs[i].t - evs[0].t);
   }
   return rc;
 }

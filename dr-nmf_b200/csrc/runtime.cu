@@ -56,4 +56,29 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t cols, uint64_t ro
   return DRNMF_OK;
 }
 
+// fp32 row-major matrix (rows x cols, cols a multiple of 32) seen as [slab = cols/32][row][32 columns]: one TMA box of
+// (32 columns x box_rows x box_slabs) lands in shared memory as box_slabs consecutive K-major tiles of box_rows x 128
+// bytes, each in the 128B-swizzle layout the tcgen05 descriptors expect (a 2-D map moves one such tile per instruction).
+int make_tmap_slabs(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
+                    uint32_t box_rows, uint32_t box_slabs) {
+  auto enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return DRNMF_ERR_CUDA; }
+  DRNMF_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  DRNMF_CHECK((row_stride_elems * sizeof(float)) % 16 == 0 && cols % 32 == 0, "TMA slab map needs cols %% 32 == 0");
+  DRNMF_CHECK(box_rows <= 256 && box_slabs >= 1 && box_slabs <= 256, "TMA box out of range");
+  cuuint64_t gdim[3] = {32, rows, cols / 32};
+  cuuint64_t gstr[2] = {row_stride_elems * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, box_rows, box_slabs};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (slabs) failed with CUresult %d (cols=%llu rows=%llu stride=%llu box=32x%ux%u)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_elems, box_rows, box_slabs);
+    return DRNMF_ERR_CUDA;
+  }
+  return DRNMF_OK;
+}
+
 }  // namespace drnmf

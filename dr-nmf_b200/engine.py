@@ -194,7 +194,7 @@ class DrnmfEngine:
         impl 'tcgen05' | 'simt' + tiling; n_tiles = batch tiles per group, groups = batch groups on disjoint SMs."""
         c = (C.c_int * 10)()
         _lib.check(self.lib.drnmf_recurrent_config2(self.h, 1 if backward else 0, c))
-        keys = ("NB", "KS", "MT", "ATOMS", "n_tiles", "WST", "HST", "RST", "groups")
+        keys = ("NB", "KS", "MT", "NSC", "n_tiles", "WST", "HST", "RST", "groups")
         d = {"impl": "tcgen05" if c[0] == 0 else "simt"}
         d.update({k: int(c[1 + i]) for i, k in enumerate(keys)})
         return d

@@ -84,8 +84,8 @@ DRNMF_API int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float
 DRNMF_API int drnmf_stage_times(drnmf_handle* h, float* ms4);
 
 /* How the recurrence of the last drnmf_forward ran: cfg9[0] = 0 persistent tcgen05 kernel / 1 SIMT per-step kernels;
- * cfg9[1..8] = batch tile NB, K-splits (cluster size) KS, M-tiles MT, weight atoms per slice, batch tiles,
- * weight / hidden / reduction ring depths of the persistent kernel. */
+ * cfg9[1..8] = batch tile NB, K-splits (cluster size) KS, M-tiles MT, 64-atom sub-chunks per K-slice, batch tiles per
+ * group, weight / hidden / reduction ring depths of the persistent kernel. */
 DRNMF_API int drnmf_recurrent_config(const drnmf_handle* h, int* cfg9);
 
 /* Extended form: which = 0 the recurrence of the last drnmf_forward, 1 the backward chain of the last

@@ -17,7 +17,8 @@ fl_rec = 2.0 * R * R * (K - 1)
 
 
 def setenv(**kw):
-    for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS", "DRNMF_REC_VERBOSE"):
+    for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS", "DRNMF_REC_VERBOSE", "DRNMF_REC_TRACE",
+              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         if v is not None:
@@ -42,8 +43,8 @@ def run(B, Tn, reps=3, **kw):
     cfg = eng.recurrent_config()
     steps = Tn * (K - 1)
     tf = fl_rec * B * Tn / (best / 1e3) / 1e12
-    print("B=%4d T=%3d req=%-32s plan=NB%d G%d tiles%d W%d H%d R%d | rec %8.3f ms  %6.2f us/step  %7.1f kframes/s  %6.1f TF/s useful" % (
-        B, Tn, kw, cfg["NB"], cfg["groups"], cfg["n_tiles"], cfg["WST"], cfg["HST"], cfg["RST"], best, 1e3 * best / steps,
+    print("B=%4d T=%3d req=%-32s plan=KS%d NB%d G%d tiles%d W%d H%d R%d | rec %8.3f ms  %6.2f us/step  %7.1f kframes/s  %6.1f TF/s useful" % (
+        B, Tn, kw, cfg["KS"], cfg["NB"], cfg["groups"], cfg["n_tiles"], cfg["WST"], cfg["HST"], cfg["RST"], best, 1e3 * best / steps,
         B * Tn / best, tf), flush=True)
     return H
 
@@ -64,24 +65,31 @@ def sweep(B, Tn, configs):
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "b64"):
-    sweep(64, T, [dict(NB=64, G=1), dict(NB=32, G=2), dict(NB=32, G=1), dict(NB=32, G=1, PUB="direct"),
-                  dict(NB=16, G=2), dict(NB=16, G=2, PUB="direct"), dict(NB=16, G=1), dict(NB=16, G=1, PUB="direct"), dict()])
+    sweep(64, T, [dict(VERBOSE=1), dict(KS=4, NB=16, G=4), dict(KS=4, NB=32, G=2), dict(KS=4, NB=64, G=1), dict(KS=4, NB=16, G=2),
+                  dict(KS=8, NB=64, G=1), dict(KS=8, NB=32, G=1), dict(KS=2, NB=16, G=4), dict(KS=4, NB=16, G=4, PUB="thread")])
 if which in ("all", "b32"):
-    sweep(32, T, [dict(NB=32, G=1), dict(NB=16, G=2), dict(NB=16, G=1), dict(NB=16, G=1, PUB="direct"), dict()])
+    sweep(32, T, [dict(), dict(KS=4, NB=16, G=2), dict(KS=4, NB=32, G=1), dict(KS=8, NB=32, G=1)])
 if which in ("all", "thr"):
-    sweep(512, 48, [dict(NB=64, G=1), dict(NB=64, G=2), dict(NB=64, G=2, PUB="direct"), dict(NB=32, G=2), dict()])
-    sweep(2048, 12, [dict(NB=64, G=1), dict(NB=64, G=2)])
-    sweep(128, 96, [dict(NB=64, G=1), dict(NB=64, G=2), dict(NB=32, G=2), dict(NB=32, G=2, PUB="direct")])
-if which in ("ks4",):
-    sweep(64, T, [dict(NB=64, G=1, VERBOSE=1), dict(KS=4, NB=64, G=1, VERBOSE=1), dict(KS=4, NB=32, G=2), dict(KS=4, NB=16, G=4),
-                  dict(KS=4, NB=16, G=2), dict(KS=16, NB=64, G=1, VERBOSE=1), dict(KS=2, NB=16, G=4, VERBOSE=1)])
-    sweep(512, 24, [dict(NB=64, G=1), dict(KS=4, NB=64, G=4), dict(KS=4, NB=64, G=2), dict(KS=4, NB=32, G=4)])
+    sweep(512, 48, [dict(VERBOSE=1), dict(KS=4, NB=64, G=4), dict(KS=4, NB=32, G=4), dict(KS=4, NB=64, G=4, PUB="direct"),
+                    dict(KS=4, NB=32, G=4, PUB="direct"), dict(KS=8, NB=64, G=1), dict(KS=2, NB=32, G=8)])
+    sweep(2048, 12, [dict(), dict(KS=4, NB=32, G=4), dict(KS=8, NB=64, G=1)])
+    sweep(128, 96, [dict(), dict(KS=4, NB=32, G=4), dict(KS=4, NB=64, G=2), dict(KS=8, NB=64, G=1)])
+    sweep(256, 96, [dict(), dict(KS=4, NB=32, G=4)])
 if which in ("all", "dbg"):
     print("---- per-role cycle counters (stderr) ----", flush=True)
-    for kw in (dict(NB=64, G=1), dict(NB=32, G=2), dict(NB=32, G=1), dict(NB=16, G=2)):
+    for kw in (dict(), dict(KS=4, NB=32, G=2), dict(KS=8, NB=64, G=1)):
         sys.stderr.write("\n## B=64 %s\n" % kw); sys.stderr.flush()
         run(64, 40, reps=1, DEBUG=1, **kw)
-    for kw in (dict(NB=64, G=1), dict(NB=64, G=2)):
+    for kw in (dict(), dict(KS=4, NB=32, G=4), dict(KS=8, NB=64, G=1)):
         sys.stderr.write("\n## B=512 %s\n" % kw); sys.stderr.flush()
         run(512, 12, reps=1, DEBUG=1, **kw)
+if which in ("trace2",):
+    for B, Tn, nt, kw in ((64, 40, 1, dict(KS=8, NB=64, G=1)), (64, 40, 1, dict())):
+        sys.stderr.write("\n## B=%d %s\n" % (B, kw)); sys.stderr.flush()
+        run(B, Tn, reps=1, DEBUG=1, TRACE="%d:%d" % (200 * nt, 200 * nt + 2 * nt), **kw)
+if which in ("trace",):
+    for B, Tn, nt, kw in ((64, 40, 1, dict()), (64, 40, 2, dict(KS=8, NB=32, G=1)), (64, 40, 2, dict(KS=8, NB=32, G=1, PUB="direct")),
+                          (64, 40, 1, dict(KS=8, NB=64, G=1)), (512, 12, 2, dict(PUB="direct")), (2048, 6, 8, dict(PUB="direct"))):
+        sys.stderr.write("\n## B=%d %s\n" % (B, kw)); sys.stderr.flush()
+        run(B, Tn, reps=1, DEBUG=1, TRACE="%d:%d" % (200 * nt, 200 * nt + 2 * nt), **kw)
 setenv()

@@ -52,7 +52,7 @@ def test_configs1_exact_forward_vs_fp64_oracle():
     torch.cuda.synchronize()
     cfg = eng.recurrent_config()
     # bench.py runs the library's default plan for this shape and prints it under config.recurrence: same plan here
-    assert cfg["impl"] == "tcgen05" and cfg["MT"] == 8 and cfg["KS"] == 8, cfg
+    assert cfg["impl"] == "tcgen05" and cfg["MT"] == 8, cfg
     assert cfg["groups"] * cfg["n_tiles"] * cfg["NB"] == 64, cfg
     print("configs[1] plan:", cfg)
     Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
