@@ -73,6 +73,7 @@ struct RecArgs {
   long long* trace;                          // optional event trace of CTA (0,0): [0] = count, then (tag, clock) pairs
   int trace_lo, trace_hi;                    // items [lo, hi) of the observed CTA are traced
   int h3d;                                   // hidden-state tensor maps are 3-D slab maps (two 32-atom tiles per TMA instruction)
+  int ll;                                    // latency mode: self-validating hidden-state exchange (see the consumer warp)
   // shapes
   int B, Bp, T, K, R, Rp;
   int MT, KS, RO, KSLICE, n_tiles;           // n_tiles = batch tiles per batch group (grid.z groups run on disjoint SMs)
@@ -138,6 +139,18 @@ constexpr int RT_TRC_PER_ROLE = 256;
     }                                                                                               \
   } while (0)
 
+// Latency mode ("LL" exchange, one batch tile per group): the new hidden rows carry their own validity.  Every fp32
+// the owners write into the ping-pong buffer has its mantissa LSB forced to the parity of the write count of that
+// slot (a <= 1 ulp perturbation that is part of the value from then on: the identity path re-reads the same bits), so a
+// consumer needs no flag, no release fence on the producer side and no second round trip: it loads the slice, checks the
+// LSB of every element against the parity it expects and repeats until all match.  Writes to slot (k & 1) happen at
+// k = 0 .. K-2 of every frame: K/2 per frame to slot 0, (K-1)/2 to slot 1.
+__device__ __forceinline__ uint32_t ll_tag(int frame, int k, int K) {
+  const int per_frame = (k & 1) ? (K - 1) / 2 : K / 2;
+  return (uint32_t)(frame * per_frame + (k >> 1) + 1) & 1u;      // +1: the first write differs from the zero-filled buffer
+}
+__device__ __forceinline__ float ll_mark(float x, uint32_t tag) { return __uint_as_float((__float_as_uint(x) & ~1u) | tag); }
+
 // ring position without runtime division (a 64-bit % and / per use cost ~100 cycles each on the critical path)
 struct RtRing {
   int idx; uint32_t ph;
@@ -149,6 +162,125 @@ struct RtRing {
 __device__ __forceinline__ uint32_t sched_at(const RecSched& sc, int i, int n, int p) {
   const int cls = (i == 0 ? 0 : ((i & 1) ? 1 : 2)) + (i == n - 1 ? 3 : 0);
   return sc.e[cls][p];
+}
+
+// Latency-mode consumer (warps 1 and 3, see ll_tag): warp `ci` serves the positions p = ci, ci + 2, ... of every step.
+// Per 64-atom sub-chunk: NB rows x 16 float4; lane l takes float4 (l & 15) of rows (l >> 4) + 2 j.  The raw values go to
+// the "hi" tiles, their tf32 remainders to the "lo" tiles, both in the 128B-swizzle layout of the MMA descriptors.  With
+// NB = 16 the loads of the warp's next position are issued before the current one is stored (two register sets).
+template <int NB>
+__device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sch, RecBars* bars, uint8_t* smem, int ci, int s,
+                                            int lane, bool dbg_on, long long (&dbg_acc)[7], int& trc) {
+  constexpr int NLD = NB / 2;                    // float4 per lane and sub-chunk
+  constexpr bool PREFETCH = (NB == 16);
+  constexpr uint32_t HB = NB * 128;
+  volatile int* err = a.dev_error;
+  const int K = a.K, T = a.T, Rp = a.Rp, NSC = a.NSC;
+  const int q = lane & 15, r0 = lane >> 4;       // float4 index inside the sub-chunk, first row
+  RtRing hr;
+  long long item = 0;
+  bool okh = true;
+  // Polling is light: a consumer that spins on the whole slice keeps eight L2 readers on every line the owners are about
+  // to write (measured: the stores queue behind the reads and the step stretches by 30 %).  The warp spins on the first
+  // row of its sub-chunk only (16 lanes x 16 bytes) and pulls the full tile once that row is valid; every element is
+  // still validated, stragglers are re-loaded.
+  float4 v[NLD], w[NLD];
+  const int n_tiles = a.n_tiles;
+  auto issue = [&](float4 (&dst)[NLD], int slot, int i, int p) {
+    const int sc = (int)(sched_at(sch, i, n_tiles, p) & 15u);
+    const bool two = (a.KSLICE - sc * 64 >= 64);
+    if (two || q < 8) {
+      const float* src = a.hb_hi + ((size_t)slot * a.Bp + i * NB + r0) * Rp + s * a.KSLICE + sc * 64 + 4 * q;
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) dst[j] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(2 * j) * Rp));
+    }
+  };
+  auto valid = [&](const float4 (&x)[NLD], int i, int p, uint32_t tag4) {
+    const int sc = (int)(sched_at(sch, i, n_tiles, p) & 15u);
+    const bool two = (a.KSLICE - sc * 64 >= 64);
+    bool good = true;
+    if (two || q < 8) {
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const uint32_t bits = (__float_as_uint(x[j].x) & 1u) | ((__float_as_uint(x[j].y) & 1u) << 8) |
+                              ((__float_as_uint(x[j].z) & 1u) << 16) | ((__float_as_uint(x[j].w) & 1u) << 24);
+        good = good && (bits == tag4);
+      }
+    }
+    return __all_sync(0xffffffffu, good);
+  };
+  for (int t = 0; t < T && okh; ++t)
+    for (int k = 1; k < K && okh; ++k)
+     for (int i = 0; i < n_tiles && okh; ++i, ++item) {
+      const uint32_t tag4 = ll_tag(t, k - 1, K) * 0x01010101u;
+      const int slot = (k - 1) & 1;
+      bool have = false;                           // v holds (possibly stale) loads of the current position
+      for (int p = 0; p < NSC && okh; ++p, hr.next(a.HST)) {
+        if ((p & 1) != ci) continue;
+        const int sc = (int)(sched_at(sch, i, n_tiles, p) & 15u);
+        const bool two = (a.KSLICE - sc * 64 >= 64);
+        const long long _t0 = clock64();
+        unsigned spins = 0;
+        if (!have) {
+          const float* sp = a.hb_hi + ((size_t)slot * a.Bp + i * NB) * Rp + s * a.KSLICE + sc * 64 + 4 * q;
+          for (;;) {                                  // sentinel: row 0 of the sub-chunk
+            bool good = true;
+            if (r0 == 0 && (two || q < 8)) {
+              const float4 x = __ldcg(reinterpret_cast<const float4*>(sp));
+              const uint32_t bits = (__float_as_uint(x.x) & 1u) | ((__float_as_uint(x.y) & 1u) << 8) |
+                                    ((__float_as_uint(x.z) & 1u) << 16) | ((__float_as_uint(x.w) & 1u) << 24);
+              good = bits == tag4;
+            }
+            if (__all_sync(0xffffffffu, good)) break;
+            if ((++spins & 0x3F) == 0 && (clock64() - _t0 > RT_WATCHDOG || *err)) { okh = false; break; }
+          }
+          if (okh) issue(v, slot, i, p);
+        }
+        while (okh && !valid(v, i, p, tag4)) {
+          if ((++spins & 0x3F) == 0 && (clock64() - _t0 > RT_WATCHDOG || *err)) { okh = false; break; }
+          issue(v, slot, i, p);
+        }
+        okh = __all_sync(0xffffffffu, okh);
+        if (!okh) { if (lane == 0) atomicCAS(a.dev_error, 0, 203); break; }
+        if (dbg_on) dbg_acc[1] += clock64() - _t0;
+        if constexpr (PREFETCH) { if (p + 2 < NSC) issue(w, slot, i, p + 2); }     // in flight while this position is stored
+        const int hs = hr.idx;
+        if (lane == 0) {
+          okh = mbar_wait(&bars->h_empty[hs], hr.ph ^ 1u, err, RT_WATCHDOG);
+          if (!okh) atomicCAS(a.dev_error, 0, 202);
+        }
+        okh = __all_sync(0xffffffffu, okh);
+        if (!okh) break;
+        if (two || q < 8) {
+          const uint32_t st0 = smem_u32(smem + a.off_h + hs * a.h_stage_bytes) + (uint32_t)(q >> 3) * HB;   // slab of this float4
+#pragma unroll
+          for (int j = 0; j < NLD; ++j) {
+            const int r = r0 + 2 * j;
+            const uint32_t ad = st0 + (uint32_t)r * 128u + (uint32_t)(((q & 7) ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "f"(v[j].x), "f"(v[j].y), "f"(v[j].z), "f"(v[j].w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ad + 2 * HB), "f"(tf32_lo(v[j].x)), "f"(tf32_lo(v[j].y)),
+                         "f"(tf32_lo(v[j].z)), "f"(tf32_lo(v[j].w)) : "memory");
+          }
+        }
+        fence_proxy_async_smem();                // generic-proxy STS -> async-proxy reads of the MMA
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bars->h_full[hs]);
+          if (dbg_on && a.trace && item >= a.trace_lo && item < a.trace_hi && trc < RT_TRC_PER_ROLE) {
+            long long* _p = a.trace + 8 + (1 * RT_TRC_PER_ROLE + trc) * 2;
+            _p[0] = ((long long)(10 + p) << 16) | (item & 0xFFFF); _p[1] = clock64(); ++trc; a.trace[1] = trc;
+          }
+        }
+        have = false;
+        if constexpr (PREFETCH) {
+          if (p + 2 < NSC) {
+#pragma unroll
+            for (int j = 0; j < NLD; ++j) v[j] = w[j];
+            have = true;
+          }
+        }
+      }
+    }
 }
 
 template <int NB, bool BWD, int CB>
@@ -250,7 +382,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     // Flags are acquired lazily, right before the first sub-chunk that needs a producer M-tile (the M-tiles of a step
     // finish up to ~2k cycles apart): the lanes poll the (at most two) M-tiles a sub-chunk overlaps in parallel - a
     // satisfied poll still costs an L2 round trip -, then lane 0 issues one slab TMA per hi / lo.
-    {
+    if (a.ll) {
+      ll_consumer<NB>(a, sch, bars, smem, 0, s, lane, dbg_on, dbg_acc, trc);
+    } else {
       const int m_lo = (s * a.KSLICE) >> 7;
       RtRing hr;
       long long item = 0;
@@ -444,7 +578,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     // ================= publisher: one gpu-scope release per (step, tile) after the owners' stores =================
     // The owner threads only arrive on pub_full (release.cta); this thread acquires it, issues the single cumulative
     // gpu-scope fence and bumps flag[tile][m], so the owners never stall on a memory fence.
-    if (lane == 0) {
+    if (a.ll) {
+      ll_consumer<NB>(a, sch, bars, smem, 1, s, lane, false, dbg_acc, trc);
+    } else if (lane == 0) {
       const long long n_items = (a.pub_unit == 1) ? (long long)T * K * n_tiles : 0;   // direct mode: the owners publish
       long long j = 0;
       while (j < n_items) {
@@ -555,7 +691,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       if (k == 0) {
         // ---- frame start: leak[b] = sum_j state[b][j] from the published partial sums of the previous frame ----
         if (t > 0) {
-          const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(t * K);
+          const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(a.ll ? t : t * K);   // LL: flags only count frames
           if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) atomicCAS(a.dev_error, 0, 209);
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
@@ -647,8 +783,12 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           }
           if (!last) {
             const size_t o2 = ((size_t)(k & 1) * a.Bp + b) * Rp + rowq;
-            __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(g[0], g[1], g[2], g[3]));
-            __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(g[0]), tf32_lo(g[1]), tf32_lo(g[2]), tf32_lo(g[3])));
+            if (a.ll) {   // only the exchanged copy carries the tag (a tagged zero is a denormal: it must not reach the
+                          // stored activations, whose sign the backward pass tests)
+              const uint32_t tg = ll_tag(t, k, K);
+              __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(ll_mark(g[0], tg), ll_mark(g[1], tg), ll_mark(g[2], tg), ll_mark(g[3], tg)));
+            } else __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(g[0], g[1], g[2], g[3]));
+            if (!a.ll) __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(g[0]), tf32_lo(g[1]), tf32_lo(g[2]), tf32_lo(g[3])));
           } else if (b < a.B) {
             // Keras masked scan: out_t = m ? g : out_{t-1} (zeros before the first step); state = m ? g : state
             const size_t bt = (size_t)b * T + t;
@@ -717,7 +857,8 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         // critical path instead of release.cta arrive + the publisher's gpu fence back to back
         __syncwarp();
         if (otid == 0 && k > 0) RT_TRACE(5, 3, it - 1);
-        if (lane == 0) RT_TIMED(1, flag_add_release(a.flags + i * a.MT + m, 1u));
+        // LL exchange: the hidden rows validate themselves; only the frame end (state / partial row sums) is flagged
+        if (lane == 0 && (!a.ll || last)) RT_TIMED(1, flag_add_release(a.flags + i * a.MT + m, 1u));
         if (otid == 0 && k > 0) RT_TRACE(5, 4, it - 1);
       } else {
         // ---- hand the item to the publisher (release.cta arrive; the publisher's fence makes it gpu-visible) ----
@@ -838,7 +979,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       float d[4][CB];                                         // [row e][batch bi]
       if (u == 0) {
         if (fi > 0) {
-          const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(fi * K);
+          const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(a.ll ? fi : fi * K);
           if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) atomicCAS(a.dev_error, 0, 219);
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
@@ -954,9 +1095,10 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const int b = i * NB + col0b + bi;
           if (la > 0) {                                        // operand of the next product (pre-scaled for vector alph)
             const size_t o2 = ((size_t)(u & 1) * a.Bp + b) * Rp + rowq;
-            const float o0v = d[0][bi] * a_pre.x, o1v = d[1][bi] * a_pre.y, o2v = d[2][bi] * a_pre.z, o3v = d[3][bi] * a_pre.w;
+            float o0v = d[0][bi] * a_pre.x, o1v = d[1][bi] * a_pre.y, o2v = d[2][bi] * a_pre.z, o3v = d[3][bi] * a_pre.w;
+            if (a.ll) { const uint32_t tg = ll_tag(fi, u, K); o0v = ll_mark(o0v, tg); o1v = ll_mark(o1v, tg); o2v = ll_mark(o2v, tg); o3v = ll_mark(o3v, tg); }
             __stcg(reinterpret_cast<float4*>(a.hb_hi + o2), make_float4(o0v, o1v, o2v, o3v));
-            __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(o0v), tf32_lo(o1v), tf32_lo(o2v), tf32_lo(o3v)));
+            if (!a.ll) __stcg(reinterpret_cast<float4*>(a.hb_lo + o2), make_float4(tf32_lo(o0v), tf32_lo(o1v), tf32_lo(o2v), tf32_lo(o3v)));
           } else if (b < a.B && mvt[bi] != 0.f) {
             // delta^0: start of the new state gradient  G = (d0-o0) delta^0 (+ rank-1 terms added at the next frame start)
             __stcg(reinterpret_cast<float4*>(a.G + (size_t)b * Rp + rowq),
@@ -981,7 +1123,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       }
       if (a.pub_unit != 1) {
         __syncwarp();
-        if (lane == 0) flag_add_release(a.flags + i * a.MT + m, 1u);
+        if (lane == 0 && (!a.ll || la == 0 || K == 1)) flag_add_release(a.flags + i * a.MT + m, 1u);
       } else {
         const int ps_ = (int)(j % RT_PST);
         if (!mbar_wait(&bars->pub_empty[ps_], (uint32_t)(((j / RT_PST) & 1) ^ 1), err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 222);
@@ -1129,10 +1271,10 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
   if (Rp % (KS * 32) != 0 || p.MT * KS * p.G > h->num_sms) { p.why = "no (M-tile x K-split) grid fits the device"; return p; }
   p.KS = KS; p.RO = 128 / KS; p.KSLICE = Rp / KS; p.NSC = (p.KSLICE + 63) / 64;
   if (p.NSC > RT_MAXSC) { p.why = "K-slice wider than 1024 atoms"; return p; }
-  {   // who publishes: every owner warp with its own red.release (default for one tile per group) or a publisher thread
+  {   // who publishes: every owner warp with its own red.release (default: measured faster at 1, 2 and 8 tiles per
+      // group) or a publisher thread that batches the gpu-scope fences (DRNMF_REC_PUB=thread)
     const char* e = getenv("DRNMF_REC_PUB");
-    const bool direct = e ? !strcmp(e, "direct") : (p.n_tiles == 1);
-    p.a.pub_unit = direct ? 4 : 1;
+    p.a.pub_unit = (e && !strcmp(e, "thread")) ? 1 : 4;
   }
   if (p.RO * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
   p.CB = p.RO * p.NB >= 2048 ? 4 : (p.RO * p.NB >= 1024 ? 2 : 1);     // batch columns per owner thread (4 rows x CB)
@@ -1250,11 +1392,16 @@ static int launch_rec(const RecPlan& p, bool bwd, const CUtensorMap& tH_hi, cons
   return DRNMF_OK;
 }
 
-// Candidate tilings.  K-splits (= cluster size) of 4 first: a B200 hosts 33 clusters of 4 but only 15 of 8, and a
-// 128 x (Rp/4) block per CTA does twice the tensor work per exchanged partial tile.  Batch groups: when the device can
-// host G x MT clusters the batch is cut into G groups on disjoint SMs (R = 1000: 4 groups x 32 CTAs).  The batch tile
-// is the widest one that still leaves a tile for every group (B = 64 -> four groups of one 16-utterance tile; B >= 256
-// -> 64-column tiles pipelined through the same weights).
+// Candidate tilings (measured on B200, R = 1000, K = 25; profiles/r2_recurrence_sweep.md):
+//   * latency regime (B <= 64 utterances): every step is a chain of ~8 dependent hops (TMA, MMA, commit, DSMEM, reduce,
+//     release, flag, TMA) of 0.5 - 2k cycles each, insensitive to the bytes moved.  K-splits of 8 (cluster of 8, one
+//     batch group: only 15 such clusters are co-resident) keep the per-CTA weight stream and MMA burst shortest:
+//     B <= 32 runs one 32-column tile with the self-validating exchange (4.9 us/step), B <= 64 pipelines two 32-column
+//     tiles through the same weights (6.1 us/step for both).
+//   * throughput regime (B > 64): K-splits of 4 (33 co-resident clusters of 4) and batch groups on disjoint SMs
+//     (R = 1000: 4 groups x 32 CTAs = 128 SMs); a 128 x (Rp/4) block per CTA does twice the tensor work per exchanged
+//     partial tile.  The batch tile is the widest one that still leaves a tile for every group.
+// When the preferred cluster size does not fit (large R: MT clusters of 8 are not co-resident) the next one is tried.
 static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
   RecPlan p{};
   p.ok = false; p.why = "no candidate tiling";
@@ -1262,9 +1409,10 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
   const char* env_nb = getenv("DRNMF_REC_NB");
   const char* env_g = getenv("DRNMF_REC_G");
   const bool verbose = getenv("DRNMF_REC_VERBOSE") != nullptr;
-  static const int ks_order[5] = {4, 8, 2, 1, 16};
+  const bool latency = B <= 64;
+  static const int ks_lat[5] = {8, 4, 2, 1, 16}, ks_thr[5] = {4, 8, 2, 1, 16};
   for (int kq = 0; kq < 5 && !p.ok; ++kq) {
-    const int KS = ks_order[kq];
+    const int KS = latency ? ks_lat[kq] : ks_thr[kq];
     if (env_ks && atoi(env_ks) != KS) continue;
     // co-resident clusters for this cluster size (probe with the smallest tile: shared memory is at the limit anyway)
     RecPlan probe = plan_recurrent(h, B, KS, 16, 1);
@@ -1273,12 +1421,12 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
     rec_max_clusters(probe, bwd, &mc);
     if (verbose) fprintf(stderr, "[libdrnmf] plan probe KS=%d MT=%d smem=%zu: %d co-resident clusters\n", KS, probe.MT, probe.smem, mc);
     if (mc < probe.MT) { p.why = "not enough co-resident clusters for any tiling"; continue; }
-    const int g_max = env_g ? atoi(env_g) : mc / probe.MT;
+    const int g_max = env_g ? atoi(env_g) : (latency ? 1 : mc / probe.MT);
     for (int NB = 64; NB >= 16 && !p.ok; NB >>= 1) {
       if (env_nb && atoi(env_nb) != NB) continue;
-      // default: the widest tile that still gives every group a tile (NB = 16 is the floor)
-      if (!env_nb && NB > 16 && (B + NB - 1) / NB < g_max && B > NB / 2) continue;
-      if (!env_nb && ((NB == 64 && B <= 32) || (NB == 32 && B <= 16))) continue;
+      if (!env_nb && latency && ((NB == 64) || (NB == 32 && B <= 16))) continue;       // 32-column tiles (16 for B <= 16)
+      // throughput: the widest tile that still gives every group a tile (NB = 16 is the floor)
+      if (!env_nb && !latency && NB > 16 && (B + NB - 1) / NB < g_max) continue;
       for (int G = g_max; G >= 1 && !p.ok; --G) {
         RecPlan c = plan_recurrent(h, B, KS, NB, G);
         if (!c.ok) { p.why = c.why; continue; }
@@ -1337,6 +1485,10 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = 0.f; a.u0_off = 0.f; a.uk_dmo = 0.f; a.uk_off = 0.f;
   DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
+  // latency mode (one batch tile per group, NB <= 32): self-validating exchange; the ping-pong buffer starts zeroed
+  // (measured: it wins with one or two groups - 5.3 -> 4.9 us/step at B = 32 - and loses when 128 CTAs pull through LDG)
+  a.ll = (p.n_tiles <= (getenv("DRNMF_REC_LLT") ? atoi(getenv("DRNMF_REC_LLT")) : 1) && p.NB <= 32 && p.G <= 2 && a.pub_unit == 4 && !(getenv("DRNMF_REC_LL") && !strcmp(getenv("DRNMF_REC_LL"), "0"))) ? 1 : 0;
+  if (a.ll) DRNMF_CUDA(cudaMemsetAsync(w.hb_hi, 0, sizeof(float) * 2 * (size_t)w.Bp * Rp, st));
   CUtensorMap tH_hi, tH_lo, tW;
   int rc;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
@@ -1381,6 +1533,10 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
   a.u0_dmo = h->u0_d - h->u0_o; a.u0_off = h->u0_o; a.uk_dmo = h->uk_d - h->uk_o; a.uk_off = h->uk_o;
   DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
+  // latency mode (one batch tile per group, NB <= 32): self-validating exchange; the ping-pong buffer starts zeroed
+  // (measured: it wins with one or two groups - 5.3 -> 4.9 us/step at B = 32 - and loses when 128 CTAs pull through LDG)
+  a.ll = (p.n_tiles <= (getenv("DRNMF_REC_LLT") ? atoi(getenv("DRNMF_REC_LLT")) : 1) && p.NB <= 32 && p.G <= 2 && a.pub_unit == 4 && !(getenv("DRNMF_REC_LL") && !strcmp(getenv("DRNMF_REC_LL"), "0"))) ? 1 : 0;
+  if (a.ll) DRNMF_CUDA(cudaMemsetAsync(w.hb_hi, 0, sizeof(float) * 2 * (size_t)w.Bp * Rp, st));
   CUtensorMap tH_hi, tH_lo, tW;
   int rc;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;

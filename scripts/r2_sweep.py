@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from drnmf_b200 import engine, synth
 
-F, R, K = 513, int(os.environ.get("SWEEP_R", "1000")), 25
+F, R, K = 513, int(os.environ.get("SWEEP_R", "1000")), int(os.environ.get("SWEEP_K", "25"))
 T = int(os.environ.get("SWEEP_T", "193"))
 p = synth.model_params(F, R, K)
 p["log_U1"], p["log_Uk"] = synth.structured_u_init()
@@ -18,7 +18,7 @@ fl_rec = 2.0 * R * R * (K - 1)
 
 def setenv(**kw):
     for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS", "DRNMF_REC_VERBOSE", "DRNMF_REC_TRACE",
-              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D"):
+              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D", "DRNMF_REC_LLT", "DRNMF_REC_LL"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         if v is not None:
@@ -83,6 +83,24 @@ if which in ("all", "dbg"):
     for kw in (dict(), dict(KS=4, NB=32, G=4), dict(KS=8, NB=64, G=1)):
         sys.stderr.write("\n## B=512 %s\n" % kw); sys.stderr.flush()
         run(512, 12, reps=1, DEBUG=1, **kw)
+if which in ("final",):
+    sweep(64, T, [dict(), dict(KS=4, NB=16, G=4), dict(H2D=1)])
+    sweep(32, T, [dict(), dict(LL=0)])
+    sweep(16, T, [dict(), dict(LL=0)])
+    sweep(48, T, [dict()])
+    sweep(128, 96, [dict(), dict(KS=8, NB=64, G=1)])
+    sweep(256, 96, [dict()])
+    sweep(512, 48, [dict(), dict(PUB="thread")])
+    sweep(2048, 12, [dict(), dict(PUB="thread")])
+if which in ("llt",):
+    sweep(64, T, [dict(KS=8, NB=32, G=1, PUB="direct", LLT=2), dict(KS=8, NB=32, G=1, PUB="direct"), dict(KS=4, NB=16, G=2, PUB="direct", LLT=2),
+                  dict(KS=8, NB=16, G=1, PUB="direct", LLT=4), dict(), dict(LL=0)])
+    sweep(128, 96, [dict(), dict(KS=8, NB=32, G=1, PUB="direct", LLT=4), dict(LL=0)])
+if which in ("crash",):
+    run(64, 4, reps=1, KS=4, NB=32, G=2)
+if which in ("l2",):
+    sweep(64, T, [dict(), dict(KS=4, NB=32, G=2), dict(KS=8, NB=32, G=1), dict(KS=4, NB=16, G=2)])
+    sweep(32, T, [dict(), dict(KS=8, NB=32, G=1)])
 if which in ("trace2",):
     for B, Tn, nt, kw in ((64, 40, 1, dict(KS=8, NB=64, G=1)), (64, 40, 1, dict())):
         sys.stderr.write("\n## B=%d %s\n" % (B, kw)); sys.stderr.flush()
