@@ -7,7 +7,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrnmf.so")
+LIB_PATH = os.environ.get("DRNMF_LIB") or os.path.join(_HERE, "libdrnmf.so")      # DRNMF_LIB: debugging aid (A/B of two builds)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "drnmf.h")
 
 IMPL_TCGEN05 = 0
@@ -24,6 +24,7 @@ class DrnmfError(RuntimeError):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+LAYER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 
 _lib = None
 
@@ -74,6 +75,8 @@ def load():
         "drnmf_ista_workspace_bytes": (sz, [i32, i32, i32]),
         "drnmf_loss_and_grads": (i32, [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "drnmf_train_workspace_bytes": (sz, [vp, i32, i32]),
+        "drnmf_loss_and_grads_cb": (i32, [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, LAYER_FN, vp]),
+        "drnmf_adam_step": (i32, [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch

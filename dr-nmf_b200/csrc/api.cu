@@ -390,6 +390,22 @@ size_t drnmf_train_workspace_bytes(const drnmf_handle* h, int B, int T) {
 int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value, float* g_log_D,
                          float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
                          double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream) {
+  return drnmf_loss_and_grads_cb(h, x, y, B, T, mask_value, g_log_D, g_log_alph, g_log_lam1, g_log_h0, g_k_clean, g_k_noise,
+                                 loss_host, irm, ws, ws_bytes, stream, nullptr, nullptr);
+}
+
+int drnmf_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable, size_t n, float lr_t,
+                    float beta_1, float beta_2, float epsilon, float grad_scale, void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  DRNMF_CHECK(params && grads && m && v, "drnmf_adam_step: NULL argument");
+  return launch_adam(params, grads, m, v, trainable, n, lr_t, beta_1, beta_2, epsilon, grad_scale, (cudaStream_t)stream);
+}
+
+int drnmf_loss_and_grads_cb(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value, float* g_log_D,
+                            float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
+                            double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream,
+                            drnmf_layer_fn layer_cb, void* user) {
   DRNMF_CHECK(h, "NULL handle");
   int rc = check_device(h);
   if (rc) return rc;
@@ -399,7 +415,7 @@ int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   rc = train_loss_and_grads(h, x, y, B, T, mask_value, g_log_D, g_log_alph, g_log_lam1, g_log_h0, g_k_clean, g_k_noise,
-                            loss_host, irm, ws, ws_bytes, st);
+                            loss_host, irm, ws, ws_bytes, st, layer_cb, user);
   if (rc) return rc;
   return check_dev_error(h, st, "drnmf_loss_and_grads");
 }

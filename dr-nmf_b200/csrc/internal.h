@@ -115,7 +115,10 @@ int ista_ed(int F, int n, int R, const float* x, const float* W, float* H, float
 size_t train_workspace_bytes(const drnmf_handle* h, int B, int T);
 int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value, float* g_log_D,
                          float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
-                         double* loss_host, float* irm_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                         double* loss_host, float* irm_out, void* ws, size_t ws_bytes, cudaStream_t st,
+                         drnmf_layer_fn layer_cb, void* cb_user);
+int launch_adam(float* p, const float* g, float* m, float* v, const uint8_t* trainable, size_t n, float lr_t, float b1, float b2,
+                float eps, float gscale, cudaStream_t st);
 int launch_init_state(const drnmf_handle* h, FwdWorkspace& w, cudaStream_t st);
 int gemm_device_error(cudaStream_t st);
 const char* last_error();

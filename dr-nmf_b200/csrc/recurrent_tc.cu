@@ -74,6 +74,7 @@ struct RecArgs {
   int trace_lo, trace_hi;                    // items [lo, hi) of the observed CTA are traced
   int h3d;                                   // hidden-state tensor maps are 3-D slab maps (two 32-atom tiles per TMA instruction)
   int ll;                                    // latency mode: self-validating hidden-state exchange (see the consumer warp)
+  int sym;                                   // S_k symmetric (scalar alph): sub-chunks below the diagonal are fetched mirrored
   // shapes
   int B, Bp, T, K, R, Rp;
   int MT, KS, RO, KSLICE, n_tiles;           // n_tiles = batch tiles per batch group (grid.z groups run on disjoint SMs)
@@ -286,7 +287,8 @@ __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sc
 template <int NB, bool BWD, int CB>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
-               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ RecSched sch, const RecArgs a_in) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW64,
+               const __grid_constant__ RecSched sch, const RecArgs a_in) {
   // Batch groups: utterances are independent, so grid.z groups of (KS x MT) CTAs each run the whole chain on their own
   // contiguous range of batch tiles (disjoint SMs, own flags, no interaction).  Everything indexed by the utterance is
   // re-based once here; below, tile i / utterance b are group-local.
@@ -334,6 +336,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo); tma_prefetch_desc(&tmW);
+#ifndef RT_VAR_NO_PREFETCH64
+    tma_prefetch_desc(&tmW64);
+#endif
     for (int i = 0; i < RT_WB; ++i) { mbar_init(&bars->wb_full[i], 128); mbar_init(&bars->wb_empty[i], 1); }
     for (int i = 0; i < RT_MAXW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], 4); }
     for (int i = 0; i < RT_MAXH; ++i) { mbar_init(&bars->h_full[i], 1); mbar_init(&bars->h_empty[i], 1); }
@@ -367,12 +372,26 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             if (!(e & 64u)) continue;                                   // resident: nothing to load
             const int col0 = s * a.KSLICE + (int)(e & 15u) * 64;
             const int npc = (a.KSLICE - (int)(e & 15u) * 64 >= 64) ? 2 : 1;
+            // Symmetric S_k: a sub-chunk whose K-columns lie in an M-tile below this CTA's own is fetched as the mirrored
+            // block (rows = its K-columns, columns = this M-tile) in four 64 x 32 pieces, two per ring slot, and read
+            // transposed by the loaders: only the blocks on and above the diagonal of a layer are ever touched (36 of 64
+            // at R = 1000: 54 of 96 MB per frame), which is what stays resident in L2 across a frame.
+#ifdef RT_VAR_NO_MIR_PRODUCER
+            const bool mir = false;
+#else
+            const bool mir = a.sym && (col0 >> 7) < m;
+#endif
             for (int pc = 0; pc < npc; ++pc, wr.next(a.WST)) {
               const int ws = wr.idx;
               RT_TIMED(0, okw = mbar_wait(&bars->w_free[ws], wr.ph ^ 1u, err, RT_WATCHDOG));
               if (!okw) { atomicCAS(a.dev_error, 0, 214); break; }
               mbar_expect_tx(&bars->w_full[ws], 16384u);
-              tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW, &bars->w_full[ws], col0 + pc * 32, (k - 1) * Rp + m * 128, pol_w);
+              if (mir) {
+                tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW64, &bars->w_full[ws], m * 128 + (2 * pc) * 32, (k - 1) * Rp + col0, pol_w);
+                tma_load_2d_hint(smem + a.off_w + ws * 16384 + 8192, &tmW64, &bars->w_full[ws], m * 128 + (2 * pc + 1) * 32, (k - 1) * Rp + col0, pol_w);
+              } else {
+                tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW, &bars->w_full[ws], col0 + pc * 32, (k - 1) * Rp + m * 128, pol_w);
+              }
             }
           }
       }
@@ -531,12 +550,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     constexpr int SWZ = (CHUNKS >= 8) ? 7 : CHUNKS - 1;
     int it = 0;
     RtRing ar, rr;
+    bool dead = false;                               // a wait failed: run through (named barriers!) without touching mbarriers
     for (int ms = 0; ms < n_mma_steps; ++ms) {      // on a watchdog error the loop keeps running (waits return at once)
       for (int i = 0; i < n_tiles; ++i, ++it, ar.next(RT_AST), rr.next(a.RST)) {     // so that the named barrier below always sees all 128 threads
         const int as = ar.idx, rs = rr.idx;
         bool okp;
         RT_TIMED(0, okp = mbar_wait(&bars->t_full[as], ar.ph, err, RT_WATCHDOG));
-        if (!okp) atomicCAS(a.dev_error, 0, 207);
+        if (!okp) { atomicCAS(a.dev_error, 0, 207); dead = true; }
         tc_fence_after();
         if (threadIdx.x == 128) RT_TRACE(4, 1, it);
         if (dbg_on) dbg_acc[2] += clock64() - *reinterpret_cast<volatile long long*>(&bars->dbg_ts[1]);   // issue -> completion
@@ -546,10 +566,10 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         tc_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->t_empty[as]);
+        if (lane == 0 && !dead) mbar_arrive(&bars->t_empty[as]);
         // slot rs (staging here, reduction slot in the owners) is free once every owner has consumed its previous use
         RT_TIMED(1, okp = mbar_wait_cluster(&bars->red_free[rs], rr.ph ^ 1u, err, RT_WATCHDOG));
-        if (!okp) atomicCAS(a.dev_error, 0, 208);
+        if (!okp) { atomicCAS(a.dev_error, 0, 208); dead = true; }
         if (threadIdx.x == 128) RT_TRACE(4, 2, it);
         const uint32_t srow = stage0 + rs * a.red_slot_bytes + rho * (NB * 4);
 #pragma unroll
@@ -564,7 +584,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         int o_first, o_cnt;
         if (a.RO <= 32) { __syncwarp(); o_cnt = 32 / a.RO; o_first = q * o_cnt; }
         else { asm volatile("bar.sync 2, 128;" ::: "memory"); o_cnt = (warp == 4) ? a.KS : 0; o_first = 0; }
-        if (lane < o_cnt) {                           // lane l copies this CTA's block for owner o_first + l
+        if (lane < o_cnt && !dead) {                  // lane l copies this CTA's block for owner o_first + l
           const uint32_t o = (uint32_t)(o_first + lane);
           const uint32_t src = stage0 + rs * a.red_slot_bytes + o * blk_bytes;
           const uint32_t dst = mapa_u32(smem_u32(smem + a.off_red) + rs * a.red_slot_bytes + (uint32_t)s * blk_bytes, o);
@@ -645,6 +665,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     fetch_xw(0, 0, 0, xa_next);
     int it = 0;
     RtRing rr;
+    bool dead = false;                              // a wait of this thread failed: run through without touching mbarriers
     long long j = 0;
     for (int t = 0; t < T; ++t)
     for (int k = 0; k < K; ++k)
@@ -713,10 +734,11 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       } else {
         // ---- wait for the KS partial tiles, sum them in rank order ----
         const int rs = rr.idx;
-        if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
-        bool oko;
-        RT_TIMED(0, oko = mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG));
-        if (!oko) atomicCAS(a.dev_error, 0, 210);
+        // (after a failed wait the thread only runs through: re-arming a barrier whose phase never completed traps)
+        if (otid == 0 && !dead) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
+        bool oko = false;
+        if (!dead) RT_TIMED(0, oko = mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG));
+        if (!oko) { atomicCAS(a.dev_error, 0, 210); dead = true; }
         const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
         if (dbg_on) _ts = clock64();
         if (otid == 0) RT_TRACE(5, 1, it);
@@ -752,7 +774,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           }
         }
         __syncwarp();                                  // this warp has consumed the slot (values are in registers):
-        if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);   // 4 warps x KS owners arrivals
+        if (lane < a.KS && !dead) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);   // 4 warps x KS owners arrivals
         if (dbg_on) { long long _n = clock64(); dbg_acc[3] += _n - _ts; _ts = _n; }
         if (otid == 0) RT_TRACE(5, 2, it);
         ++it; rr.next(a.RST);
@@ -927,6 +949,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     fetch_act(0, 0, 0, act_next);
     int it = 0;
     RtRing rr;
+    bool dead = false;                              // a wait of this thread failed: run through without touching mbarriers
     long long j = 0;
     for (int fi = 0; fi < T; ++fi)
     for (int u = 0; u < K; ++u)
@@ -1017,8 +1040,8 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         }
       } else {
         const int rs = rr.idx;
-        if (otid == 0) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
-        if (!mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 220);
+        if (otid == 0 && !dead) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
+        if (dead || !mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 220); dead = true; }
         const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -1054,7 +1077,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           }
         }
         __syncwarp();
-        if (lane < a.KS) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);
+        if (lane < a.KS && !dead) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);
         ++it; rr.next(a.RST);
 #pragma unroll
         for (int bi = 0; bi < CB; ++bi) {   // identity part of S_k: this owner's rows of the operand; scale back (vector alph)
@@ -1155,6 +1178,43 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const int col0 = s * a.KSLICE + sc * 64;
           const int npc = (a.KSLICE - sc * 64 >= 64) ? 2 : 1;
           const uint32_t tb = trow + (uint32_t)wb * 128u;
+#ifdef RT_VAR_NO_MIR_LOADER
+          if (false) {
+#else
+          if (a.sym && (col0 >> 7) < m) {
+#endif
+            // mirrored sub-chunk: piece q (two per ring slot) = [64 K-columns (rows)] x [output rows 32q .. 32q+31 (128 bytes)].
+            // Warp q owns exactly those TMEM lanes and reads its piece transposed: for a fixed K-column the 32 lanes read
+            // one 128-byte row (conflict-free).  No diagonal in these blocks.  Every warp waits for and hands back both
+            // slots so that the arrival counts of consecutive sub-chunks cannot mix.
+            const int ws0 = wr.idx; const uint32_t ph0 = wr.ph; wr.next(a.WST);
+            const int ws1 = wr.idx; const uint32_t ph1 = wr.ph; wr.next(a.WST);
+            RT_TIMED(1, okl = mbar_wait(&bars->w_full[ws0], ph0, err, RT_WATCHDOG) && mbar_wait(&bars->w_full[ws1], ph1, err, RT_WATCHDOG));
+            if (!okl) { atomicCAS(a.dev_error, 0, 215); break; }
+            const uint32_t piece = smem_u32(smem + a.off_w + ((q >> 1) ? ws1 : ws0) * 16384 + (q & 1) * 8192);
+            const uint32_t lcol = (uint32_t)(lane & 3) * 4u, lchunk = (uint32_t)(lane >> 2);
+            {
+              const uint32_t f = wb == 0 ? f0 : (wb == 1 ? f1 : f2);
+              RT_TIMED(0, okl = mbar_wait(&bars->wb_empty[wb], (f & 1u) ^ 1u, err, RT_WATCHDOG));
+              if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
+              tc_fence_after();
+            }
+            for (int half = 0; half < 2; ++half) {
+              float v[32], lo[32];
+#pragma unroll
+              for (int e2 = 0; e2 < 32; ++e2) {
+                const uint32_t c = (uint32_t)(half * 32 + e2);
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[e2]) : "r"(piece + c * 128u + ((lchunk ^ (c & 7u)) << 4) + lcol));
+              }
+#pragma unroll
+              for (int e2 = 0; e2 < 32; ++e2) lo[e2] = tf32_lo(v[e2]);
+              tmem_st32(tb + half * 32, v);
+              tmem_st32(tb + 64 + half * 32, lo);
+            }
+            fence_proxy_async_smem();                // all values have been consumed by the arithmetic above
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&bars->w_free[ws0]); mbar_arrive(&bars->w_free[ws1]); }
+          } else
           for (int pc = 0; pc < npc; ++pc, wr.next(a.WST)) {
             const int ws = wr.idx;
             RT_TIMED(1, okl = mbar_wait(&bars->w_full[ws], wr.ph, err, RT_WATCHDOG));
@@ -1329,7 +1389,7 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
   return p;
 }
 
-using RecKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const RecSched, const RecArgs);
+using RecKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const RecSched, const RecArgs);
 
 template <int NB>
 static RecKernel rec_kernel_nb(bool bwd, int CB) {
@@ -1375,13 +1435,13 @@ static int rec_max_clusters(const RecPlan& p, bool bwd, int* out) {
 }
 
 static int launch_rec(const RecPlan& p, bool bwd, const CUtensorMap& tH_hi, const CUtensorMap& tH_lo, const CUtensorMap& tW,
-                      cudaStream_t st) {
+                      const CUtensorMap& tW64, cudaStream_t st) {
   RecKernel kern = rec_kernel(p, bwd);
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p.KS > 8 ? 1 : 0));
   cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[2];
   rec_launch_config(p, cfg, attr, st);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tH_hi, tH_lo, tW, p.sch, p.a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tH_hi, tH_lo, tW, tW64, p.sch, p.a);
   if (e != cudaSuccess) {
     cudaGetLastError();
     set_error("persistent recurrence launch failed (%s): grid %d x %d x %d CTAs must be co-resident; SMs in use by another "
@@ -1425,8 +1485,9 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
     for (int NB = 64; NB >= 16 && !p.ok; NB >>= 1) {
       if (env_nb && atoi(env_nb) != NB) continue;
       if (!env_nb && latency && ((NB == 64) || (NB == 32 && B <= 16))) continue;       // 32-column tiles (16 for B <= 16)
-      // throughput: the widest tile that still gives every group a tile (NB = 16 is the floor)
-      if (!env_nb && !latency && NB > 16 && (B + NB - 1) / NB < g_max) continue;
+      // throughput: the widest tile that still gives every group a tile; 32 columns is the floor (fewer groups then)
+      if (!env_nb && !latency && NB == 16) continue;
+      if (!env_nb && !latency && NB > 32 && (B + NB - 1) / NB < g_max) continue;
       for (int G = g_max; G >= 1 && !p.ok; --G) {
         RecPlan c = plan_recurrent(h, B, KS, NB, G);
         if (!c.ok) { p.why = c.why; continue; }
@@ -1489,11 +1550,14 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   // (measured: it wins with one or two groups - 5.3 -> 4.9 us/step at B = 32 - and loses when 128 CTAs pull through LDG)
   a.ll = (p.n_tiles <= (getenv("DRNMF_REC_LLT") ? atoi(getenv("DRNMF_REC_LLT")) : 1) && p.NB <= 32 && p.G <= 2 && a.pub_unit == 4 && !(getenv("DRNMF_REC_LL") && !strcmp(getenv("DRNMF_REC_LL"), "0"))) ? 1 : 0;
   if (a.ll) DRNMF_CUDA(cudaMemsetAsync(w.hb_hi, 0, sizeof(float) * 2 * (size_t)w.Bp * Rp, st));
-  CUtensorMap tH_hi, tH_lo, tW;
+  CUtensorMap tH_hi, tH_lo, tW, tW64;
   int rc;
+  // scalar alph: S_k is symmetric -> mirrored fetches below the diagonal (needs 64-aligned sub-chunks)
+  a.sym = (h->alph_dim == 1 && p.KSLICE % 64 == 0 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
+  if ((rc = make_tmap_2d(&tW64, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 64))) return rc;
   if ((rc = make_h_maps(&tH_hi, &tH_lo, w, Rp, p.NB, &a.h3d))) return rc;
-  return launch_rec(p, true, tH_hi, tH_lo, tW, st);
+  return launch_rec(p, true, tH_hi, tH_lo, tW, tW64, st);
 }
 
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
@@ -1537,11 +1601,14 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   // (measured: it wins with one or two groups - 5.3 -> 4.9 us/step at B = 32 - and loses when 128 CTAs pull through LDG)
   a.ll = (p.n_tiles <= (getenv("DRNMF_REC_LLT") ? atoi(getenv("DRNMF_REC_LLT")) : 1) && p.NB <= 32 && p.G <= 2 && a.pub_unit == 4 && !(getenv("DRNMF_REC_LL") && !strcmp(getenv("DRNMF_REC_LL"), "0"))) ? 1 : 0;
   if (a.ll) DRNMF_CUDA(cudaMemsetAsync(w.hb_hi, 0, sizeof(float) * 2 * (size_t)w.Bp * Rp, st));
-  CUtensorMap tH_hi, tH_lo, tW;
+  CUtensorMap tH_hi, tH_lo, tW, tW64;
   int rc;
+  // scalar alph: S_k is symmetric -> mirrored fetches below the diagonal (needs 64-aligned sub-chunks)
+  a.sym = (h->alph_dim == 1 && p.KSLICE % 64 == 0 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
+  if ((rc = make_tmap_2d(&tW64, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 64))) return rc;
   if ((rc = make_h_maps(&tH_hi, &tH_lo, w, Rp, p.NB, &a.h3d))) return rc;
-  rc = launch_rec(p, false, tH_hi, tH_lo, tW, st);
+  rc = launch_rec(p, false, tH_hi, tH_lo, tW, tW64, st);
   if (rc == DRNMF_OK && want_dbg) {
     long long d[16 * 8];
     DRNMF_CUDA(cudaMemcpyAsync(d, dbg_dev, sizeof(d), cudaMemcpyDeviceToHost, st));

@@ -402,9 +402,50 @@ static int gemm(const drnmf_handle* h, GemmEpi epi, const GemmArgs& a, cudaStrea
   return h->impl == DRNMF_IMPL_SIMT ? launch_gemm_simt(epi, a, st) : launch_gemm_tc(epi, a, st);
 }
 
+// Keras 2.0.4 Adam on a flat parameter segment, fused with the 1/frames normalisation of the gradient and the
+// trainable mask:  g' = g * gscale ; m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2 ; p -= lr_t m / (sqrt(v) + eps).
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       const uint8_t* __restrict__ trainable, size_t n, float lr_t, float b1, float b2, float eps, float gscale) {
+  const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 + 3 < n) {
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i0);
+    float4 p4 = *reinterpret_cast<const float4*>(p + i0), m4 = *reinterpret_cast<const float4*>(m + i0), v4 = *reinterpret_cast<const float4*>(v + i0);
+    const uchar4 t4 = trainable ? *reinterpret_cast<const uchar4*>(trainable + i0) : make_uchar4(1, 1, 1, 1);
+    auto upd = [&](float& pp, float gg, float& mm, float& vv, unsigned char tt) {
+      if (!tt) return;
+      gg *= gscale;
+      mm = b1 * mm + (1.f - b1) * gg; vv = b2 * vv + (1.f - b2) * gg * gg;
+      pp -= lr_t * mm / (sqrtf(vv) + eps);
+    };
+    upd(p4.x, g4.x, m4.x, v4.x, t4.x); upd(p4.y, g4.y, m4.y, v4.y, t4.y); upd(p4.z, g4.z, m4.z, v4.z, t4.z); upd(p4.w, g4.w, m4.w, v4.w, t4.w);
+    *reinterpret_cast<float4*>(p + i0) = p4; *reinterpret_cast<float4*>(m + i0) = m4; *reinterpret_cast<float4*>(v + i0) = v4;
+  } else {
+    for (size_t i = i0; i < n; ++i) {
+      if (trainable && !trainable[i]) continue;
+      const float gg = g[i] * gscale;
+      m[i] = b1 * m[i] + (1.f - b1) * gg; v[i] = b2 * v[i] + (1.f - b2) * gg * gg;
+      p[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+    }
+  }
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, const uint8_t* trainable, size_t n, float lr_t, float b1, float b2,
+                float eps, float gscale, cudaStream_t st) {
+  if (n == 0) return DRNMF_OK;
+  DRNMF_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (!trainable || (reinterpret_cast<uintptr_t>(trainable) & 3) == 0),
+              "drnmf_adam_step: buffers must be 16-byte aligned (mask 4-byte)");
+  const size_t nthreads = (n + 3) / 4;
+  k_adam<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(p, g, m, v, trainable, n, lr_t, b1, b2, eps, gscale);
+  count_launch();
+  DRNMF_CUDA(cudaGetLastError());
+  return DRNMF_OK;
+}
+
 int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value, float* g_log_D,
                          float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
-                         double* loss_host, float* irm_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                         double* loss_host, float* irm_out, void* ws, size_t ws_bytes, cudaStream_t st,
+                         drnmf_layer_fn layer_cb, void* cb_user) {
   DRNMF_CHECK(h->uk_d == h->uk_o, "training assumes U_k = c*11^T for k >= 1 (what build_alt creates)");
   TrainWs w = carve_train(h, B, T, ws);
   if (ws_bytes < w.bytes) { set_error("training workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
@@ -533,6 +574,9 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
     k_scalar_grads<<<1, 256, 0, st>>>(w.rowacc, w.rowS, k >= 1 ? Rp / 32 : 0, R, h->alph_dim, g_log_alph + (tied_a ? 0 : (size_t)k * h->alph_dim), g_log_lam1 + (tied_l ? 0 : k),
                                       (tied_a && k > 0) ? 1 : 0, (tied_l && k > 0) ? 1 : 0);
     count_launch(2);
+    // the gradients of layer k are enqueued: a data-parallel caller starts their all-reduce now, under the GEMMs of
+    // the layers that follow (enhance.py:1152 trains through Keras; bucketing is this build's)
+    if (layer_cb && (rc = layer_cb(cb_user, k, (void*)st))) { set_error("drnmf_loss_and_grads: layer callback failed for layer %d (%d)", k, rc); return DRNMF_ERR_INVALID; }
   }
   {   // recon kernels: dEc = act^{K-1}(time-major)^T-rows . dS'^T-rows  and the same with dN'
     for (int which = 0; which < 2; ++which) {

@@ -160,28 +160,63 @@ class DrnmfEngine:
                                                float(mask_value), _ptr(out), ws, wsb, _stream()))
         return out
 
-    def loss_and_grads(self, x, y, mask_value=-1.0, want_irm=False):
+    def loss_and_grads(self, x, y, mask_value=-1.0, want_irm=False, out=None, layer_ready=None):
         """Training step on the device: forward with stored activations, masked-MSE loss (enhance.py:1040-1073) and
         hand-written BPTT.  Returns (loss_sum, mask_sum, grads dict of CUDA tensors [, irm]); the loss is
-        loss_sum / mask_sum and the gradients are those of loss_sum (divide by the all-reduced frame count)."""
+        loss_sum / mask_sum and the gradients are those of loss_sum (divide by the all-reduced frame count).
+        out: dict of preallocated gradient tensors (same keys / shapes as returned) to write into.
+        layer_ready(k): called right after the kernels producing the gradients of layer k have been enqueued on the
+        current stream (drnmf_loss_and_grads_cb) - the hook for per-layer gradient all-reduce under the later GEMMs."""
         if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32):
             raise TypeError("x must be a float32 CUDA tensor")
         x, y = x.contiguous(), y.contiguous()
         B, T, F = x.shape
         dev = x.device
         log_D, log_alph, log_lam1 = self._keep[0], self._keep[1], self._keep[2]
-        g = {"log_D": torch.zeros_like(log_D), "log_alph": torch.zeros_like(log_alph).reshape(-1),
-             "log_lam1": torch.zeros_like(log_lam1), "log_h0": torch.zeros(self.R, device=dev),
-             "k_clean": torch.zeros((self.R // 2, F), device=dev), "k_noise": torch.zeros((self.R // 2, F), device=dev)}
+        if out is None:
+            g = {"log_D": torch.zeros_like(log_D), "log_alph": torch.zeros_like(log_alph).reshape(-1),
+                 "log_lam1": torch.zeros_like(log_lam1), "log_h0": torch.zeros(self.R, device=dev),
+                 "k_clean": torch.zeros((self.R // 2, F), device=dev), "k_noise": torch.zeros((self.R // 2, F), device=dev)}
+        else:
+            g = out
+            want = {"log_D": log_D.numel(), "log_alph": log_alph.numel(), "log_lam1": log_lam1.numel(), "log_h0": self.R,
+                    "k_clean": (self.R // 2) * F, "k_noise": (self.R // 2) * F}
+            for k, n in want.items():
+                if not (g[k].is_cuda and g[k].dtype == torch.float32 and g[k].is_contiguous() and g[k].numel() == n):
+                    raise ValueError("out[%r] must be a contiguous float32 CUDA tensor with %d elements" % (k, n))
         irm = torch.empty((B, T, F), dtype=torch.float32, device=dev) if want_irm else None
         need = self.lib.drnmf_train_workspace_bytes(self.h, B, T)
         ws, wsb = self._workspace(need, "_tws")
         loss = (C.c_double * 2)()
-        _lib.check(self.lib.drnmf_loss_and_grads(self.h, _ptr(x), _ptr(y), B, T, float(mask_value), _ptr(g["log_D"]),
-                                                 _ptr(g["log_alph"]), _ptr(g["log_lam1"]), _ptr(g["log_h0"]),
-                                                 _ptr(g["k_clean"]), _ptr(g["k_noise"]), loss, _ptr(irm), ws, wsb, _stream()))
-        out = (float(loss[0]), float(loss[1]), g)
-        return out + (irm,) if want_irm else out
+        failed = []
+
+        def _cb(user, k, stream):
+            try:
+                layer_ready(int(k))
+                return 0
+            except Exception as e:      # an exception must not unwind through the C frames
+                failed.append(e)
+                return 1
+        cb = _lib.LAYER_FN(_cb) if layer_ready is not None else _lib.LAYER_FN(0)
+        rc = self.lib.drnmf_loss_and_grads_cb(self.h, _ptr(x), _ptr(y), B, T, float(mask_value), _ptr(g["log_D"]),
+                                              _ptr(g["log_alph"]), _ptr(g["log_lam1"]), _ptr(g["log_h0"]),
+                                              _ptr(g["k_clean"]), _ptr(g["k_noise"]), loss, _ptr(irm), ws, wsb, _stream(), cb, None)
+        if failed:
+            raise failed[0]
+        _lib.check(rc)
+        res = (float(loss[0]), float(loss[1]), g)
+        return res + (irm,) if want_irm else res
+
+    def adam_step(self, params, grads, m, v, lr_t, beta_1=0.9, beta_2=0.999, epsilon=1e-8, grad_scale=1.0, trainable=None):
+        """Fused Keras-formula Adam on flat float32 CUDA buffers (drnmf_adam_step); `trainable`: uint8 mask or None."""
+        n = params.numel()
+        for t in (params, grads, m, v):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n):
+                raise ValueError("adam_step needs contiguous float32 CUDA buffers of equal size")
+        if trainable is not None and not (trainable.is_cuda and trainable.dtype == torch.uint8 and trainable.numel() == n):
+            raise ValueError("trainable must be a uint8 CUDA tensor with one byte per parameter")
+        _lib.check(self.lib.drnmf_adam_step(_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _ptr(trainable), n, float(lr_t),
+                                            float(beta_1), float(beta_2), float(epsilon), float(grad_scale), _stream()))
 
     def stage_times(self):
         """ms of (masking, projection GEMM, recurrence, recon+mask GEMM) of the last forward (CUDA events)."""

@@ -168,6 +168,25 @@ DRNMF_API int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float*
                          float* g_k_noise, double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream);
 DRNMF_API size_t drnmf_train_workspace_bytes(const drnmf_handle* h, int B, int T);
 
+/* Data-parallel variant: `layer_ready(user, k, stream)` is called on the host right after the kernels that produce the
+ * gradients of layer k (g_log_D[k], g_log_alph[k], g_log_lam1[k]; k = 0 .. K-1 in order) have been enqueued on `stream`,
+ * so that the caller can start that layer's gradient all-reduce (ordered after an event it records on `stream`) under the
+ * weight-gradient GEMMs of the layers that follow.  Tied parameters accumulate over the layers: their gradient is
+ * complete at k = K-1.  g_log_h0, g_k_clean, g_k_noise are complete when the call returns.  Return 0 from the callback;
+ * NULL = no callback.  The reference trains through Keras' model.fit (enhance.py:1152-1157) on one device. */
+typedef int (*drnmf_layer_fn)(void* user, int layer, void* stream);
+DRNMF_API int drnmf_loss_and_grads_cb(drnmf_handle* h, const float* x, const float* y, int B, int T, float mask_value,
+                            float* g_log_D, float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean,
+                            float* g_k_noise, double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream,
+                            drnmf_layer_fn layer_ready, void* user);
+
+/* Keras 2.0.4 Adam update (optimizers.py: lr_t = lr sqrt(1-b2^t)/(1-b1^t), passed in by the caller) fused with the
+ * gradient normalisation on `n` consecutive floats:  g' = grads * grad_scale ; m = b1 m + (1-b1) g' ;
+ * v = b2 v + (1-b2) g'^2 ; params -= lr_t m / (sqrt(v) + epsilon).  `trainable` (n bytes, may be NULL = all) freezes
+ * entries whose byte is 0 (enhance.py:239-248 `params_trainable`).  All device pointers, 16-byte aligned. */
+DRNMF_API int drnmf_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable, size_t n,
+                    float lr_t, float beta_1, float beta_2, float epsilon, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

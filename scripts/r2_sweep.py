@@ -97,7 +97,7 @@ if which in ("llt",):
                   dict(KS=8, NB=16, G=1, PUB="direct", LLT=4), dict(), dict(LL=0)])
     sweep(128, 96, [dict(), dict(KS=8, NB=32, G=1, PUB="direct", LLT=4), dict(LL=0)])
 if which in ("crash",):
-    run(64, 4, reps=1, KS=4, NB=32, G=2)
+    run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
 if which in ("l2",):
     sweep(64, T, [dict(), dict(KS=4, NB=32, G=2), dict(KS=8, NB=32, G=1), dict(KS=4, NB=16, G=2)])
     sweep(32, T, [dict(), dict(KS=8, NB=32, G=1)])

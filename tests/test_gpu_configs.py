@@ -179,3 +179,57 @@ def test_device_error_is_not_sticky():
         eng.forward(x)
     H, _ = eng.forward(x)            # the failure was reported once; the handle works again
     assert torch.isfinite(H).all()
+
+
+def test_device_trainer_step_matches_keras_adam_formula():
+    """DeviceTrainer (flat buffers, fused drnmf_adam_step, rebuild) against the Keras-formula Adam in torch applied to the
+    engine's own gradients; frozen parameters (log_lam1) must not move; the loss decreases over a few steps."""
+    from drnmf_b200 import training
+    F, R, K, B, T = 65, 40, 4, 6, 7
+    rng = np.random.default_rng(21)
+    p = synth.model_params(F, R, K, alph=30.0, lam1=0.5)
+    x = (np.abs(rng.standard_normal((B, T, F))) * 2).astype(np.float32)
+    y = (x * 0.6).astype(np.float32)
+    x[3, 5:] = -1.0; y[3, 5:] = -1.0
+    xt, yt = torch.as_tensor(x, device="cuda"), torch.as_tensor(y, device="cuda")
+    eng = engine.DrnmfEngine(F, R, K)
+    eng.set_params(p)
+    ls, ms, g = eng.loss_and_grads(xt, yt)
+    ref = training.Adam(lr=2e-3)
+    names = ("log_D", "log_alph", "log_h0", "k_clean", "k_noise")
+    pt = {n: torch.as_tensor(np.asarray(p[n], np.float32).reshape(g[n].shape), device="cuda").clone() for n in names}
+    ref.step(pt, {n: g[n] / ms for n in names})
+    eng2 = engine.DrnmfEngine(F, R, K)
+    tr = training.DeviceTrainer(eng2, p, learning_rate=2e-3)
+    loss0 = tr.train_on_batch(xt, yt)
+    assert abs(loss0 - ls / ms) < 1e-6 * abs(loss0)
+    for n in names:
+        got, want = tr.p[n].reshape(-1), pt[n].reshape(-1)
+        assert float((got - want).abs().max()) < 2e-6, (n, float((got - want).abs().max()))
+    np.testing.assert_array_equal(tr.p["log_lam1"].cpu().numpy(), np.asarray(p["log_lam1"], np.float32))
+    losses = [loss0] + [tr.train_on_batch(xt, yt) for _ in range(5)]
+    assert losses[-1] < losses[0]
+
+
+def test_trainer_untied_vector_alph_config():
+    """Trainer/fit with untie_alph and params_untied = [log_D, log_alph] (enhance.py:225-226, 628-633)."""
+    from drnmf_b200 import enhance
+    F, r, K, B, T = 33, 8, 3, 4, 6
+    rng = np.random.default_rng(5)
+    W = synth.dictionary(F, 2 * r)
+    prm = {"input_dim": F, "hidden_dim": 2 * r, "output_dim": F, "mask_value": -1.0, "maxseq": T, "K_layers": K, "W": W,
+           "alph": 20.0, "lam1": 0.5, "params_untied": ["log_D", "log_alph"], "params_trainable": ["log_D", "log_alph"],
+           "untie_alph": True}
+    model = enhance.build_unfolded_snmf(prm)
+    clean = (np.abs(rng.standard_normal((B, T, F))) * 1.5).astype(np.float32)
+    x = (clean + np.abs(rng.standard_normal((B, T, F))) * 0.8).astype(np.float32)
+    w0 = dict(zip(model.weight_names(), model.get_weights()))
+    hist = model.fit(x, clean, batch_size=2, epochs=3, learning_rate=5e-3)
+    w1 = dict(zip(model.weight_names(), model.get_weights()))
+    assert len(hist["loss"]) == 3 and hist["loss"][-1] < hist["loss"][0]
+    a1 = [n for n in w0 if n.endswith("log_alph_1")][0]
+    assert w0[a1].shape == (2 * r,) and np.abs(w1[a1] - w0[a1]).max() > 0
+    prm2 = dict(prm, params_trainable=["log_D", "log_U1"])
+    model2 = enhance.build_unfolded_snmf(prm2)
+    with pytest.raises(NotImplementedError):
+        model2.fit(x, clean, batch_size=2, epochs=1)

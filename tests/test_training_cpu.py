@@ -136,3 +136,48 @@ def test_mu_frame_sharding_gloo():
         np.testing.assert_allclose(hr, h[:, rank * n // 2:(rank + 1) * n // 2], rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(cr, info["cost"], rtol=1e-10)
     np.testing.assert_array_equal(res[0][1], res[1][1])
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # flat gradient: 3 per-layer buckets of 4 floats, then a tail of 5 (scalars, h0, recon kernels)
+    flat = torch.arange(17, dtype=torch.float32) * (rank + 1)
+    b = training.GradBuckets(flat, [(0, 4), (4, 8), (8, 12)], 12)
+    for k in range(3):          # what drnmf_loss_and_grads_cb does layer by layer
+        b.layer_ready(k)
+    loss_sum, mask_sum = b.finish(2.0 * (rank + 1), 10.0 * (rank + 1))
+    flat2 = torch.ones(6) * (rank + 1)          # tied dictionary: one reduction of everything at the end
+    b2 = training.GradBuckets(flat2, [], 0)
+    b2.layer_ready(0)
+    l2, m2 = b2.finish(1.0, 1.0, reduce_all=True)
+    q.put((rank, loss_sum, mask_sum, flat.clone(), flat2.clone(), m2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_per_layer_gradient_buckets_gloo():
+    """world_size 2 over gloo: per-layer buckets + tail + statistics give the global sums on every rank."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ls, ms, flat, flat2, m2 in res:
+        assert ls == 6.0 and ms == 30.0 and m2 == 2.0
+        torch.testing.assert_close(flat, torch.arange(17, dtype=torch.float32) * 3.0)
+        torch.testing.assert_close(flat2, torch.full((6,), 3.0))
+
+
+def test_grad_buckets_single_process_is_a_no_op():
+    flat = torch.arange(8, dtype=torch.float32)
+    b = training.GradBuckets(flat, [(0, 4)], 4)
+    b.layer_ready(0)
+    assert b.finish(3.0, 2.0) == (3.0, 2.0) and b.launched == 0
+    torch.testing.assert_close(flat, torch.arange(8, dtype=torch.float32))
