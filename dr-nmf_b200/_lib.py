@@ -71,11 +71,15 @@ def load():
         "drnmf_snmf_workspace_bytes": (sz, [i32, i32, i32]),
         "drnmf_snmf_mu_ed_dist": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, C.POINTER(i32), i32, vp, sz, vp,
                                         ALLREDUCE_FN, vp]),
+        "drnmf_snmf_irm": (i32, [i32, i32, i32, i32, vp, vp, vp, i32, vp, sz, vp]),
+        "drnmf_snmf_irm_workspace_bytes": (sz, [i32, i32, i32]),
         "drnmf_ista_ed": (i32, [i32, i32, i32, vp, vp, vp, f32, f32, i32, i32, vp, sz, vp]),
         "drnmf_ista_workspace_bytes": (sz, [i32, i32, i32]),
         "drnmf_loss_and_grads": (i32, [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "drnmf_train_workspace_bytes": (sz, [vp, i32, i32]),
         "drnmf_loss_and_grads_cb": (i32, [vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, LAYER_FN, vp]),
+        "drnmf_set_training_loss": (i32, [vp, i32, f32]),
+        "drnmf_forward_all_hidden": (i32, [vp, vp, i32, i32, f32, vp, vp, sz, vp]),
         "drnmf_adam_step": (i32, [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp]),
     }
     for name, (res, args) in sig.items():

@@ -5,6 +5,8 @@ maxlen, d) tensors with a mask (reshape_and_pad_stacks, :116-169; get_padded_dat
 scoring) is out of scope; AudioDataset here is built from in-memory waveforms."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -74,7 +76,53 @@ def clip_x_to_y(x, y, xfidx, yfidx):
 
 
 class AudioDataset:
-    def __init__(self, x_waveforms, y_waveforms=None, params_stft={"N": 320, "hop": 160, "nch": 1}):
+    """In-memory form: AudioDataset(list of waveforms [, list of target waveforms], params_stft=...).
+    Reference form (audio_dataset.py:177-262): AudioDataset(taskfile_input, taskfile_output, datafile=..., params_stft=...,
+    downsample=1) with text files listing one wav path per line; the [Re;Im] stacks and the fidx table are cached in
+    `datafile` and served from it when it exists (an .npz here; the reference writes HDF5 through h5py)."""
+
+    def __init__(self, x_waveforms, y_waveforms=None, datafile=None, params_stft={"N": 320, "hop": 160, "nch": 1}, downsample=1):
+        self.datafile = datafile
+        self.x_wavfiles = self.y_wavfiles = None
+        if isinstance(x_waveforms, str):          # taskfiles
+            from .util import wavread
+            if datafile is not None and os.path.isfile(self._cache_name(datafile)):
+                self._load_cache(params_stft)
+                return
+            with open(x_waveforms) as f:
+                self.x_wavfiles = [l.strip() for l in f if l.strip()][::downsample]
+            with open(y_waveforms) as f:
+                self.y_wavfiles = [l.strip() for l in f if l.strip()][::downsample]
+            x_waveforms = [wavread(w)[0] for w in self.x_wavfiles]
+            y_waveforms = [wavread(w)[0] for w in self.y_wavfiles]
+        self._from_waveforms(x_waveforms, y_waveforms, params_stft)
+        if datafile is not None:
+            self._save_cache()
+
+    @staticmethod
+    def _cache_name(datafile):
+        return datafile if str(datafile).endswith(".npz") else str(datafile) + ".npz"
+
+    def _save_cache(self):
+        y = getattr(self, "y_stack", None)
+        np.savez(self._cache_name(self.datafile), x_stack=self.x_stack, y_stack=self.x_stack if y is None else y, fidx=self.fidx,
+                 x_wavfiles=np.asarray(self.x_wavfiles or [], dtype=str), y_wavfiles=np.asarray(self.y_wavfiles or [], dtype=str),
+                 stft_N=self.params_stft["N"], stft_hop=self.params_stft["hop"])
+
+    def _load_cache(self, params_stft):
+        z = np.load(self._cache_name(self.datafile))
+        if int(z["stft_N"]) != int(params_stft["N"]) or int(z["stft_hop"]) != int(params_stft["hop"]):
+            raise ValueError("datafile '%s' was computed with a different STFT (N=%d, hop=%d)" % (self.datafile, z["stft_N"], z["stft_hop"]))
+        self.params_stft = dict(params_stft)
+        self.params_stft["window"] = sqrt_hann(self.params_stft["N"])
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.x_stack, self.y_stack, self.fidx = z["x_stack"], z["y_stack"], z["fidx"]
+        self.x_wavfiles, self.y_wavfiles = list(z["x_wavfiles"]), list(z["y_wavfiles"])
+        self.x_stack_dev = torch.as_tensor(self.x_stack, device=dev)
+        self.y_stack_dev = torch.as_tensor(self.y_stack, device=dev)
+        self.fidx_dev = torch.as_tensor(self.fidx.astype(np.int64), device=dev)
+
+    def _from_waveforms(self, x_waveforms, y_waveforms, params_stft):
         self.params_stft = dict(params_stft)
         self.params_stft["window"] = sqrt_hann(self.params_stft["N"])            # audio_dataset.py:194
         N, hop = self.params_stft["N"], self.params_stft["hop"]
@@ -90,8 +138,15 @@ class AudioDataset:
         self.x_stack = self.x_stack_dev.cpu().numpy()                             # (2F, total frames), util.py:351
         self.fidx = self.fidx_dev.cpu().numpy().astype(np.int32)                  # (n_files, 2), util.py:335-337
         if y_waveforms is not None:
-            self.y_stack_dev, self.y_mag_dev, _ = stacks(y_waveforms)
+            self.y_stack_dev, self.y_mag_dev, yfidx_dev = stacks(y_waveforms)
             self.y_stack = self.y_stack_dev.cpu().numpy()
+            yfidx = yfidx_dev.cpu().numpy().astype(np.int32)
+            if not np.array_equal(yfidx, self.fidx):                              # audio_dataset.py:232-241
+                if not np.all(self.fidx[:, 1] - self.fidx[:, 0] >= yfidx[:, 1] - yfidx[:, 0]):
+                    raise ValueError("Not all input files have greater than or equal length to all output files!")
+                self.x_stack = clip_x_to_y(self.x_stack, self.y_stack, self.fidx, yfidx)
+                self.x_stack_dev = torch.as_tensor(self.x_stack, device=dev)
+                self.fidx, self.fidx_dev = yfidx, yfidx_dev
 
     def _reconstruct(self, stack_dev, idx, mask):
         N, hop = self.params_stft["N"], self.params_stft["hop"]

@@ -363,6 +363,25 @@ int drnmf_snmf_mu_ed_dist(int F, int n, int R, const float* V, float* W, float* 
   return DRNMF_OK;
 }
 
+size_t drnmf_snmf_irm_workspace_bytes(int F, int n, int R) {
+  if (F < 1 || n < 1 || R < 2) return 0;
+  return snmf_irm_workspace_bytes(F, n, R);
+}
+
+int drnmf_snmf_irm(int F, int n, int R, int r, const float* W, const float* H, float* irm, int flags, void* ws, size_t ws_bytes,
+                   void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  DRNMF_CHECK(W && H && irm && ws && F >= 1 && n >= 1 && R >= 2 && r >= 1 && r < R, "drnmf_snmf_irm: bad arguments");
+  DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = snmf_irm(F, n, R, r, W, H, irm, ws, ws_bytes, pick_impl(flags) == DRNMF_IMPL_SIMT, st);
+  if (rc) return rc;
+  int g = gemm_device_error(st);
+  if (g) { set_error("drnmf_snmf_irm: device-side failure code %d in a GEMM kernel", g); return DRNMF_ERR_DEVICE; }
+  return DRNMF_OK;
+}
+
 size_t drnmf_ista_workspace_bytes(int F, int n, int R) {
   if (F < 1 || n < 1 || R < 1) return 0;
   return ista_workspace_bytes(F, n, R);
@@ -392,6 +411,26 @@ int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
                          double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream) {
   return drnmf_loss_and_grads_cb(h, x, y, B, T, mask_value, g_log_D, g_log_alph, g_log_lam1, g_log_h0, g_k_clean, g_k_noise,
                                  loss_host, irm, ws, ws_bytes, stream, nullptr, nullptr);
+}
+
+int drnmf_set_training_loss(drnmf_handle* h, int kind, float lam1) {
+  DRNMF_CHECK(h, "NULL handle");
+  DRNMF_CHECK(kind == 0 || kind == 1, "drnmf_set_training_loss: kind must be 0 (mse_of_masked) or 1 (snmf pretraining cost)");
+  h->loss_kind = kind; h->loss_lam1 = lam1;
+  return DRNMF_OK;
+}
+
+int drnmf_forward_all_hidden(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H_all, void* ws,
+                             size_t ws_bytes, void* stream) {
+  DRNMF_CHECK(h, "NULL handle");
+  int rc = check_device(h);
+  if (rc) return rc;
+  DRNMF_CHECK(h->params_set, "drnmf_forward_all_hidden before drnmf_set_params");
+  DRNMF_CHECK(x && H_all && ws && B >= 1 && T >= 1, "drnmf_forward_all_hidden: bad arguments");
+  DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = forward_all_hidden(h, x, B, T, mask_value, H_all, ws, ws_bytes, st))) return rc;
+  return h->impl != DRNMF_IMPL_SIMT ? check_dev_error(h, st, "drnmf_forward_all_hidden") : DRNMF_OK;
 }
 
 int drnmf_adam_step(float* params, const float* grads, float* m, float* v, const uint8_t* trainable, size_t n, float lr_t,

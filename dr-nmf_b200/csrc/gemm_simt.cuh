@@ -59,9 +59,11 @@ __device__ __forceinline__ float epi_gram_value(int m, int n, int R_valid, float
   if (m >= R_valid || n >= R_valid) return 0.f;
   return ((m == n) ? 1.f : 0.f) - acc;
 }
-// DivideAbyAplusB (custom_layers.py:41-45): exp(log(1e-7 + A) - log(1e-7 + A + B)), optional 'square' transform.
-__device__ __forceinline__ float epi_irm_value(float s, float n, int square) {
-  if (square) { s *= s; n *= n; }
+// DivideAbyAplusB (custom_layers.py:41-45): exp(log(1e-7 + A) - log(1e-7 + A + B)), optional 'square' transform (mode 1).
+// mode 2: the SNMF baseline's ratio mask  A / (1e-9 + A + B)  (enhance.py:848-852).
+__device__ __forceinline__ float epi_irm_value(float s, float n, int mode) {
+  if (mode == 2) return s / (1e-9f + s + n);
+  if (mode == 1) { s *= s; n *= n; }
   return expf(logf(1e-7f + s) - logf(1e-7f + s + n));
 }
 

@@ -36,6 +36,8 @@ struct drnmf_handle {
   int rec_cfg[8];          // NB, KS, MT, ATOMS, n_tiles, WST, HST, RST of the last persistent launch
   int rec_groups;          // batch groups (grid.z) of the last persistent launch
   int bwd_cfg[8], bwd_groups;   // the same for the backward chain of the last drnmf_loss_and_grads
+  int loss_kind;           // 0 = 'mse_of_masked' (enhance.py:1040-1047), 1 = SNMF pretraining cost (enhance.py:1024-1036)
+  float loss_lam1;         // lam1 of the pretraining cost
 };
 
 namespace drnmf {
@@ -108,6 +110,9 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
                int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
                double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st,
                drnmf_allreduce_fn allreduce, void* user);
+size_t snmf_irm_workspace_bytes(int F, int n, int R);
+int snmf_irm(int F, int n, int R, int r, const float* W, const float* H, float* irm, void* ws, size_t ws_bytes, bool simt,
+             cudaStream_t st);
 size_t ista_workspace_bytes(int F, int n, int R);
 int ista_ed(int F, int n, int R, const float* x, const float* W, float* H, float lam1, float alph, int iters, void* ws,
             size_t ws_bytes, bool simt, cudaStream_t st);
@@ -117,6 +122,8 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
                          float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean, float* g_k_noise,
                          double* loss_host, float* irm_out, void* ws, size_t ws_bytes, cudaStream_t st,
                          drnmf_layer_fn layer_cb, void* cb_user);
+int forward_all_hidden(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H_all, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, const uint8_t* trainable, size_t n, float lr_t, float b1, float b2,
                 float eps, float gscale, cudaStream_t st);
 int launch_init_state(const drnmf_handle* h, FwdWorkspace& w, cudaStream_t st);

@@ -428,4 +428,60 @@ int ista_ed(int F, int n, int R, const float* x, const float* W, float* H, float
   return DRNMF_OK;
 }
 
+// ---- SNMF ratio mask (enhance.py:847-852): irm = S^/(1e-9 + S^ + N^), S^ = W[:, :r] H[:r], N^ = W[:, r:] H[r:] -------------
+// One dual-B GEMM with the ratio epilogue: A = W (F x Rp, K-major over the atoms), B = H_clean^T, B2 = H_noise^T
+// (n x Rp, the other source's columns zeroed), C = irm (F x n).
+// H (R x n) -> HcT / HnT (np x Rp) hi | lo: 32 x 32 tiled transpose
+__global__ void k_irm_prep_h(const float* __restrict__ H, int R, int r, int n, int Rp, float* __restrict__ HcT_hi,
+                             float* __restrict__ HcT_lo, float* __restrict__ HnT_hi, float* __restrict__ HnT_lo) {
+  __shared__ float tile[32][33];
+  const int j0 = blockIdx.y * 32, c0 = blockIdx.x * 32;       // atoms, frames
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int j = j0 + y, c = c0 + threadIdx.x;
+    tile[y][threadIdx.x] = (j < R && c < n) ? H[(size_t)j * n + c] : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    const int c = c0 + y, j = j0 + threadIdx.x;
+    if (j >= Rp) continue;
+    const float v = tile[threadIdx.x][y];
+    const float vc = (j < r) ? v : 0.f, vn = (j >= r && j < R) ? v : 0.f;
+    const size_t o = (size_t)c * Rp + j;
+    HcT_hi[o] = vc; HcT_lo[o] = tf32_lo(vc); HnT_hi[o] = vn; HnT_lo[o] = tf32_lo(vn);
+  }
+}
+__global__ void k_irm_prep_w(const float* __restrict__ W, int F, int R, int Rp, float* __restrict__ A_hi, float* __restrict__ A_lo) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)F * Rp) return;
+  const int f = (int)(idx / Rp), j = (int)(idx % Rp);
+  const float v = j < R ? W[(size_t)f * R + j] : 0.f;
+  A_hi[idx] = v; A_lo[idx] = tf32_lo(v);
+}
+
+size_t snmf_irm_workspace_bytes(int F, int n, int R) {
+  const size_t Rp = round_up(R, 32), np_ = round_up(n, 128);
+  return 4 * round_up_sz(np_ * Rp * 4, 256) + 2 * round_up_sz((size_t)F * Rp * 4, 256);
+}
+
+int snmf_irm(int F, int n, int R, int r, const float* W, const float* H, float* irm, void* ws, size_t ws_bytes, bool simt,
+             cudaStream_t st) {
+  const size_t need = snmf_irm_workspace_bytes(F, n, R);
+  if (ws_bytes < need) { set_error("snmf_irm workspace too small: need %zu bytes, got %zu", need, ws_bytes); return DRNMF_ERR_WORKSPACE; }
+  const int Rp = round_up(R, 32);
+  const size_t np_ = round_up(n, 128), hb = round_up_sz(np_ * Rp * 4, 256), wb = round_up_sz((size_t)F * Rp * 4, 256);
+  uint8_t* p = (uint8_t*)ws;
+  float *HcT_hi = (float*)p, *HcT_lo = (float*)(p + hb), *HnT_hi = (float*)(p + 2 * hb), *HnT_lo = (float*)(p + 3 * hb);
+  float *A_hi = (float*)(p + 4 * hb), *A_lo = (float*)(p + 4 * hb + wb);
+  k_irm_prep_h<<<dim3((unsigned)(np_ / 32), (Rp + 31) / 32), dim3(32, 8), 0, st>>>(H, R, r, n, Rp, HcT_hi, HcT_lo, HnT_hi, HnT_lo);
+  k_irm_prep_w<<<(unsigned)(((size_t)F * Rp + 255) / 256), 256, 0, st>>>(W, F, R, Rp, A_hi, A_lo);
+  count_launch(2);
+  DRNMF_CUDA(cudaGetLastError());
+  GemmArgs a{};
+  a.A_hi = A_hi; a.A_lo = A_lo; a.lda = Rp;
+  a.B_hi = HcT_hi; a.B_lo = HcT_lo; a.B2_hi = HnT_hi; a.B2_lo = HnT_lo; a.ldb = Rp;
+  a.M = F; a.N = n; a.Kd = Rp; a.C = irm; a.ldc = n; a.M_valid = F; a.N_valid = n;
+  a.square = 2;                       // ratio epilogue S / (1e-9 + S + N)
+  return simt ? launch_gemm_simt(EPI_RECON, a, st) : launch_gemm_tc(EPI_RECON, a, st);
+}
+
 }  // namespace drnmf

@@ -84,9 +84,11 @@ size_t train_workspace_bytes(const drnmf_handle* h, int B, int T) { return carve
 // One warp per frame (b,t): err = x*irm - y ; L += m * mean_f err^2 ; dirm = m * 2 err x / F ;
 // irm = A/Bq with A = eps + S', Bq = eps + S' + N' (S' = S or S^2): dS' = dirm * N'/Bq^2, dN' = -dirm * A/Bq^2.
 // Writes [dS|dN] frame-major (hi, lo) and transposed time-major (hi, lo).
+// kind 1 = SNMF pretraining cost (enhance.py:1024-1036): 0.5 * mean_f (S + N - x)^2 per frame (the l1 term on H is added
+// by k_l1_head); dS = dN = (S + N - x) / F.
 __global__ void k_loss_head(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ S,
                             const float* __restrict__ N, const float* __restrict__ mvalid, int B, int T, int Bp, int F,
-                            int Fp, int square, float* __restrict__ dSN_hi, float* __restrict__ dSN_lo,
+                            int Fp, int square, int kind, float* __restrict__ dSN_hi, float* __restrict__ dSN_lo,
                             float* __restrict__ dSNT_hi, float* __restrict__ dSNT_lo, double* __restrict__ loss_part) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -104,6 +106,11 @@ __global__ void k_loss_head(const float* __restrict__ x, const float* __restrict
         const size_t o = (size_t)row * F + f;
         float s = S[o], n = N[o];
         const float s0 = s, n0 = n;
+        if (kind == 1) {
+          const float err = s + n - x[o];
+          acc = fmaf(0.5f * err, err, acc);
+          dS = err / (float)F; dN = dS;
+        } else {
         if (square) { s *= s; n *= n; }
         const float A = 1e-7f + s, Bq = A + n;
         const float irm = expf(logf(A) - logf(Bq));
@@ -113,6 +120,7 @@ __global__ void k_loss_head(const float* __restrict__ x, const float* __restrict
         dS = dirm * n / (Bq * Bq);
         dN = -dirm * A / (Bq * Bq);
         if (square) { dS *= 2.f * s0; dN *= 2.f * n0; }
+        }
       }
       const size_t o2 = (size_t)row * (2 * Fp);
       dSN_hi[o2 + f] = dS; dSN_lo[o2 + f] = tf32_lo(dS);
@@ -131,6 +139,31 @@ __global__ void k_loss_head(const float* __restrict__ x, const float* __restrict
     loss_part[2 * (size_t)blockIdx.x] = a; loss_part[2 * (size_t)blockIdx.x + 1] = c;
   }
 }
+
+// l1 term of the SNMF pretraining cost: per valid frame  lam1 * (R/F) * mean_j |H_j| = (lam1/F) * sum_j H_j  (H >= 0);
+// dH[bt][j] += (lam1/F) [H_j > 0].  One warp per frame; per-block partial sums go to loss_part (pairs: value, 0).
+__global__ void k_l1_head(const float* __restrict__ H, const float* __restrict__ mvalid, int BT, int R, int Rp, float coef,
+                          float* __restrict__ dH, double* __restrict__ loss_part) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  __shared__ double red[8];
+  float sum = 0.f;
+  if (row < BT && mvalid[row] != 0.f) {
+    for (int j = lane; j < R; j += 32) {
+      const float h = H[(size_t)row * Rp + j];
+      sum += h;
+      if (h > 0.f) dH[(size_t)row * Rp + j] += coef;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  }
+  if (lane == 0) red[threadIdx.x >> 5] = (double)sum * coef;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < 8; ++w) a += red[w];
+    loss_part[2 * (size_t)blockIdx.x] = a; loss_part[2 * (size_t)blockIdx.x + 1] = 0.0;
+  }
+}
+__global__ void k_add_scal(double* __restrict__ scal) { scal[0] += scal[2]; }
 
 __global__ void k_reduce_pairs(const double* __restrict__ part, int n, double* __restrict__ out) {
   __shared__ double ra[256], rb[256];
@@ -484,7 +517,7 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   DRNMF_CUDA(cudaMemsetAsync(w.dSNT_hi, 0, (size_t)2 * Fp * TB * 4, st));
   DRNMF_CUDA(cudaMemsetAsync(w.dSNT_lo, 0, (size_t)2 * Fp * TB * 4, st));
   const int nblk = (BT + 7) / 8;
-  k_loss_head<<<nblk, 256, 0, st>>>(x, y, w.S, w.N, w.fwd.mvalid, B, T, Bp, F, Fp, sq, w.dSN_hi, w.dSN_lo, w.dSNT_hi, w.dSNT_lo, w.loss_part);
+  k_loss_head<<<nblk, 256, 0, st>>>(x, y, w.S, w.N, w.fwd.mvalid, B, T, Bp, F, Fp, sq, h->loss_kind, w.dSN_hi, w.dSN_lo, w.dSNT_hi, w.dSNT_lo, w.loss_part);
   k_reduce_pairs<<<1, 256, 0, st>>>(w.loss_part, nblk, w.scal);
   count_launch(2);
   {   // dH = [dS | dN] . EcB^T   (BT x Rp)
@@ -493,6 +526,12 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
     a.B_hi = h->EcB_hi; a.B_lo = h->EcB_lo; a.ldb = 2 * Fp;
     a.M = BT; a.N = Rp; a.Kd = 2 * Fp; a.C = w.dH; a.ldc = Rp; a.M_valid = BT; a.N_valid = Rp;
     if ((rc = gemm(h, EPI_STORE, a, st))) return rc;
+  }
+  if (h->loss_kind == 1) {   // + lam1 * (R/F) * mean_j |H_j| per frame and its gradient into dH
+    k_l1_head<<<nblk, 256, 0, st>>>(w.fwd.Hp_hi, w.fwd.mvalid, BT, R, Rp, h->loss_lam1 / (float)F, w.dH, w.loss_part);
+    k_reduce_pairs<<<1, 256, 0, st>>>(w.loss_part, nblk, w.scal + 2);
+    k_add_scal<<<1, 1, 0, st>>>(w.scal);
+    count_launch(3);
   }
   k_xT<<<dim3((unsigned)(TB / 32), w.Fx / 32), tb, 0, st>>>(w.fwd.xp_hi, B, T, Bp, F, Fp, w.Fx, w.xT_hi, w.xT_lo);
   count_launch();
@@ -591,6 +630,48 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   }
   DRNMF_CUDA(cudaMemcpyAsync(loss_host, w.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   DRNMF_CUDA(cudaStreamSynchronize(st));
+  DRNMF_CUDA(cudaGetLastError());
+  return DRNMF_OK;
+}
+
+// ---- flag_return_all_hidden (custom_layers.py:178-181, 371-374): the concatenated hidden vectors of all K layers ----------
+// Keras' masked scan carries the whole output vector over masked frames (zeros before the first valid one).
+// actT: K x Rp x (T*Bp) time-major activations of the forward pass.  One thread per (b, k, j), sequential over t.
+__global__ void k_gather_all_hidden(const float* __restrict__ actT, const float* __restrict__ mvalid, int B, int T, int Bp, int K,
+                                    int R, int Rp, float* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * K * R) return;
+  const int j = (int)(idx % R), k = (int)((idx / R) % K), b = (int)(idx / ((size_t)R * K));
+  const float* src = actT + ((size_t)k * Rp + j) * ((size_t)T * Bp) + b;
+  float prev = 0.f;
+  for (int t = 0; t < T; ++t) {
+    if (mvalid[(size_t)b * T + t] != 0.f) prev = src[(size_t)t * Bp];
+    out[((size_t)b * T + t) * ((size_t)K * R) + (size_t)k * R + j] = prev;
+  }
+}
+
+int forward_all_hidden(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H_all, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+  TrainWs w = carve_train(h, B, T, ws);
+  if (ws_bytes < w.bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
+  const int K = h->K, Rp = h->Rp, Fp = h->Fp, BT = B * T;
+  const size_t TB = (size_t)w.TB;
+  int rc;
+  DRNMF_CUDA(cudaMemsetAsync(w.fwd.actT_hi, 0, (size_t)K * Rp * TB * 4, st));
+  DRNMF_CUDA(cudaMemsetAsync(w.fwd.actT_lo, 0, (size_t)K * Rp * TB * 4, st));
+  if ((rc = launch_mask_pad(h, x, BT, mask_value, w.fwd, st))) return rc;
+  {
+    GemmArgs a{};
+    a.A_hi = w.fwd.xp_hi; a.A_lo = w.fwd.xp_lo; a.lda = Fp;
+    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = Fp;
+    a.M = BT; a.N = K * Rp; a.Kd = Fp; a.C = w.fwd.XW; a.ldc = K * Rp; a.M_valid = BT; a.N_valid = a.N; a.bias = h->bias;
+    if ((rc = gemm(h, EPI_STORE, a, st))) return rc;
+  }
+  rc = (h->impl == DRNMF_IMPL_SIMT) ? launch_recurrent_simt(h, w.fwd, B, T, nullptr, st) : launch_recurrent_tc(h, w.fwd, B, T, nullptr, st);
+  if (rc) return rc;
+  const size_t n = (size_t)B * K * h->R;
+  k_gather_all_hidden<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.fwd.actT_hi, w.fwd.mvalid, B, T, w.fwd.Bp, K, h->R, Rp, H_all);
+  count_launch();
   DRNMF_CUDA(cudaGetLastError());
   return DRNMF_OK;
 }

@@ -45,8 +45,9 @@ class SimpleDeepRNN:
         if activation != "relu" or not flag_connect_input_to_layers or not flag_nonnegative:
             raise NotImplementedError("only the DR-NMF configuration is implemented: activation='relu', "
                                       "flag_connect_input_to_layers=True, flag_nonnegative=True (enhance.py:257-266)")
-        if dropout_W or dropout_U or flag_return_all_hidden or W_regularizer or U_regularizer or b_regularizer:
-            raise NotImplementedError("dropout / regularizers / flag_return_all_hidden are off the shipped path")
+        if dropout_W or dropout_U or W_regularizer or U_regularizer or b_regularizer:
+            raise NotImplementedError("dropout / regularizers are off the shipped path")
+        self.flag_return_all_hidden = bool(flag_return_all_hidden)
         if not self.return_sequences:
             raise NotImplementedError("return_sequences=False is not used by the DR-NMF path")
         self.built = False
@@ -54,7 +55,8 @@ class SimpleDeepRNN:
         self.log_h0 = None
 
     def compute_output_shape(self, input_shape):
-        return (input_shape[0], input_shape[1], self.units)
+        units = self.K_layers * self.units if self.flag_return_all_hidden else self.units      # custom_layers.py:176-181
+        return (input_shape[0], input_shape[1], units)
 
     def build(self, input_shape, recon=None):
         """custom_layers.py:187-294.  Like the reference, the numpy arrays in `alt_params` are replaced IN PLACE by

@@ -207,6 +207,23 @@ class DrnmfEngine:
         res = (float(loss[0]), float(loss[1]), g)
         return res + (irm,) if want_irm else res
 
+    def set_training_loss(self, kind="mse_of_masked", lam1=0.0):
+        """'mse_of_masked' (enhance.py:1040-1047) or 'snmf_cost' = the optional pretraining objective of enhance.py:1024-1036."""
+        kinds = {"mse_of_masked": 0, "snmf_cost": 1}
+        if kind not in kinds:
+            raise ValueError("Unknown 'loss' of '%s'" % kind)        # the reference constructs and drops this error
+        _lib.check(self.lib.drnmf_set_training_loss(self.h, kinds[kind], float(lam1)))
+
+    def forward_all_hidden(self, x, mask_value=-1.0):
+        """flag_return_all_hidden (custom_layers.py:371-374): (B,T,K*R) hidden vectors of all layers, layer-major."""
+        x = x.contiguous()
+        B, T, F = x.shape
+        out = torch.empty((B, T, self.K * self.R), dtype=torch.float32, device=x.device)
+        need = self.lib.drnmf_train_workspace_bytes(self.h, B, T)
+        ws, wsb = self._workspace(need, "_tws")
+        _lib.check(self.lib.drnmf_forward_all_hidden(self.h, _ptr(x), B, T, float(mask_value), _ptr(out), ws, wsb, _stream()))
+        return out
+
     def adam_step(self, params, grads, m, v, lr_t, beta_1=0.9, beta_2=0.999, epsilon=1e-8, grad_scale=1.0, trainable=None):
         """Fused Keras-formula Adam on flat float32 CUDA buffers (drnmf_adam_step); `trainable`: uint8 mask or None."""
         n = params.numel()
@@ -387,6 +404,24 @@ def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_updat
                                          C.byref(iters), flags, C.c_void_p(ws.data_ptr() + off), nb, _stream(), cb, None))
     k = iters.value
     return cost[:k].copy(), div[:k].copy()
+
+
+def snmf_irm(W, H, r, impl=None):
+    """enhance.py:847-852 on the GPU: W (F,R), H (R,n) float32 CUDA tensors -> irm (F,n) = S^/(1e-9 + S^ + N^)."""
+    _require_cuda()
+    lib = _lib.load()
+    W, H = W.contiguous(), H.contiguous()
+    F, R = W.shape
+    n = H.shape[1]
+    if H.shape[0] != R or n % 4 != 0:
+        raise ValueError("H must be (R, n) with n a multiple of 4 (16-byte rows); pad with zero frames")
+    out = torch.empty((F, n), dtype=torch.float32, device=W.device)
+    nb = lib.drnmf_snmf_irm_workspace_bytes(F, n, R)
+    ws = torch.empty(nb + 256, dtype=torch.uint8, device=W.device)
+    off = (-ws.data_ptr()) % 256
+    _lib.check(lib.drnmf_snmf_irm(F, n, R, int(r), _ptr(W), _ptr(H), _ptr(out), _lib.IMPL_SIMT if impl == "simt" else 0,
+                                  C.c_void_p(ws.data_ptr() + off), nb, _stream()))
+    return out
 
 
 def ista_ed(x, W, H, lam1, alph, K, impl=None):

@@ -93,10 +93,25 @@ class UnfoldedSNMFModel:
         xt = x if torch.is_tensor(x) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
         xt = xt.to(eng.device, torch.float32)
         H, irm = eng.forward(xt, self.mask_value, want_H=return_hidden)
+        if return_hidden and self.rnn.flag_return_all_hidden:      # the layer's output is the concatenation of all layers
+            H = eng.forward_all_hidden(xt, self.mask_value)
         if torch.is_tensor(x):
             return (irm, H) if return_hidden else irm
         irm = irm.cpu().numpy()
         return (irm, H.cpu().numpy()) if return_hidden else irm
+
+    def fit_pretrain(self, x, lam1, batch_size=32, epochs=1, validation_data=None, learning_rate=1e-3, clipnorm=0.0,
+                     decay=0.0, patience=50, savefile=None, verbose=0):
+        """Optional pretraining with the SNMF cost (enhance.py:1024-1036, 1088-1120): model_pretrain.fit(x, [x, x], ...)
+        with losses ['mse' of x_recon = S^ + N^, l1 of the hidden output] and weights [0.5, lam1 * 2r / F]."""
+        from .training import Trainer
+        tr = Trainer(self, learning_rate=learning_rate, clipnorm=clipnorm, decay=decay, loss="snmf_cost", lam1=lam1)
+        vd = None if validation_data is None else (validation_data, validation_data)
+        try:
+            return tr.fit(x, x, batch_size=batch_size, epochs=epochs, validation_data=vd, patience=patience, savefile=savefile,
+                          verbose=verbose)
+        finally:
+            self._engine_ready().set_training_loss("mse_of_masked")
 
     def fit(self, x, y, sample_weight=None, batch_size=32, epochs=1, validation_data=None, learning_rate=1e-3,
             clipnorm=0.0, decay=0.0, patience=50, savefile=None, verbose=0):
@@ -132,7 +147,8 @@ def build_unfolded_snmf(params_unfolded_snmf):
         keys_trainable += [name + ("_%d" % k) for k in range(K_layers)] if name in params_untied else [name]
     rnn = SimpleDeepRNN(hidden_dim, input_shape=(p["maxseq"], input_dim), return_sequences=True, activation="relu",
                         K_layers=K_layers, alt_params=alt_params, keys_trainable=keys_trainable,
-                        maps_from_alt=maps_from_alt, flag_connect_input_to_layers=True, flag_nonnegative=True)
+                        maps_from_alt=maps_from_alt, flag_connect_input_to_layers=True, flag_nonnegative=True,
+                        flag_return_all_hidden=bool(p.get("flag_return_all_hidden", False)))
     rnn.build((None, p["maxseq"], input_dim))
     r = hidden_dim // 2
     log_W_clean = np.log(1e-7 + W_noisy[:, :r])

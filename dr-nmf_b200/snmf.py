@@ -177,11 +177,15 @@ def snmf_infer(x_frames, W_noisy, params_snmf, max_iter=200, verbose=False):
 
 
 def snmf_irm(W_noisy, H, r):
-    """enhance.py:847-852: irm = S^ / (1e-9 + S^ + N^) with S^ = W_clean H_clean, N^ = W_noise H_noise (two plain
-    GEMMs on the device).  W_noisy (F, 2r), H (2r, n) -> (F, n) float32 numpy array."""
+    """enhance.py:847-852: irm = S^ / (1e-9 + S^ + N^) with S^ = W_clean H_clean, N^ = W_noise H_noise, as ONE dual-operand
+    tcgen05 GEMM with the ratio in its epilogue (drnmf_snmf_irm).  W_noisy (F, 2r), H (2r, n) -> (F, n) float32 numpy."""
+    from . import engine as _engine
     dev = torch.device("cuda", torch.cuda.current_device())
     Wd = torch.as_tensor(np.ascontiguousarray(W_noisy, dtype=np.float32), device=dev)
-    Hd = torch.as_tensor(np.ascontiguousarray(H, dtype=np.float32), device=dev)
-    clean = Wd[:, :r] @ Hd[:r]
-    noise = Wd[:, r:] @ Hd[r:]
-    return (clean / (1e-9 + clean + noise)).cpu().numpy()
+    Hn = np.ascontiguousarray(H, dtype=np.float32)
+    n = Hn.shape[1]
+    pad = (-n) % 4
+    if pad:
+        Hn = np.concatenate([Hn, np.zeros((Hn.shape[0], pad), np.float32)], axis=1)
+    irm = _engine.snmf_irm(Wd, torch.as_tensor(Hn, device=dev), r)
+    return irm[:, :n].cpu().numpy()

@@ -204,8 +204,9 @@ class Trainer:
     """model: enhance.UnfoldedSNMFModel.  Trainable tensors follow the reference: keys_trainable of the RNN layer
     (log_D_k, log_alph_k in the shipped configs), log_h0, and the two DenseNonNegW kernels (enhance.py:283,292)."""
 
-    def __init__(self, model, learning_rate=1e-3, clipnorm=0.0, decay=0.0, group=None):
+    def __init__(self, model, learning_rate=1e-3, clipnorm=0.0, decay=0.0, group=None, loss="mse_of_masked", lam1=0.0):
         self.model, self.group = model, group
+        self.loss, self.lam1 = loss, lam1             # 'mse_of_masked' | 'snmf_cost' (enhance.py:1024-1047)
         self.opt = Adam(lr=learning_rate, clipnorm=clipnorm, decay=decay)
 
     # ---- mapping between the engine's stacked gradients and the model's named tensors -------------------------------
@@ -249,6 +250,7 @@ class Trainer:
         dev = eng.device
         xt = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(dev) if not torch.is_tensor(x) else x
         yt = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float32)).to(dev) if not torch.is_tensor(y) else y
+        eng.set_training_loss(self.loss, self.lam1)
         ls, ms, g = eng.loss_and_grads(xt, yt, self.model.mask_value)
         loss, grads = allreduce_grads(self._named_grads(g), ls, ms, self.group)
         self.opt.step(self._named_params(), grads)
@@ -261,6 +263,7 @@ class Trainer:
         for s in range(0, len(x), batch_size):
             xb = torch.as_tensor(np.ascontiguousarray(x[s:s + batch_size], dtype=np.float32)).to(eng.device)
             yb = torch.as_tensor(np.ascontiguousarray(y[s:s + batch_size], dtype=np.float32)).to(eng.device)
+            eng.set_training_loss(self.loss, self.lam1)
             ls, ms, _ = eng.loss_and_grads(xb, yb, self.model.mask_value)
             tot += ls; cnt += ms
         stats = torch.tensor([tot, cnt], dtype=torch.float64, device=eng.device)

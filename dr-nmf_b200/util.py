@@ -65,3 +65,37 @@ def masked_seqs_to_frames(x, mask):
     xr = np.reshape(x.transpose((2, 0, 1)), (n_feature, n_examples * time_steps))
     m = np.reshape(mask.transpose((2, 0, 1)), (n_examples * time_steps,))
     return xr[:, np.where(m == m[0])[0]]
+
+
+def wavread(wavfile):
+    """util.py:29-35: int16 wav -> float32 (nch, nsampl) scaled by 1/32768 (a list argument means its first entry)."""
+    import scipy.io.wavfile
+    if isinstance(wavfile, list):
+        wavfile = wavfile[0]
+    fs, x = scipy.io.wavfile.read(wavfile)
+    x = np.transpose(x).astype(np.float32) / np.float32(32768.0)
+    return x.reshape(1, -1) if x.ndim == 1 else x
+
+
+def wavwrite(wavfile, fs, x):
+    """util.py:37-45: x (nch, nsampl); float32 data is peak-normalised only when it clips, then cast to int16 (x * 32767)."""
+    import scipy.io.wavfile
+    x = np.asarray(x)
+    if x.dtype == np.float32:
+        mx = np.max(np.abs(x)) if x.size else 0.0
+        if mx > 1:
+            x = x / mx
+        x = np.int16(x * 32767.0)
+    scipy.io.wavfile.write(wavfile, fs, x.T)
+
+
+def compute_STFTs(wavfiles, params_stft):
+    """util.py:327-352: [Re;Im] stack (2F, total frames) of all files (first `nch` channels... here channel 0, as
+    params_stft['nch'] = 1 in every shipped config) and the (n_files, 2) frame index table, computed by the CUDA STFT."""
+    waves = [wavread(f)[0] for f in wavfiles]
+    lens = [len(w) for w in waves]
+    offs = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    audio = torch.as_tensor(np.concatenate(waves).astype(np.float32), device=dev)
+    stack, _, fidx = _engine.stft_mag(audio, list(offs), lens, int(params_stft["N"]), int(params_stft["hop"]), want_mag=False)
+    return stack.cpu().numpy(), fidx.cpu().numpy().astype(np.int32)

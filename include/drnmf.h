@@ -148,6 +148,13 @@ DRNMF_API int drnmf_snmf_mu_ed_dist(int F, int n, int R, const float* V, float* 
                           double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream,
                           drnmf_allreduce_fn allreduce, void* user);
 
+/* ---- SNMF baseline ratio mask (enhance.py:847-852): irm = S^ / (1e-9 + S^ + N^) with S^ = W[:, :r] H[:r],
+ * N^ = W[:, r:] H[r:].  W (F,R), H (R,n), irm (F,n) row-major device arrays.  One dual-operand tcgen05 GEMM with the ratio
+ * fused into its epilogue (the reference: two np.dot and an elementwise divide on the host). */
+DRNMF_API int drnmf_snmf_irm(int F, int n, int R, int r, const float* W, const float* H, float* irm, int flags, void* ws,
+                   size_t ws_bytes, void* stream);
+DRNMF_API size_t drnmf_snmf_irm_workspace_bytes(int F, int n, int R);
+
 /* ---- frame-parallel ISTA with a tied dictionary (enhance.py:402-418 `ista_ed`; defined but never called there) ---
  * x (F,n), W (F,R), H (R,n) in/out, row-major device arrays: H <- max(0, -lam1/alph + H + (1/alph) W^T (x - W H)),
  * `iters` times.  n must be a multiple of 4. */
@@ -167,6 +174,17 @@ DRNMF_API int drnmf_loss_and_grads(drnmf_handle* h, const float* x, const float*
                          float* g_log_D, float* g_log_alph, float* g_log_lam1, float* g_log_h0, float* g_k_clean,
                          float* g_k_noise, double* loss_host, float* irm, void* ws, size_t ws_bytes, void* stream);
 DRNMF_API size_t drnmf_train_workspace_bytes(const drnmf_handle* h, int B, int T);
+
+/* Training objective of drnmf_loss_and_grads*: kind 0 = 'mse_of_masked' (enhance.py:1040-1047, the default);
+ * kind 1 = the optional SNMF pretraining cost of enhance.py:1024-1036 (two-output model, loss weights [0.5, lam1 2r/F]):
+ * per valid frame 0.5 mean_f (S^ + N^ - x)^2 + lam1 (R/F) mean_j |H_j|; `y` is ignored (the reference passes x twice). */
+DRNMF_API int drnmf_set_training_loss(drnmf_handle* h, int kind, float lam1);
+
+/* SimpleDeepRNN(flag_return_all_hidden=True) (custom_layers.py:178-181, 371-374): H_all (B,T,K*R) = the hidden vectors
+ * of all K layers of every frame, concatenated layer-major; masked frames carry the previous frame's vector (Keras
+ * masked scan).  Workspace: drnmf_train_workspace_bytes(h, B, T). */
+DRNMF_API int drnmf_forward_all_hidden(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H_all,
+                             void* ws, size_t ws_bytes, void* stream);
 
 /* Data-parallel variant: `layer_ready(user, k, stream)` is called on the host right after the kernels that produce the
  * gradients of layer k (g_log_D[k], g_log_alph[k], g_log_lam1[k]; k = 0 .. K-1 in order) have been enqueued on `stream`,

@@ -9,6 +9,8 @@ oracle / torch.autograd on the float64 oracle -- no transitive argument through 
 
 Tolerances: north_star (1e-4 on H and the mask, Frobenius and max-abs/max); gradients 2e-4.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -233,3 +235,86 @@ def test_trainer_untied_vector_alph_config():
     model2 = enhance.build_unfolded_snmf(prm2)
     with pytest.raises(NotImplementedError):
         model2.fit(x, clean, batch_size=2, epochs=1)
+
+
+def test_pretrain_snmf_cost_grads_vs_autograd():
+    """f4: the optional SNMF pretraining objective (enhance.py:1024-1036) against torch.autograd on the float64 oracle."""
+    from oracle import torch_oracle as TO
+    F, R, K, B, T = 65, 40, 4, 5, 7
+    rng = np.random.default_rng(8)
+    p = synth.model_params(F, R, K, alph=30.0, lam1=0.5)
+    x = (np.abs(rng.standard_normal((B, T, F))) * 2).astype(np.float32)
+    x[2, 4:] = -1.0
+    lam1 = 0.7
+    loss_o, g_o, _, _ = TO.loss_and_grads(x, x, p, loss="snmf_cost", lam1=lam1)
+    eng = engine.DrnmfEngine(F, R, K)
+    eng.set_params(p)
+    eng.set_training_loss("snmf_cost", lam1)
+    xt = torch.as_tensor(x, device="cuda")
+    ls, ms, g = eng.loss_and_grads(xt, xt)
+    assert abs(ls / ms - loss_o) < 2e-5 * abs(loss_o), (ls / ms, loss_o)
+    for key in ("log_D", "log_alph", "log_lam1", "log_h0", "k_clean", "k_noise"):
+        got = g[key].cpu().numpy().reshape(g_o[key].shape) / ms
+        fro, mx = rel_err(got, g_o[key])
+        assert fro < 2e-4 and mx < 2e-4, (key, fro, mx)
+    eng.set_training_loss("mse_of_masked")
+    with pytest.raises(ValueError):
+        eng.set_training_loss("kl")
+
+
+def test_flag_return_all_hidden_vs_oracle():
+    """f4: SimpleDeepRNN(flag_return_all_hidden=True) (custom_layers.py:371-374): all K hidden vectors per frame."""
+    from oracle import torch_oracle as TO
+    from drnmf_b200 import enhance
+    F, R, K, B, T = 40, 24, 3, 4, 6
+    rng = np.random.default_rng(3)
+    p = synth.model_params(F, R, K, alph=15.0)
+    x = (np.abs(rng.standard_normal((B, T, F))) * 2).astype(np.float32)
+    x[1, 3:] = -1.0
+    x[2, 0] = -1.0
+    Hall_o = TO.forward_loss(x, x, p, return_all_hidden=True)[4].detach().numpy()
+    eng = engine.DrnmfEngine(F, R, K)
+    eng.set_params(p)
+    Hall = eng.forward_all_hidden(torch.as_tensor(x, device="cuda")).cpu().numpy()
+    assert Hall.shape == (B, T, K * R)
+    assert max(rel_err(Hall, Hall_o)) < TOL
+    np.testing.assert_array_equal(Hall[1, 3:], np.broadcast_to(Hall[1, 2], (T - 3, K * R)))
+    assert np.all(Hall[2, 0] == 0)
+    prm = {"input_dim": F, "hidden_dim": R, "output_dim": F, "mask_value": -1.0, "maxseq": T, "K_layers": K, "W": synth.dictionary(F, R),
+           "alph": 15.0, "lam1": 0.5, "params_untied": ["log_D", "log_alph"], "params_trainable": ["log_D", "log_alph"],
+           "flag_return_all_hidden": True}
+    model = enhance.build_unfolded_snmf(prm)
+    irm, Hm = model.predict_on_batch(x, return_hidden=True)
+    assert Hm.shape == (B, T, K * R) and model.rnn.compute_output_shape((B, T, F)) == (B, T, K * R)
+    hist = model.fit_pretrain(x, lam1=0.5, batch_size=2, epochs=2, learning_rate=2e-3)
+    assert len(hist["loss"]) == 2 and np.isfinite(hist["loss"]).all()
+
+
+def test_dataset_from_taskfiles_with_cache(tmp_path):
+    """f2: AudioDataset(taskfile_input, taskfile_output, datafile=...) (audio_dataset.py:177-262): wav files listed in
+    text files, int16 convention of util.wavread, stacks cached on disk and served from the cache on the second load;
+    inputs longer than their targets are clipped (clip_x_to_y)."""
+    from drnmf_b200 import audio_dataset as ad, util
+    N, hop = 128, 32
+    xs, ys = [], []
+    for i, s in enumerate((0.10, 0.07)):
+        noisy, clean = synth.utterance(i, seconds=s)
+        fx, fy = str(tmp_path / ("x%d.wav" % i)), str(tmp_path / ("y%d.wav" % i))
+        util.wavwrite(fx, 16000, np.concatenate([noisy, np.zeros(40 * i, np.float32)]).reshape(1, -1))   # second input is longer
+        util.wavwrite(fy, 16000, clean.reshape(1, -1))
+        xs.append(fx); ys.append(fy)
+    tx, ty = tmp_path / "in.txt", tmp_path / "out.txt"
+    tx.write_text("\n".join(xs) + "\n"); ty.write_text("\n".join(ys) + "\n")
+    cache = str(tmp_path / "data_train")
+    ds = ad.AudioDataset(str(tx), str(ty), datafile=cache, params_stft={"N": N, "hop": hop, "nch": 1})
+    assert os.path.isfile(cache + ".npz") and ds.x_stack.shape == ds.y_stack.shape and ds.x_stack.shape[0] == N + 2
+    win = O.sqrt_hann(N)
+    ref = O.stack_reim(O.stft_mc(util.wavread(ys[0]), N, hop, win))
+    np.testing.assert_allclose(ds.y_stack[:, ds.fidx[0, 0]:ds.fidx[0, 1]], ref, atol=3e-5)
+    ds2 = ad.AudioDataset(str(tx), str(ty), datafile=cache, params_stft={"N": N, "hop": hop, "nch": 1})    # from the cache
+    np.testing.assert_array_equal(ds2.x_stack, ds.x_stack)
+    np.testing.assert_array_equal(ds2.fidx, ds.fidx)
+    x, y, mask = ad.load_data({"transform_x": "mag", "transform_y": "mag", "maxlen": 30}, ds2)
+    assert x.shape == y.shape and int(mask.sum()) == int((ds.fidx[:, 1] - ds.fidx[:, 0]).sum())
+    with pytest.raises(ValueError):
+        ad.AudioDataset(str(tx), str(ty), datafile=cache, params_stft={"N": 256, "hop": 64, "nch": 1})

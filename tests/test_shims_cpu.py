@@ -102,4 +102,43 @@ def test_scoring_snr_and_table():
     assert 19.0 < scoring.snr_db(est, ref) < 21.0
     row, labels = scoring.compute_scores(est[:3900], ref)
     assert labels[:2] == ["SDR", "SNR"] and len(row) == len(labels) == 6
-    assert abs(row[0] - O.sdr_db(est[:3900], ref)) < 1e-9 and np.isnan(row[2:]).all()
+    assert abs(row[0] - O.sdr_db(est[:3900], ref)) < 1e-9 and np.isfinite(row[2:4]).all() and np.isnan(row[4:]).all()
+
+
+def test_wav_io_int16_convention(tmp_path):
+    """util.py:29-45: float32 -> int16 (x * 32767, peak-normalised only when clipping) -> float32 / 32768."""
+    from drnmf_b200 import util, scoring
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((1, 800)) * 0.2).astype(np.float32)
+    f = str(tmp_path / "a.wav")
+    util.wavwrite(f, 16000, x)
+    y = util.wavread(f)
+    assert y.shape == x.shape and y.dtype == np.float32
+    np.testing.assert_allclose(y, np.int16(x * 32767.0).astype(np.float32) / 32768.0)
+    np.testing.assert_allclose(y[0], scoring.wav_quantize(x[0]))
+    big = (x * 10).astype(np.float32)                       # clips: normalised by its peak first
+    util.wavwrite(f, 16000, big)
+    assert abs(np.abs(util.wavread(f)).max() - 32767.0 / 32768.0) < 1e-4
+    assert util.wavread([f]).shape == (1, 800)
+
+
+def test_segsnr_and_per_snr_aggregation():
+    """score_audio.m:209-212 / print_scores.py:84-114."""
+    from drnmf_b200 import scoring
+    rng = np.random.default_rng(1)
+    fs = 16000
+    ref = rng.standard_normal(fs)
+    est = ref + 0.1 * rng.standard_normal(fs)
+    loc, glo = scoring.snrseg(est, ref, fs)
+    assert abs(glo - scoring.snr_db(est, ref)) < 1e-9            # whole frames here: global segSNR = raw SNR
+    assert abs(loc - 20.0) < 0.5 and abs(glo - 20.0) < 0.3
+    loc2, _ = scoring.snrseg(ref, ref, fs)                       # perfect estimate: clipped at 35 dB per frame
+    assert loc2 == 35.0
+    loc3, _ = scoring.snrseg(-5 * ref, ref, fs)                  # terrible estimate: clipped at -10 dB
+    assert loc3 == -10.0
+    row, labels = scoring.compute_scores(est, ref, fs)
+    assert labels[2] == "SegSNR local" and abs(row[2] - loc) < 1e-12 and np.isnan(row[4]) and np.isnan(row[5])
+    per = {"m6dB": np.array([[1.0, 2.0, 0, 0, 0, 0], [3.0, 4.0, 0, 0, 0, 0]]), "9dB": np.array([[10.0, 20.0, 0, 0, 0, 0]])}
+    agg, latex = scoring.aggregate_scores(per, scores_to_print=("SDR", "SNR"))
+    assert agg["SDR"]["per_snr"] == {"m6dB": 2.0, "9dB": 10.0} and abs(agg["SDR"]["all"] - 14.0 / 3) < 1e-12
+    assert latex == "2.00 & 10.00 & 4.67 & 3.00 & 20.00 & 8.67 \\\\"
