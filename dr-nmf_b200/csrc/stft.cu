@@ -244,10 +244,12 @@ static StftTile stft_tile(int N, int hop) {
   t.pairs_a = t.FT / 2;
   t.pairs_s = (t.FT + t.halo + 1) / 2;
   t.N2 = (N == 512 || N == 1024) ? N / 32 : 0;            // register four-step FFT; 0 = shared-memory radix-2
-  t.WB = t.N2 ? 33 * t.N2 : N;                            // float2 per warp buffer (padded transpose tile)
+  t.WB = (t.N2 ? 33 * t.N2 : N) + 1;                      // float2 per warp buffer (padded transpose tile; +1: the pair
+                                                          // buffers start in different banks for the cross-pair store loop)
   const size_t common = sizeof(float2) * (N / 2) + sizeof(float) * N;          // twiddles + window
-  t.smem_a = 16 + common + sizeof(float) * ((size_t)(t.FT - 1) * hop + N) + sizeof(float2) * (size_t)t.pairs_a * t.WB +
-             2 * sizeof(float) * (size_t)F * (t.FT + 1);
+  // analysis: twiddles + window + audio segment + one FFT buffer per frame pair (the [Re;Im] runs are rebuilt from the
+  // buffers at store time: no staging tile, which halves the shared memory per CTA -> two CTAs per SM at N = 1024)
+  t.smem_a = 16 + common + sizeof(float) * ((size_t)(t.FT - 1) * hop + N) + sizeof(float2) * (size_t)t.pairs_a * t.WB;
   t.smem_s = 16 + common + sizeof(float2) * (size_t)t.pairs_s * t.WB + 2 * sizeof(float) * (size_t)F * (2 * t.pairs_s + 1);
   t.ok = N >= 64 && N <= 2048 && t.halo <= 15 && t.pairs_s <= 32 && t.smem_a <= 200 * 1024 && t.smem_s <= 200 * 1024;
   return t;
@@ -265,9 +267,8 @@ __global__ void k_stft_mag_tiled(const float* __restrict__ audio, const int64_t*
   float* win = reinterpret_cast<float*>(tw + N / 2);
   float* seg = win + N;
   float2* buf = reinterpret_cast<float2*>(seg + ((seg_n + 1) & ~1));
-  const int WB = N2 ? 33 * N2 : N;
-  float* st_re = reinterpret_cast<float*>(buf + (size_t)pairs * WB);
-  float* st_im = st_re + (size_t)F * ld;
+  const int WB = (N2 ? 33 * N2 : N) + 1;
+  (void)pairs; (void)ld;
   const int u = blockIdx.y, j0 = blockIdx.x * FT;
   const int Tu = (int)(fidx[2 * u + 1] - fidx[2 * u]);
   if (j0 >= Tu) return;
@@ -300,26 +301,31 @@ __global__ void k_stft_mag_tiled(const float* __restrict__ audio, const int64_t*
     } else {
       fft_warp(d, tw, N, logN, lane);
     }
-    for (int f = lane; f < F; f += 32) {
-      const float2 zk = d[f], zm = d[(N - f) & (N - 1)];
-      // X_a = (Z[k] + conj Z[N-k]) / 2,  X_b = (Z[k] - conj Z[N-k]) / (2i);  librosa 0.5.1 conjugates the FFT
-      const float are = 0.5f * (zk.x + zm.x), aim = -0.5f * (zk.y - zm.y);
-      const float bre = 0.5f * (zk.y + zm.y), bim = 0.5f * (zk.x - zm.x);
-      st_re[f * ld + ja] = are; st_im[f * ld + ja] = aim;
-      if (mag) mag[(size_t)(g0 + ja) * F + f] = sqrtf(are * are + aim * aim);
-      if (hb) {
-        st_re[f * ld + jb] = bre; st_im[f * ld + jb] = bim;
-        if (mag) mag[(size_t)(g0 + jb) * F + f] = sqrtf(bre * bre + bim * bim);
+    if (mag) {
+      for (int f = lane; f < F; f += 32) {
+        const float2 zk = d[f], zm = d[(N - f) & (N - 1)];
+        // X_a = (Z[k] + conj Z[N-k]) / 2,  X_b = (Z[k] - conj Z[N-k]) / (2i);  librosa 0.5.1 conjugates the FFT
+        const float are = 0.5f * (zk.x + zm.x), aim = -0.5f * (zk.y - zm.y);
+        const float bre = 0.5f * (zk.y + zm.y), bim = 0.5f * (zk.x - zm.x);
+        mag[(size_t)(g0 + ja) * F + f] = sqrtf(are * are + aim * aim);
+        if (hb) mag[(size_t)(g0 + jb) * F + f] = sqrtf(bre * bre + bim * bim);
       }
     }
   }
   __syncthreads();
   if (stack) {
+    // [Re;Im] stack: frame index fastest -> every thread rebuilds (bin f, frame j) from the pair buffer Z of frame j and
+    // the CTA writes runs of FT consecutive floats per bin (the spectra stay in the FFT buffers: no staging tile)
     for (int e = threadIdx.x; e < F * FT; e += blockDim.x) {
       const int f = e / FT, j = e - f * FT;
       if (j < nval) {
-        stack[(size_t)f * total_frames + g0 + j] = st_re[f * ld + j];
-        stack[(size_t)(F + f) * total_frames + g0 + j] = st_im[f * ld + j];
+        const float2* d = buf + (size_t)(j >> 1) * WB;
+        const float2 zk = d[f], zm = d[(N - f) & (N - 1)];
+        float re, im;
+        if (j & 1) { re = 0.5f * (zk.y + zm.y); im = 0.5f * (zk.x - zm.x); }
+        else       { re = 0.5f * (zk.x + zm.x); im = -0.5f * (zk.y - zm.y); }
+        stack[(size_t)f * total_frames + g0 + j] = re;
+        stack[(size_t)(F + f) * total_frames + g0 + j] = im;
       }
     }
   }
@@ -338,7 +344,7 @@ __global__ void k_istft_ola_tiled(const float* __restrict__ stack, const float* 
   float2* tw = reinterpret_cast<float2*>(smraw);
   float* win = reinterpret_cast<float*>(tw + N / 2);
   float2* buf = reinterpret_cast<float2*>(win + N);
-  const int WB = N2 ? 33 * N2 : N;
+  const int WB = (N2 ? 33 * N2 : N) + 1;
   float* st_re = reinterpret_cast<float*>(buf + (size_t)pairs * WB);
   float* st_im = st_re + (size_t)F * ld;
   const int u = blockIdx.y, j0 = blockIdx.x * FT;
