@@ -77,30 +77,9 @@ if which in ("all", "thr"):
     sweep(256, 96, [dict(), dict(KS=4, NB=32, G=4)])
 if which in ("all", "dbg"):
     print("---- per-role cycle counters (stderr) ----", flush=True)
-    for kw in (dict(), dict(KS=4, NB=32, G=2), dict(KS=8, NB=64, G=1)):
-        sys.stderr.write("\n## B=64 %s\n" % kw); sys.stderr.flush()
-        run(64, 40, reps=1, DEBUG=1, **kw)
-    for kw in (dict(), dict(KS=4, NB=32, G=4), dict(KS=8, NB=64, G=1)):
-        sys.stderr.write("\n## B=512 %s\n" % kw); sys.stderr.flush()
-        run(512, 12, reps=1, DEBUG=1, **kw)
-if which in ("final",):
-    sweep(64, T, [dict(), dict(KS=4, NB=16, G=4), dict(H2D=1)])
-    sweep(32, T, [dict(), dict(LL=0)])
-    sweep(16, T, [dict(), dict(LL=0)])
-    sweep(48, T, [dict()])
-    sweep(128, 96, [dict(), dict(KS=8, NB=64, G=1)])
-    sweep(256, 96, [dict()])
-    sweep(512, 48, [dict(), dict(PUB="thread")])
-    sweep(2048, 12, [dict(), dict(PUB="thread")])
-if which in ("llt",):
-    sweep(64, T, [dict(KS=8, NB=32, G=1, PUB="direct", LLT=2), dict(KS=8, NB=32, G=1, PUB="direct"), dict(KS=4, NB=16, G=2, PUB="direct", LLT=2),
-                  dict(KS=8, NB=16, G=1, PUB="direct", LLT=4), dict(), dict(LL=0)])
-    sweep(128, 96, [dict(), dict(KS=8, NB=32, G=1, PUB="direct", LLT=4), dict(LL=0)])
-if which in ("crash",):
-    run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
-if which in ("l2",):
-    sweep(64, T, [dict(), dict(KS=4, NB=32, G=2), dict(KS=8, NB=32, G=1), dict(KS=4, NB=16, G=2)])
-    sweep(32, T, [dict(), dict(KS=8, NB=32, G=1)])
+    for B, Tn in ((64, 40), (32, 40), (512, 12), (2048, 6)):
+        sys.stderr.write("\n## B=%d (default plan)\n" % B); sys.stderr.flush()
+        run(B, Tn, reps=1, DEBUG=1)
 if which in ("trace2",):
     for B, Tn, nt, kw in ((64, 40, 1, dict(KS=8, NB=64, G=1)), (64, 40, 1, dict())):
         sys.stderr.write("\n## B=%d %s\n" % (B, kw)); sys.stderr.flush()
