@@ -7,6 +7,8 @@
 #include "internal.h"
 #include "gemm_simt.cuh"
 
+#include <cstdlib>
+
 namespace drnmf {
 
 // ------------------------------------------------------------------------------------------------
@@ -80,31 +82,35 @@ int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // tcgen05
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32;          // BK = one 128-byte swizzle atom of fp32
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;             // 16 KB per operand tile
+constexpr int TC_BM = 128, TC_BK = 32;                        // BK = one 128-byte swizzle atom of fp32
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;             // 16 KB per A tile (and per 128-row B tile)
 constexpr int TC_THREADS = 192;                              // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
-template <int EPI> struct TcCfg {
+// BN = 128 or 256 output columns per CTA.  With both operands in shared memory an M128 x N x K8 TF32 MMA reads
+// (128 + N) * 32 bytes per N/2 cycles: 128 B/clk at N = 128 (the whole shared-memory port, while TMA refills the ring),
+// 96 B/clk at N = 256 - the wide tile is used whenever the grid still fills the device.
+template <int EPI, int BN> struct TcCfg {
   static constexpr bool DUAL = (EPI == EPI_RECON);
-  static constexpr int TILES_PER_STAGE = DUAL ? 6 : 4;        // A_hi A_lo B_hi B_lo [B2_hi B2_lo]
-  static constexpr int STAGES = DUAL ? 2 : 3;
-  static constexpr int STAGE_BYTES = TILES_PER_STAGE * TC_TILE_BYTES;
+  static_assert(!(DUAL && BN != 128), "the dual-B epilogue needs both accumulators: 128 columns each");
+  static constexpr int B_TILE_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGES = (DUAL || BN == 256) ? 2 : 3;
+  static constexpr int STAGE_BYTES = 2 * TC_TILE_BYTES + (DUAL ? 4 : 2) * B_TILE_BYTES;   // A_hi A_lo B_hi B_lo [B2_hi B2_lo]
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // tcgen05 accumulates with round-toward-zero: a long chain of MMAs into one accumulator is biased low by about half an
   // ulp per instruction.  The k-blocks are therefore dealt round-robin to NACC independent TMEM accumulators (all 512
   // columns) that the epilogue adds in fp32 round-to-nearest: chains are NACC times shorter, so is the bias.
-  static constexpr int NACC = DUAL ? 2 : 4;
-  static constexpr uint32_t ACC_COLS = DUAL ? 256 : 128;
+  static constexpr int NACC = (DUAL || BN == 256) ? 2 : 4;
+  static constexpr uint32_t ACC_COLS = DUAL ? 256 : BN;
   static constexpr uint32_t TMEM_COLS = 512;
 };
 
-template <int EPI>
+template <int EPI, int TC_BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
           const __grid_constant__ CUtensorMap tmB2_hi, const __grid_constant__ CUtensorMap tmB2_lo, GemmArgs a,
           int* dev_error) {
-  using Cfg = TcCfg<EPI>;
+  using Cfg = TcCfg<EPI, TC_BN>;
   extern __shared__ __align__(1024) uint8_t smem[];      // no static smem: the dynamic window is 1024-aligned
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
@@ -148,10 +154,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         tma_load_2d(st + 0 * TC_TILE_BYTES, &tmA_hi, &full[s], kc, m0);
         tma_load_2d(st + 1 * TC_TILE_BYTES, &tmA_lo, &full[s], kc, m0);
         tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full[s], kc, n0);
-        tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full[s], kc, n0);
+        tma_load_2d(st + 2 * TC_TILE_BYTES + Cfg::B_TILE_BYTES, &tmB_lo, &full[s], kc, n0);
         if (Cfg::DUAL) {
-          tma_load_2d(st + 4 * TC_TILE_BYTES, &tmB2_hi, &full[s], kc, n0);
-          tma_load_2d(st + 5 * TC_TILE_BYTES, &tmB2_lo, &full[s], kc, n0);
+          tma_load_2d(st + 2 * TC_TILE_BYTES + 2 * Cfg::B_TILE_BYTES, &tmB2_hi, &full[s], kc, n0);
+          tma_load_2d(st + 2 * TC_TILE_BYTES + 3 * Cfg::B_TILE_BYTES, &tmB2_lo, &full[s], kc, n0);
         }
       }
     }
@@ -171,11 +177,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
           constexpr uint32_t T16 = TC_TILE_BYTES >> 4;   // descriptor address field counts 16-byte units
+          constexpr uint32_t B16 = Cfg::B_TILE_BYTES >> 4;
           const uint32_t koff = ks * 2;                 // 8 tf32 = 32 bytes inside the 128-byte swizzle row
           const uint64_t a_hi = d0 + (uint64_t)(0 * T16 + koff);
           const uint64_t a_lo = d0 + (uint64_t)(1 * T16 + koff);
           const uint64_t b_hi = d0 + (uint64_t)(2 * T16 + koff);
-          const uint64_t b_lo = d0 + (uint64_t)(3 * T16 + koff);
+          const uint64_t b_lo = d0 + (uint64_t)(2 * T16 + B16 + koff);
           const bool first = (kb < Cfg::NACC && ks == 0);          // first MMA into this accumulator overwrites
           const uint32_t acc_t = tmem_base + (uint32_t)(kb % Cfg::NACC) * Cfg::ACC_COLS;
           if (leader) {
@@ -184,8 +191,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             umma_tf32(acc_t, a_hi, b_hi, idesc, true);
           }
           if (Cfg::DUAL) {
-            const uint64_t c_hi = d0 + (uint64_t)(4 * T16 + koff);
-            const uint64_t c_lo = d0 + (uint64_t)(5 * T16 + koff);
+            const uint64_t c_hi = d0 + (uint64_t)(2 * T16 + 2 * B16 + koff);
+            const uint64_t c_lo = d0 + (uint64_t)(2 * T16 + 3 * B16 + koff);
             if (leader) {
               umma_tf32(acc_t + TC_BN, a_lo, c_hi, idesc, !first);
               umma_tf32(acc_t + TC_BN, a_hi, c_lo, idesc, true);
@@ -308,9 +315,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   if (warp == 1) { tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
-template <int EPI>
+template <int EPI, int TC_BN>
 static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
-  using Cfg = TcCfg<EPI>;
+  using Cfg = TcCfg<EPI, TC_BN>;
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo;
   int rc;
   if ((rc = make_tmap_2d(&tA_hi, a.A_hi, a.Kd, a.M, a.lda, TC_BK, TC_BM))) return rc;
@@ -328,11 +335,11 @@ static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
   DRNMF_CUDA(cudaGetDevice(&dev));
   DRNMF_CHECK(dev >= 0 && dev < DRNMF_MAX_DEVICES, "device ordinal %d out of range", dev);
   if (!attr_set[dev]) {
-    DRNMF_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DRNMF_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, TC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[dev] = true;
   }
   dim3 grid((a.M + TC_BM - 1) / TC_BM, (a.N + TC_BN - 1) / TC_BN, a.splits > 1 ? a.splits : 1);
-  k_gemm_tc<EPI><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo, a, dev_error);
+  k_gemm_tc<EPI, TC_BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo, a, dev_error);
   count_launch();
   DRNMF_CUDA(cudaGetLastError());
   return DRNMF_OK;
@@ -360,11 +367,16 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
   int* errw = nullptr;
   int rc = gemm_error_word(&errw);
   if (rc) return rc;
+  // wide tiles when the grid still fills the device (and never for the dual-B epilogue)
+  static const int force_bn = getenv("DRNMF_GEMM_BN") ? atoi(getenv("DRNMF_GEMM_BN")) : 0;
+  const long long ctas256 = (long long)((a.M + TC_BM - 1) / TC_BM) * ((a.N + 255) / 256) * (a.splits > 1 ? a.splits : 1);
+  const bool wide = force_bn ? force_bn == 256 : (a.N >= 256 && ctas256 >= 4 * 148);     // >= 4 waves: no tail effect (measured:
+                                                                                           // split-K weight-gradient GEMMs of 256 CTAs lose)
   switch (epi) {
-    case EPI_STORE: return launch_tc_impl<EPI_STORE>(a, st, errw);
-    case EPI_GRAM:  return launch_tc_impl<EPI_GRAM>(a, st, errw);
-    case EPI_RECON: return launch_tc_impl<EPI_RECON>(a, st, errw);
-    case EPI_LAMBDA: return launch_tc_impl<EPI_LAMBDA>(a, st, errw);
+    case EPI_STORE: return wide ? launch_tc_impl<EPI_STORE, 256>(a, st, errw) : launch_tc_impl<EPI_STORE, 128>(a, st, errw);
+    case EPI_GRAM:  return wide ? launch_tc_impl<EPI_GRAM, 256>(a, st, errw) : launch_tc_impl<EPI_GRAM, 128>(a, st, errw);
+    case EPI_RECON: return launch_tc_impl<EPI_RECON, 128>(a, st, errw);
+    case EPI_LAMBDA: return wide ? launch_tc_impl<EPI_LAMBDA, 256>(a, st, errw) : launch_tc_impl<EPI_LAMBDA, 128>(a, st, errw);
   }
   return DRNMF_ERR_INVALID;
 }
