@@ -8,13 +8,14 @@
 //       grid = (KS, MT, G), cluster = the KS K-splits of one M-tile.
 // What bounds a step (measured, profiles/r2_*): the split-K exchange inside the cluster moves a 128 x NB fp32 partial
 // tile per CTA through distributed shared memory at ~13 B/clk (700 + 40 NB cycles), the hop to the consumers through
-// L2 costs ~2.5k cycles, while the 3xTF32 product of a 128-atom slice takes 26 NB cycles.  Hence
-//   * K-splits of 4 (cluster of 4 CTAs, 33 clusters are co-resident on a B200; only 15 clusters of 8): a CTA multiplies
-//     a 128 x (Rp/4) block, i.e. twice the tensor work per exchanged byte of the round-1 tiling (KS = 8);
-//   * batch groups: utterances are independent, so the batch is cut into G = (co-resident clusters) / MT groups that
-//     run the whole chain on disjoint SMs with their own flags (R = 1000: 4 groups x 32 CTAs = 128 SMs).  At B = 64
-//     a group steps 16 utterances: a quarter of the exchange bytes per step; at B >= 512 every group pipelines
-//     64-column batch tiles through the same weights.
+// L2 costs ~3.5k cycles whatever the bytes, while the 3xTF32 product of a 128-atom slice takes 26 NB cycles.  Hence
+//   * throughput regime (B > 64): K-splits of 4 (cluster of 4 CTAs: 33 clusters are co-resident on a B200, only 15
+//     clusters of 8) - a CTA multiplies a 128 x (Rp/4) block, twice the tensor work per exchanged byte - and batch
+//     groups: utterances are independent, so the batch is cut into G = (co-resident clusters) / MT groups that run the
+//     whole chain on disjoint SMs with their own flags (R = 1000: 4 groups x 32 CTAs = 128 SMs), every group
+//     pipelining 64-column batch tiles through the same weights;
+//   * latency regime (B <= 64): the chain of dependent hops decides, not the bytes: K-splits of 8, one group, one or two
+//     32-column tiles (see choose_plan).
 //   * weights: the CTA's block of S_k^T - I streams through a shared-memory ring (TMA, 16 KB pieces of 32 K-columns),
 //     is split into tf32 hi + remainder lo by the loader warps and lands in TENSOR MEMORY in 64-column sub-chunks
 //     (3 buffers of hi|lo = 384 TMEM columns).  The MMA takes A from TMEM (no per-instruction smem read of A).  With
@@ -28,11 +29,14 @@
 //   * split-K reduction INSIDE the cluster over distributed shared memory (staging + cp.async.bulk + mbarrier
 //     complete_tx): CTA o owns rows [o*RO, (o+1)*RO) of the M-tile, sums the KS partials in a fixed order
 //     (deterministic), applies the fused epilogue (identity part, input projection, bias, rank-1 leak, relu, Keras mask
-//     carry) and writes hi/lo of the new hidden rows; the owner warps release their stores with red.release.gpu
-//     (one tile per group) or hand them to a publisher thread that batches the gpu-scope fences (several tiles).
+//     carry) and writes hi/lo of the new hidden rows; every owner warp releases its own stores with red.release.gpu
+//     (measured faster at 1, 2 and 8 tiles per group than a publisher thread that batches the gpu-scope fences, which
+//     remains selectable with DRNMF_REC_PUB=thread).
+//   * latency regime, one tile per group: the hidden rows validate themselves (mantissa-LSB tag, see ll_tag) and two
+//     consumer warps pull them with L2 loads - no flag, no release fence on the producer side.
 //
 // Warp roles (512 threads): 0 weight producer (TMA ring) | 1 hidden-state TMA (+flag acquire) | 2 MMA issuer / TMEM
-//     owner | 3 publisher | 4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue) | 12-15 weight loaders
+//     owner | 3 publisher (or second consumer in the latency regime) | 4-7 TMEM -> DSMEM pushers | 8-11 row owners (reduce + epilogue) | 12-15 weight loaders
 //     (smem ring -> regs -> TMEM).
 #include "internal.h"
 
@@ -284,7 +288,7 @@ __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sc
     }
 }
 
-template <int NB, bool BWD, int CB>
+template <int NB, bool BWD, int CB, bool SYM>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW64,
@@ -336,9 +340,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo); tma_prefetch_desc(&tmW);
-#ifndef RT_VAR_NO_PREFETCH64
-    tma_prefetch_desc(&tmW64);
-#endif
+    if (SYM) tma_prefetch_desc(&tmW64);
     for (int i = 0; i < RT_WB; ++i) { mbar_init(&bars->wb_full[i], 128); mbar_init(&bars->wb_empty[i], 1); }
     for (int i = 0; i < RT_MAXW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], 4); }
     for (int i = 0; i < RT_MAXH; ++i) { mbar_init(&bars->h_full[i], 1); mbar_init(&bars->h_empty[i], 1); }
@@ -376,11 +378,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             // block (rows = its K-columns, columns = this M-tile) in four 64 x 32 pieces, two per ring slot, and read
             // transposed by the loaders: only the blocks on and above the diagonal of a layer are ever touched (36 of 64
             // at R = 1000: 54 of 96 MB per frame), which is what stays resident in L2 across a frame.
-#ifdef RT_VAR_NO_MIR_PRODUCER
-            const bool mir = false;
-#else
-            const bool mir = a.sym && (col0 >> 7) < m;
-#endif
+            const bool mir = SYM && (col0 >> 7) < m;
             for (int pc = 0; pc < npc; ++pc, wr.next(a.WST)) {
               const int ws = wr.idx;
               RT_TIMED(0, okw = mbar_wait(&bars->w_free[ws], wr.ph ^ 1u, err, RT_WATCHDOG));
@@ -1178,11 +1176,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const int col0 = s * a.KSLICE + sc * 64;
           const int npc = (a.KSLICE - sc * 64 >= 64) ? 2 : 1;
           const uint32_t tb = trow + (uint32_t)wb * 128u;
-#ifdef RT_VAR_NO_MIR_LOADER
-          if (false) {
-#else
-          if (a.sym && (col0 >> 7) < m) {
-#endif
+          if (SYM && (col0 >> 7) < m) {
             // mirrored sub-chunk: piece q (two per ring slot) = [64 K-columns (rows)] x [output rows 32q .. 32q+31 (128 bytes)].
             // Warp q owns exactly those TMEM lanes and reads its piece transposed: for a fixed K-column the 32 lanes read
             // one 128-byte row (conflict-free).  No diagonal in these blocks.  Every warp waits for and hands back both
@@ -1360,6 +1354,11 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
   if (p.n_tiles == 1) {
     grow(p.HST, h_stage, min(p.NSC, RT_MAXH));
     grow(p.WST, w_stage, min(pieces_per_step, RT_MAXW));
+  } else if (B <= 64) {
+    // two pipelined tiles of the latency regime: a deeper weight ring only adds TMA traffic ahead of the hidden-state
+    // loads that are on the critical path (measured 6.15 -> 6.00 us/step with 2 instead of 4 pieces in flight)
+    grow(p.RST, 2 * red_slot, 2);
+    grow(p.HST, h_stage, min(2 * p.NSC, RT_MAXH));
   } else {
     grow(p.RST, 2 * red_slot, 2);
     grow(p.HST, h_stage, 3);
@@ -1385,19 +1384,27 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
   p.a.n_tiles_total = p.n_tiles_total;
   p.a.WST = p.WST; p.a.HST = p.HST; p.a.RST = p.RST;
   build_schedule(p.sch, p.NSC, p.n_tiles, &p.a.rot);
+  // scalar alph: S_k is symmetric -> mirrored fetches below the diagonal (64-aligned sub-chunks).  Latency regime only:
+  // there they keep the weights L2-resident (1.6 GB instead of 16.5 GB of DRAM traffic per launch, 3 % faster); with
+  // several tiles / groups the weights are reused anyway and the transposed loader costs 4 - 10 %.
+  p.a.sym = (h->alph_dim == 1 && p.KSLICE % 64 == 0 && p.n_tiles * p.G <= 2 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
   p.ok = true;
   return p;
 }
 
 using RecKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const RecSched, const RecArgs);
 
-template <int NB>
+// SYM (mirrored weight fetches, scalar alph) is a template parameter: the transposed loader costs registers and issue
+// slots that the throughput regime, whose loaders are on the critical path, should not pay for.
+template <int NB, bool SYM>
 static RecKernel rec_kernel_nb(bool bwd, int CB) {
-  if (bwd) return CB == 4 ? k_recurrent_tc<NB, true, 4> : (CB == 2 ? k_recurrent_tc<NB, true, 2> : k_recurrent_tc<NB, true, 1>);
-  return CB == 4 ? k_recurrent_tc<NB, false, 4> : (CB == 2 ? k_recurrent_tc<NB, false, 2> : k_recurrent_tc<NB, false, 1>);
+  if (bwd) return CB == 4 ? k_recurrent_tc<NB, true, 4, SYM> : (CB == 2 ? k_recurrent_tc<NB, true, 2, SYM> : k_recurrent_tc<NB, true, 1, SYM>);
+  return CB == 4 ? k_recurrent_tc<NB, false, 4, SYM> : (CB == 2 ? k_recurrent_tc<NB, false, 2, SYM> : k_recurrent_tc<NB, false, 1, SYM>);
 }
 static RecKernel rec_kernel(const RecPlan& p, bool bwd) {
-  return p.NB == 16 ? rec_kernel_nb<16>(bwd, p.CB) : (p.NB == 32 ? rec_kernel_nb<32>(bwd, p.CB) : rec_kernel_nb<64>(bwd, p.CB));
+  if (p.a.sym)
+    return p.NB == 16 ? rec_kernel_nb<16, true>(bwd, p.CB) : (p.NB == 32 ? rec_kernel_nb<32, true>(bwd, p.CB) : rec_kernel_nb<64, true>(bwd, p.CB));
+  return p.NB == 16 ? rec_kernel_nb<16, false>(bwd, p.CB) : (p.NB == 32 ? rec_kernel_nb<32, false>(bwd, p.CB) : rec_kernel_nb<64, false>(bwd, p.CB));
 }
 
 static void rec_launch_config(const RecPlan& p, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, cudaStream_t st) {
@@ -1552,8 +1559,6 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   if (a.ll) DRNMF_CUDA(cudaMemsetAsync(w.hb_hi, 0, sizeof(float) * 2 * (size_t)w.Bp * Rp, st));
   CUtensorMap tH_hi, tH_lo, tW, tW64;
   int rc;
-  // scalar alph: S_k is symmetric -> mirrored fetches below the diagonal (needs 64-aligned sub-chunks)
-  a.sym = (h->alph_dim == 1 && p.KSLICE % 64 == 0 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
   if ((rc = make_tmap_2d(&tW64, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 64))) return rc;
   if ((rc = make_h_maps(&tH_hi, &tH_lo, w, Rp, p.NB, &a.h3d))) return rc;
@@ -1603,8 +1608,6 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   if (a.ll) DRNMF_CUDA(cudaMemsetAsync(w.hb_hi, 0, sizeof(float) * 2 * (size_t)w.Bp * Rp, st));
   CUtensorMap tH_hi, tH_lo, tW, tW64;
   int rc;
-  // scalar alph: S_k is symmetric -> mirrored fetches below the diagonal (needs 64-aligned sub-chunks)
-  a.sym = (h->alph_dim == 1 && p.KSLICE % 64 == 0 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
   if ((rc = make_tmap_2d(&tW, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 128))) return rc;
   if ((rc = make_tmap_2d(&tW64, h->ST_hi, Rp, (uint64_t)(K > 1 ? K - 1 : 1) * Rp, Rp, 32, 64))) return rc;
   if ((rc = make_h_maps(&tH_hi, &tH_lo, w, Rp, p.NB, &a.h3d))) return rc;

@@ -18,7 +18,7 @@ fl_rec = 2.0 * R * R * (K - 1)
 
 def setenv(**kw):
     for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS", "DRNMF_REC_VERBOSE", "DRNMF_REC_TRACE",
-              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D", "DRNMF_REC_LLT", "DRNMF_REC_LL"):
+              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D", "DRNMF_REC_LLT", "DRNMF_REC_LL", "DRNMF_REC_NOSYM"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         if v is not None:
@@ -80,6 +80,22 @@ if which in ("all", "dbg"):
     for B, Tn in ((64, 40), (32, 40), (512, 12), (2048, 6)):
         sys.stderr.write("\n## B=%d (default plan)\n" % B); sys.stderr.flush()
         run(B, Tn, reps=1, DEBUG=1)
+if which in ("final",):
+    sweep(64, T, [dict(), dict(KS=4, NB=16, G=4), dict(NOSYM=1)])
+    sweep(32, T, [dict(), dict(LL=0)])
+    sweep(16, T, [dict(), dict(LL=0)])
+    sweep(48, T, [dict()])
+    sweep(128, 96, [dict(), dict(KS=8, NB=64, G=1)])
+    sweep(256, 96, [dict()])
+    sweep(512, 48, [dict(), dict(PUB="thread")])
+    sweep(2048, 12, [dict(), dict(PUB="thread")])
+if which in ("b64x",):
+    sweep(64, T, [dict(), dict(HST=2, RST=1, WST=2), dict(HST=2, RST=2, WST=2), dict(HST=4, RST=1, WST=2), dict(HST=2, RST=1, WST=4),
+                  dict(HST=2, RST=1, WST=3), dict(HST=3, RST=1, WST=2)])
+    sweep(512, 48, [dict(), dict(NOSYM=1), dict(NOSYM=1, WST=2), dict(NOSYM=1, HST=2, WST=4)])
+    sweep(2048, 12, [dict(), dict(NOSYM=1)])
+if which in ("crash",):
+    run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
 if which in ("trace2",):
     for B, Tn, nt, kw in ((64, 40, 1, dict(KS=8, NB=64, G=1)), (64, 40, 1, dict())):
         sys.stderr.write("\n## B=%d %s\n" % (B, kw)); sys.stderr.flush()
