@@ -57,14 +57,16 @@ static int run_gemm(const drnmf_handle* h, GemmEpi epi, const GemmArgs& a, cudaS
 }
 
 static int check_dev_error(drnmf_handle* h, cudaStream_t st, const char* what) {
-  int v = 0;
-  DRNMF_CUDA(cudaMemcpyAsync(&v, h->dev_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int e4[4] = {0, 0, 0, 0};             // [0] first code, [1] mask of all recurrence codes (bit = code - 200), [2] detail
+  DRNMF_CUDA(cudaMemcpyAsync(e4, h->dev_error, sizeof(e4), cudaMemcpyDeviceToHost, st));
   DRNMF_CUDA(cudaStreamSynchronize(st));
+  const int v = e4[0];
   int g = gemm_device_error(st);
   if (v != 0 || g != 0) {
     // report once, then clear: a transient failure (e.g. a watchdog expiry under SM contention) must not latch
-    if (v != 0) cudaMemsetAsync(h->dev_error, 0, sizeof(int), st);
-    set_error("%s: device-side failure code %d (gemm %d): a kernel watchdog expired or a protocol check failed", what, v, g);
+    if (v != 0) cudaMemsetAsync(h->dev_error, 0, sizeof(e4), st);
+    set_error("%s: device-side failure code %d (gemm %d; codes seen 0x%x, detail 0x%x): a kernel watchdog expired or a protocol check failed",
+              what, v, g, (unsigned)e4[1], (unsigned)e4[2]);
     return DRNMF_ERR_DEVICE;
   }
   return DRNMF_OK;
@@ -122,7 +124,7 @@ int drnmf_create(drnmf_handle** out, int F, int R, int K_layers, int flags) {
       return DRNMF_ERR_CUDA;
     }
   }
-  if (cudaMalloc(&h->dev_error, sizeof(int)) != cudaSuccess || cudaMemset(h->dev_error, 0, sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&h->dev_error, 4 * sizeof(int)) != cudaSuccess || cudaMemset(h->dev_error, 0, 4 * sizeof(int)) != cudaSuccess) {
     set_error("cudaMalloc(dev_error) failed");
     drnmf_destroy(h);
     return DRNMF_ERR_CUDA;

@@ -272,6 +272,16 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Polling load (16 bytes): a STRONG relaxed.gpu load.  A weak load (plain or .cg - what __ldcg emits) in a spin loop
+// that contains no store or fence is loop-invariant to ptxas, which may hoist it in front of the loop (it did, depending
+// on register pressure: the loop then spins on a stale register for ever).  Data that other CTAs write while this
+// thread is looking must be read with this, never with __ldcg.
+__device__ __forceinline__ float4 ld_poll_v4(const float* p) {
+  float4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
 // 16-byte store into another CTA's shared memory that signals `bytes` on that CTA's mbarrier when it lands
 __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_bar, float a, float b, float c,
                                             float d) {

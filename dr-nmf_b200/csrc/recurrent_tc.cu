@@ -101,7 +101,18 @@ struct RecBars {   // all mbarriers, laid out at off_bar
   uint32_t tmem_slot;
   int abort;
   long long dbg_ts[2];                       // debug: clock of the first satisfied h_full / of the last MMA issue of an item
+  // debug accumulators live here, not in registers: 14 registers per thread of a kernel capped at 128 spilled loop
+  // invariants of the production path (ptxas -v: ~500 bytes at NB = 32)
+  long long dbg_acc[16][8];                  // [warp][0..6 = slots, 7 = start clock]
+  int dbg_trc[8];                            // per-role trace counters
 };
+
+// Failure record (slow path, out of line): word 0 = first code, word 1 = mask of every code seen (bit = code - 200),
+// so that a watchdog report tells which waits were stuck, not only which role started waiting first.
+__device__ __noinline__ void rt_fail(int* e, int code) {
+  atomicCAS(e, 0, code);
+  if (code >= 200 && code < 232) atomicOr(e + 1, 1 << (code - 200));
+}
 
 // named-barrier AND-reduction over the 128 owner threads (barrier id 1): uniform agreement on a predicate
 __device__ __forceinline__ bool owners_all(bool pred) {
@@ -125,10 +136,12 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int ta
   return true;
 }
 
-// accumulate the cycles spent in `stmt` into debug slot `slot` (only CTA (0,0), only when a.dbg is set)
+// accumulate the cycles spent in `stmt` into debug slot `slot` (only CTA (0,0), only when a.dbg is set; dbg_on is
+// warp-uniform so that `stmt` may contain warp collectives, only the role's reporting lane accumulates)
+#define DBG_ADD(slot, v) do { if (dbg_w) bars->dbg_acc[dbg_wi][slot] += (v); } while (0)
 #define RT_TIMED(slot, stmt)                                   \
   do {                                                         \
-    if (dbg_on) { long long _t0 = clock64(); stmt; dbg_acc[slot] += clock64() - _t0; } \
+    if (dbg_on) { long long _t0 = clock64(); stmt; DBG_ADD(slot, clock64() - _t0); } \
     else { stmt; }                                             \
   } while (0)
 
@@ -137,10 +150,11 @@ __device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int ta
 constexpr int RT_TRC_PER_ROLE = 256;
 #define RT_TRACE(role, ev, item)                                                                    \
   do {                                                                                              \
-    if (dbg_on && a.trace && (long long)(item) >= a.trace_lo && (long long)(item) < a.trace_hi && trc < RT_TRC_PER_ROLE) { \
-      long long* _p = a.trace + 8 + ((role) * RT_TRC_PER_ROLE + trc) * 2;                           \
-      _p[0] = ((long long)(ev) << 16) | (long long)((item) & 0xFFFF); _p[1] = clock64(); ++trc;     \
-      a.trace[role] = trc;                                                                          \
+    if (dbg_on && a.trace && (long long)(item) >= a.trace_lo && (long long)(item) < a.trace_hi && bars->dbg_trc[role] < RT_TRC_PER_ROLE) { \
+      const int _c = bars->dbg_trc[role];                                                           \
+      long long* _p = a.trace + 8 + ((role) * RT_TRC_PER_ROLE + _c) * 2;                            \
+      _p[0] = ((long long)(ev) << 16) | (long long)((item) & 0xFFFF); _p[1] = clock64();            \
+      bars->dbg_trc[role] = _c + 1; a.trace[role] = _c + 1;                                         \
     }                                                                                               \
   } while (0)
 
@@ -175,7 +189,7 @@ __device__ __forceinline__ uint32_t sched_at(const RecSched& sc, int i, int n, i
 // NB = 16 the loads of the warp's next position are issued before the current one is stored (two register sets).
 template <int NB>
 __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sch, RecBars* bars, uint8_t* smem, int ci, int s,
-                                            int lane, bool dbg_on, long long (&dbg_acc)[7], int& trc) {
+                                            int lane, bool dbg_on, bool dbg_w, int dbg_wi) {
   constexpr int NLD = NB / 2;                    // float4 per lane and sub-chunk
   constexpr bool PREFETCH = (NB == 16);
   constexpr uint32_t HB = NB * 128;
@@ -197,7 +211,7 @@ __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sc
     if (two || q < 8) {
       const float* src = a.hb_hi + ((size_t)slot * a.Bp + i * NB + r0) * Rp + s * a.KSLICE + sc * 64 + 4 * q;
 #pragma unroll
-      for (int j = 0; j < NLD; ++j) dst[j] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(2 * j) * Rp));
+      for (int j = 0; j < NLD; ++j) dst[j] = ld_poll_v4(src + (size_t)(2 * j) * Rp);     // strong load: see ld_poll_v4
     }
   };
   auto valid = [&](const float4 (&x)[NLD], int i, int p, uint32_t tag4) {
@@ -231,7 +245,7 @@ __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sc
           for (;;) {                                  // sentinel: row 0 of the sub-chunk
             bool good = true;
             if (r0 == 0 && (two || q < 8)) {
-              const float4 x = __ldcg(reinterpret_cast<const float4*>(sp));
+              const float4 x = ld_poll_v4(sp);
               const uint32_t bits = (__float_as_uint(x.x) & 1u) | ((__float_as_uint(x.y) & 1u) << 8) |
                                     ((__float_as_uint(x.z) & 1u) << 16) | ((__float_as_uint(x.w) & 1u) << 24);
               good = bits == tag4;
@@ -246,13 +260,16 @@ __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sc
           issue(v, slot, i, p);
         }
         okh = __all_sync(0xffffffffu, okh);
-        if (!okh) { if (lane == 0) atomicCAS(a.dev_error, 0, 203); break; }
-        if (dbg_on) dbg_acc[1] += clock64() - _t0;
+        if (!okh) {
+          if (lane == 0) { atomicCAS(a.dev_error + 2, 0, (1 << 30) | (t << 16) | (k << 8) | (p << 4) | (ci << 1) | (have ? 1 : 0)); rt_fail(a.dev_error, 203); }
+          break;
+        }
+        if (dbg_on) DBG_ADD(1, clock64() - _t0);
         if constexpr (PREFETCH) { if (p + 2 < NSC) issue(w, slot, i, p + 2); }     // in flight while this position is stored
         const int hs = hr.idx;
         if (lane == 0) {
           okh = mbar_wait(&bars->h_empty[hs], hr.ph ^ 1u, err, RT_WATCHDOG);
-          if (!okh) atomicCAS(a.dev_error, 0, 202);
+          if (!okh) rt_fail(a.dev_error, 202);
         }
         okh = __all_sync(0xffffffffu, okh);
         if (!okh) break;
@@ -271,10 +288,7 @@ __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sc
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&bars->h_full[hs]);
-          if (dbg_on && a.trace && item >= a.trace_lo && item < a.trace_hi && trc < RT_TRC_PER_ROLE) {
-            long long* _p = a.trace + 8 + (1 * RT_TRC_PER_ROLE + trc) * 2;
-            _p[0] = ((long long)(10 + p) << 16) | (item & 0xFFFF); _p[1] = clock64(); ++trc; a.trace[1] = trc;
-          }
+          RT_TRACE(1, 10 + p, item);
         }
         have = false;
         if constexpr (PREFETCH) {
@@ -324,13 +338,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) {               // uniform across the grid: everybody leaves
-    if (threadIdx.x == 0) atomicCAS(a.dev_error, 0, 299);
+    if (threadIdx.x == 0) rt_fail(a.dev_error, 299);
     return;
   }
   const bool dbg_on = (a.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == a.dbg_m && blockIdx.z == 0;
-  long long dbg_acc[7] = {0, 0, 0, 0, 0, 0, 0};
-  int trc = 0;
-  const long long dbg_t0 = clock64();
+  // reporting lanes: lane 0 of the single-warp roles, first thread of the four-warp roles
+  const bool dbg_w = dbg_on && lane == 0 && (warp <= 4 || warp == 8 || warp == 12);
+  const int dbg_wi = warp;
   const int s = blockIdx.x;            // K-split == rank in cluster
   const int m = blockIdx.y;            // M-tile
   const int K = a.K, T = a.T, Rp = a.Rp, n_tiles = a.n_tiles, NSC = a.NSC;
@@ -348,6 +362,10 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     for (int i = 0; i < 4; ++i) { mbar_init(&bars->red_full[i], 1); mbar_init(&bars->red_free[i], 4 * a.KS); }
     for (int i = 0; i < RT_PST; ++i) { mbar_init(&bars->pub_full[i], 4); mbar_init(&bars->pub_empty[i], 1); }
     bars->abort = 0;
+    if (a.dbg) {
+      for (int z = 0; z < 16 * 8; ++z) (&bars->dbg_acc[0][0])[z] = 0;
+      for (int z = 0; z < 8; ++z) bars->dbg_trc[z] = 0;
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(&bars->tmem_slot);
@@ -357,6 +375,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
   const int n_mma_steps = T * (K - 1);
+  if (dbg_w) bars->dbg_acc[dbg_wi][7] = clock64();
 
   if (warp == 0) {
     // ================= weight producer: TMA S_k^T[m*128 .. +128][32 K-columns] pieces into the smem ring ===============
@@ -382,7 +401,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             for (int pc = 0; pc < npc; ++pc, wr.next(a.WST)) {
               const int ws = wr.idx;
               RT_TIMED(0, okw = mbar_wait(&bars->w_free[ws], wr.ph ^ 1u, err, RT_WATCHDOG));
-              if (!okw) { atomicCAS(a.dev_error, 0, 214); break; }
+              if (!okw) { rt_fail(a.dev_error, 214); break; }
               mbar_expect_tx(&bars->w_full[ws], 16384u);
               if (mir) {
                 tma_load_2d_hint(smem + a.off_w + ws * 16384, &tmW64, &bars->w_full[ws], m * 128 + (2 * pc) * 32, (k - 1) * Rp + col0, pol_w);
@@ -400,7 +419,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     // finish up to ~2k cycles apart): the lanes poll the (at most two) M-tiles a sub-chunk overlaps in parallel - a
     // satisfied poll still costs an L2 round trip -, then lane 0 issues one slab TMA per hi / lo.
     if (a.ll) {
-      ll_consumer<NB>(a, sch, bars, smem, 0, s, lane, dbg_on, dbg_acc, trc);
+      if constexpr (NB <= 32) ll_consumer<NB>(a, sch, bars, smem, 0, s, lane, dbg_on, dbg_w, dbg_wi);   // (the host never sets ll with NB = 64)
     } else {
       const int m_lo = (s * a.KSLICE) >> 7;
       RtRing hr;
@@ -427,8 +446,8 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
                     mine_ok = poll_flag(a.flags + i * a.MT + mt, target, err);
                 }
                 okh = __all_sync(0xffffffffu, mine_ok);
-                if (dbg_on) dbg_acc[1] += clock64() - _t0;
-                if (!okh) { if (lane == 0) atomicCAS(a.dev_error, 0, 203); break; }
+                if (dbg_on) DBG_ADD(1, clock64() - _t0);
+                if (!okh) { if (lane == 0) rt_fail(a.dev_error, 203); break; }
                 polled |= need;
                 if (lane == 0) fence_proxy_async_global();          // generic-proxy writes of the owners -> async-proxy (TMA) reads
                 if (lane == 0) RT_TRACE(1, 1 + p, item);
@@ -436,7 +455,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
               if (lane == 0) {
                 const int hs = hr.idx;
                 RT_TIMED(0, okh = mbar_wait(&bars->h_empty[hs], hr.ph ^ 1u, err, RT_WATCHDOG));
-                if (!okh) atomicCAS(a.dev_error, 0, 202);
+                if (!okh) rt_fail(a.dev_error, 202);
                 else {
                   uint8_t* dst = smem + a.off_h + hs * a.h_stage_bytes;
                   const int slab = c0 >> 5;
@@ -479,7 +498,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         for (int i = 0; i < n_tiles && okm; ++i, ++it, ar.next(RT_AST)) {
           const int as = ar.idx;
           RT_TIMED(0, okm = mbar_wait(&bars->t_empty[as], ar.ph ^ 1u, err, RT_WATCHDOG));
-          if (!okm) { atomicCAS(a.dev_error, 0, 204); break; }
+          if (!okm) { rt_fail(a.dev_error, 204); break; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + ACC_COL0 + as * NB;
           for (int p = 0; p < NSC; ++p, hr.next(a.HST)) {
@@ -489,13 +508,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             if (e & 64u) {                           // first use: the loaders fill the buffer for this position
               const uint32_t f = wb == 0 ? f0 : (wb == 1 ? f1 : f2);
               RT_TIMED(2, okm = mbar_wait(&bars->wb_full[wb], f & 1u, err, RT_WATCHDOG));
-              if (!okm) { atomicCAS(a.dev_error, 0, 206); break; }
+              if (!okm) { rt_fail(a.dev_error, 206); break; }
               tc_fence_after();
               if (wb == 0) ++f0; else if (wb == 1) ++f1; else ++f2;
             }
             const int hs = hr.idx;
             RT_TIMED(1, okm = mbar_wait(&bars->h_full[hs], hr.ph, err, RT_WATCHDOG));
-            if (!okm) { atomicCAS(a.dev_error, 0, 205); break; }
+            if (!okm) { rt_fail(a.dev_error, 205); break; }
             // (no tcgen05.fence after this wait: the barrier is completed by TMA bytes, not by tcgen05 work)
             if (dbg_on && lane == 0 && p == 0) bars->dbg_ts[0] = clock64();
             if (lane == 0) RT_TRACE(2, 1 + p, it);
@@ -528,7 +547,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           __syncwarp();
           if (lane == 0) RT_TRACE(2, 20, it);
           if (dbg_on && lane == 0) {   // acc3: first sub-chunk ready -> last MMA issued (the product phase)
-            const long long _n = clock64(); dbg_acc[3] += _n - bars->dbg_ts[0]; bars->dbg_ts[1] = _n;
+            const long long _n = clock64(); DBG_ADD(3, _n - bars->dbg_ts[0]); bars->dbg_ts[1] = _n;
           }
         }
         rot += a.rot; rot = rot >= RT_WB ? rot - RT_WB : rot;
@@ -554,10 +573,10 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         const int as = ar.idx, rs = rr.idx;
         bool okp;
         RT_TIMED(0, okp = mbar_wait(&bars->t_full[as], ar.ph, err, RT_WATCHDOG));
-        if (!okp) { atomicCAS(a.dev_error, 0, 207); dead = true; }
+        if (!okp) { rt_fail(a.dev_error, 207); dead = true; }
         tc_fence_after();
         if (threadIdx.x == 128) RT_TRACE(4, 1, it);
-        if (dbg_on) dbg_acc[2] += clock64() - *reinterpret_cast<volatile long long*>(&bars->dbg_ts[1]);   // issue -> completion
+        if (dbg_on) DBG_ADD(2, clock64() - *reinterpret_cast<volatile long long*>(&bars->dbg_ts[1]));   // issue -> completion
         float v[NB];
 #pragma unroll
         for (int c = 0; c < NB; c += 16) tmem_ld16(trow + ACC_COL0 + as * NB + c, v + c);
@@ -567,7 +586,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (lane == 0 && !dead) mbar_arrive(&bars->t_empty[as]);
         // slot rs (staging here, reduction slot in the owners) is free once every owner has consumed its previous use
         RT_TIMED(1, okp = mbar_wait_cluster(&bars->red_free[rs], rr.ph ^ 1u, err, RT_WATCHDOG));
-        if (!okp) { atomicCAS(a.dev_error, 0, 208); dead = true; }
+        if (!okp) { rt_fail(a.dev_error, 208); dead = true; }
         if (threadIdx.x == 128) RT_TRACE(4, 2, it);
         const uint32_t srow = stage0 + rs * a.red_slot_bytes + rho * (NB * 4);
 #pragma unroll
@@ -597,14 +616,14 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     // The owner threads only arrive on pub_full (release.cta); this thread acquires it, issues the single cumulative
     // gpu-scope fence and bumps flag[tile][m], so the owners never stall on a memory fence.
     if (a.ll) {
-      ll_consumer<NB>(a, sch, bars, smem, 1, s, lane, false, dbg_acc, trc);
+      if constexpr (NB <= 32) ll_consumer<NB>(a, sch, bars, smem, 1, s, lane, false, false, 3);
     } else if (lane == 0) {
       const long long n_items = (a.pub_unit == 1) ? (long long)T * K * n_tiles : 0;   // direct mode: the owners publish
       long long j = 0;
       while (j < n_items) {
         bool okb;
         RT_TIMED(0, okb = mbar_wait(&bars->pub_full[(int)(j % RT_PST)], (uint32_t)((j / RT_PST) & 1), err, RT_WATCHDOG));
-        if (!okb) { atomicCAS(a.dev_error, 0, 211); break; }
+        if (!okb) { rt_fail(a.dev_error, 211); break; }
         // batch every further item that is already complete behind ONE gpu-scope fence (throughput mode)
         long long jend = j + 1;
         while (jend < n_items && jend - j < RT_PST &&
@@ -706,12 +725,12 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           if (last) mvp[bi] = __ldg(a.mvalid + (size_t)bc * T + t);
         }
       }
-      if (dbg_on) { long long _n = clock64(); dbg_acc[2] += _n - _ts; _ts = _n; }
+      if (dbg_on) { long long _n = clock64(); DBG_ADD(2, _n - _ts); _ts = _n; }
       if (k == 0) {
         // ---- frame start: leak[b] = sum_j state[b][j] from the published partial sums of the previous frame ----
         if (t > 0) {
           const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(a.ll ? t : t * K);   // LL: flags only count frames
-          if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) atomicCAS(a.dev_error, 0, 209);
+          if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) rt_fail(a.dev_error, 209);
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
           float sacc = 0.f;
@@ -736,7 +755,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (otid == 0 && !dead) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
         bool oko = false;
         if (!dead) RT_TIMED(0, oko = mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG));
-        if (!oko) { atomicCAS(a.dev_error, 0, 210); dead = true; }
+        if (!oko) { rt_fail(a.dev_error, 210); dead = true; }
         const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
         if (dbg_on) _ts = clock64();
         if (otid == 0) RT_TRACE(5, 1, it);
@@ -773,7 +792,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         }
         __syncwarp();                                  // this warp has consumed the slot (values are in registers):
         if (lane < a.KS && !dead) mbar_arrive_remote_relaxed(&bars->red_free[rs], (uint32_t)lane);   // 4 warps x KS owners arrivals
-        if (dbg_on) { long long _n = clock64(); dbg_acc[3] += _n - _ts; _ts = _n; }
+        if (dbg_on) { long long _n = clock64(); DBG_ADD(3, _n - _ts); _ts = _n; }
         if (otid == 0) RT_TRACE(5, 2, it);
         ++it; rr.next(a.RST);
       }
@@ -870,7 +889,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       }
       if (dbg_on) {   // epilogue time by item kind: frame start (k = 0, incl. the psum flag wait) | last layer | regular
         const long long _n = clock64(), _d = _n - _ts; _ts = _n;
-        if (k == 0) dbg_acc[4] += _d; else if (last) dbg_acc[6] += _d; else dbg_acc[5] += _d;
+        if (k == 0) DBG_ADD(4, _d); else if (last) DBG_ADD(6, _d); else DBG_ADD(5, _d);
       }
       if (a.pub_unit != 1) {
         // latency mode (one batch tile): every owner warp releases its own stores - ONE wait for the write acks on the
@@ -885,7 +904,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         const int ps_ = (int)(j % RT_PST);
         bool okq;
         RT_TIMED(1, okq = mbar_wait(&bars->pub_empty[ps_], (uint32_t)(((j / RT_PST) & 1) ^ 1), err, RT_WATCHDOG));
-        if (!okq) atomicCAS(a.dev_error, 0, 212);
+        if (!okq) rt_fail(a.dev_error, 212);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->pub_full[ps_]);   // release.cta, cumulative over the warp's stores (after __syncwarp)
       }
@@ -1001,7 +1020,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       if (u == 0) {
         if (fi > 0) {
           const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(a.ll ? fi : fi * K);
-          if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) atomicCAS(a.dev_error, 0, 219);
+          if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) rt_fail(a.dev_error, 219);
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
           float s0 = 0.f, s1 = 0.f;
@@ -1039,7 +1058,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       } else {
         const int rs = rr.idx;
         if (otid == 0 && !dead) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
-        if (dead || !mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG)) { atomicCAS(a.dev_error, 0, 220); dead = true; }
+        if (dead || !mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG)) { rt_fail(a.dev_error, 220); dead = true; }
         const uint32_t red = smem_u32(smem + a.off_red) + rs * a.red_slot_bytes;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -1147,7 +1166,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (lane == 0 && (!a.ll || la == 0 || K == 1)) flag_add_release(a.flags + i * a.MT + m, 1u);
       } else {
         const int ps_ = (int)(j % RT_PST);
-        if (!mbar_wait(&bars->pub_empty[ps_], (uint32_t)(((j / RT_PST) & 1) ^ 1), err, RT_WATCHDOG)) atomicCAS(a.dev_error, 0, 222);
+        if (!mbar_wait(&bars->pub_empty[ps_], (uint32_t)(((j / RT_PST) & 1) ^ 1), err, RT_WATCHDOG)) rt_fail(a.dev_error, 222);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->pub_full[ps_]);
       }
@@ -1184,13 +1203,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             const int ws0 = wr.idx; const uint32_t ph0 = wr.ph; wr.next(a.WST);
             const int ws1 = wr.idx; const uint32_t ph1 = wr.ph; wr.next(a.WST);
             RT_TIMED(1, okl = mbar_wait(&bars->w_full[ws0], ph0, err, RT_WATCHDOG) && mbar_wait(&bars->w_full[ws1], ph1, err, RT_WATCHDOG));
-            if (!okl) { atomicCAS(a.dev_error, 0, 215); break; }
+            if (!okl) { rt_fail(a.dev_error, 215); break; }
             const uint32_t piece = smem_u32(smem + a.off_w + ((q >> 1) ? ws1 : ws0) * 16384 + (q & 1) * 8192);
             const uint32_t lcol = (uint32_t)(lane & 3) * 4u, lchunk = (uint32_t)(lane >> 2);
             {
               const uint32_t f = wb == 0 ? f0 : (wb == 1 ? f1 : f2);
               RT_TIMED(0, okl = mbar_wait(&bars->wb_empty[wb], (f & 1u) ^ 1u, err, RT_WATCHDOG));
-              if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
+              if (!okl) { rt_fail(a.dev_error, 213); break; }
               tc_fence_after();
             }
             for (int half = 0; half < 2; ++half) {
@@ -1212,7 +1231,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           for (int pc = 0; pc < npc; ++pc, wr.next(a.WST)) {
             const int ws = wr.idx;
             RT_TIMED(1, okl = mbar_wait(&bars->w_full[ws], wr.ph, err, RT_WATCHDOG));
-            if (!okl) { atomicCAS(a.dev_error, 0, 215); break; }
+            if (!okl) { rt_fail(a.dev_error, 215); break; }
             const uint32_t rbase = smem_u32(smem + a.off_w + ws * 16384) + (uint32_t)row * 128u;
             float v[32];
 #pragma unroll
@@ -1222,7 +1241,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
             if (pc == 0) {
               const uint32_t f = wb == 0 ? f0 : (wb == 1 ? f1 : f2);
               RT_TIMED(0, okl = mbar_wait(&bars->wb_empty[wb], (f & 1u) ^ 1u, err, RT_WATCHDOG));
-              if (!okl) { atomicCAS(a.dev_error, 0, 213); break; }
+              if (!okl) { rt_fail(a.dev_error, 213); break; }
               tc_fence_after();
             }
             // The tensor core multiplies by S_k^T - I = -(G_k)^T only; the identity part of the product (the operand
@@ -1255,11 +1274,10 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       rot += a.rot; rot = rot >= RT_WB ? rot - RT_WB : rot;
     }
   }
-  if (dbg_on && (lane == 0 || warp >= 4) && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64 ||
-                                              threadIdx.x == 96 || threadIdx.x == 128 || threadIdx.x == 256 || threadIdx.x == 384)) {
-    long long* d = a.dbg + (threadIdx.x / 32) * 8;        // slot per warp: [total, acc0..acc5]
-    d[0] = clock64() - dbg_t0;
-    for (int q2 = 0; q2 < 7; ++q2) d[1 + q2] = dbg_acc[q2];
+  if (dbg_w) {
+    long long* d = a.dbg + dbg_wi * 8;                    // slot per warp: [total, acc0..acc6]
+    d[0] = clock64() - bars->dbg_acc[dbg_wi][7];
+    for (int q2 = 0; q2 < 7; ++q2) d[1 + q2] = bars->dbg_acc[dbg_wi][q2];
   }
   // ---- teardown: nobody leaves while a peer may still touch its shared memory ----
   tc_fence_before();

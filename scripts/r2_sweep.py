@@ -18,7 +18,7 @@ fl_rec = 2.0 * R * R * (K - 1)
 
 def setenv(**kw):
     for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS", "DRNMF_REC_VERBOSE", "DRNMF_REC_TRACE",
-              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D", "DRNMF_REC_LLT", "DRNMF_REC_LL", "DRNMF_REC_NOSYM"):
+              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D", "DRNMF_REC_LLT", "DRNMF_REC_LL", "DRNMF_REC_NOSYM", "DRNMF_REC_PUSH", "DRNMF_REC_DEFER"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         if v is not None:
@@ -94,6 +94,23 @@ if which in ("b64x",):
                   dict(HST=2, RST=1, WST=3), dict(HST=3, RST=1, WST=2)])
     sweep(512, 48, [dict(), dict(NOSYM=1), dict(NOSYM=1, WST=2), dict(NOSYM=1, HST=2, WST=4)])
     sweep(2048, 12, [dict(), dict(NOSYM=1)])
+if which in ("llt",):
+    sweep(64, T, [dict(), dict(LLT=2), dict(LLT=2, WST=4), dict(LLT=2, HST=2), dict(KS=4, NB=32, G=2), dict(KS=4, NB=32, G=2, WST=2),
+                  dict(KS=4, NB=16, G=2, LLT=2), dict(KS=8, NB=16, G=1, LLT=4), dict(KS=8, NB=16, G=1)])
+    sweep(48, T, [dict(), dict(LLT=2)])
+if which in ("thr2",):
+    sweep(512, 48, [dict(PUSH=0, DEFER=0), dict(), dict(PUSH=1, DEFER=0), dict(PUSH=0, DEFER=1), dict(RST=3, HST=2), dict(RST=2, HST=2, WST=4),
+                    dict(KS=4, NB=32, G=4), dict(KS=8, NB=64, G=1)])
+    sweep(2048, 12, [dict(PUSH=0, DEFER=0), dict(), dict(PUSH=1, DEFER=0), dict(PUSH=0, DEFER=1), dict(RST=3, HST=2), dict(RST=2, HST=2, WST=4)])
+    sweep(256, 96, [dict(PUSH=0, DEFER=0), dict(), dict(KS=4, NB=32, G=4), dict(KS=4, NB=32, G=4, PUSH=1, DEFER=1)])
+    sweep(64, T, [dict(), dict(DEFER=1), dict(PUSH=1), dict(PUSH=1, DEFER=1)])
+if which in ("b32dbg",):
+    for kw, Tn in ((dict(), 193), (dict(), 8), (dict(), 2), (dict(LL=0), 193), (dict(NOSYM=1), 193), (dict(WST=2), 193), (dict(DEBUG=1), 40), (dict(NB=16), 193)):
+        sys.stderr.write("\n## B=32 T=%d %s\n" % (Tn, kw)); sys.stderr.flush()
+        run(32, Tn, reps=1, **kw)
+if which in ("ab",):
+    for B, Tn in ((64, T), (32, T), (16, T), (512, 48), (2048, 12)):
+        run(B, Tn)
 if which in ("crash",):
     run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
 if which in ("trace2",):
