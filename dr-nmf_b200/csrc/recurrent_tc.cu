@@ -59,7 +59,9 @@ constexpr long long RT_WATCHDOG = 3000000000LL;
 // which TMEM weight buffer it lives, whether that buffer is filled for this use (first use) and whether it may be
 // overwritten afterwards (last use).  Tile classes: 0 first tile, 1 odd tile, 2 even tile > 0; +3 when the tile is the
 // last of the step.  Entry bits: [3:0] sub-chunk, [5:4] buffer, 6 first use, 7 last use.
-struct RecSched { uint8_t e[6][RT_MAXSC]; };
+// e_last: the same table for the last batch group when it holds fewer tiles (the classes depend on the tile count).
+struct RecSched { uint8_t e[6][RT_MAXSC]; uint8_t e_last[6][RT_MAXSC]; };
+using SchedTab = const uint8_t (*)[RT_MAXSC];
 
 struct RecArgs {
   // tensors
@@ -85,6 +87,7 @@ struct RecArgs {
   int n_tiles_total;                         // batch tiles of the whole batch
   int NSC;                                   // 64-column sub-chunks per K-slice (the last one may be 32 wide)
   int rot;                                   // NSC <= RT_WB: the buffers rotate by NSC per step (next step's weights prefetch)
+  int split;                                 // forward, RO x NB = 4096: warps 4-7 push an item and then own the upper half of its rows
   int pub_unit;                              // flag increments per (CTA, item): 1 = publisher thread, 4 = each owner warp releases its own stores
   int WST, HST, RST;                         // weight-piece / hidden-sub-chunk / reduction-slot ring depths
   float u0_dmo, u0_off, uk_dmo, uk_off;
@@ -178,9 +181,52 @@ struct RtRing {
 };
 
 // schedule entry of (tile i of n, position p)
-__device__ __forceinline__ uint32_t sched_at(const RecSched& sc, int i, int n, int p) {
+__device__ __forceinline__ uint32_t sched_at(SchedTab sc, int i, int n, int p) {
   const int cls = (i == 0 ? 0 : ((i & 1) ? 1 : 2)) + (i == n - 1 ? 3 : 0);
-  return sc.e[cls][p];
+  return sc[cls][p];
+}
+
+// One pusher step (see the pusher role in the kernel) as a function: accumulator stage `as` -> staging slot `rs` -> bulk
+// DSMEM copies into the owners' reduction slots.  Used by the split epilogue, where warps 4-7 push an item and then own
+// half of its rows.  Executed by all 128 threads of warps 4-7.
+template <int NB>
+__device__ __forceinline__ void push_item(const RecArgs& a, RecBars* bars, uint8_t* smem, uint32_t tmem_base, uint32_t acc_col0,
+                                          int s, int q, int lane, int as, uint32_t as_ph, int rs, uint32_t rs_ph, bool& dead) {
+  constexpr int CHUNKS = NB / 4;
+  constexpr int SWZ = (CHUNKS >= 8) ? 7 : CHUNKS - 1;
+  volatile int* err = a.dev_error;
+  const int rho = q * 32 + lane;
+  const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+  const uint32_t stage0 = smem_u32(smem + a.off_push);
+  const uint32_t blk_bytes = (uint32_t)(a.RO * NB * 4);
+  if (!dead && !mbar_wait(&bars->t_full[as], as_ph, err, RT_WATCHDOG)) { rt_fail(a.dev_error, 207); dead = true; }
+  tc_fence_after();
+  float v[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 16) tmem_ld16(trow + acc_col0 + as * NB + c, v + c);
+  tc_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0 && !dead) mbar_arrive(&bars->t_empty[as]);
+  if (!dead && !mbar_wait_cluster(&bars->red_free[rs], rs_ph ^ 1u, err, RT_WATCHDOG)) { rt_fail(a.dev_error, 208); dead = true; }
+  const uint32_t srow = stage0 + rs * a.red_slot_bytes + rho * (NB * 4);
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const uint32_t addr = srow + (uint32_t)(((c & ~SWZ) | ((c ^ rho) & SWZ)) * 16);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                 "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+  }
+  fence_proxy_async_smem();
+  int o_first, o_cnt;
+  if (a.RO <= 32) { __syncwarp(); o_cnt = 32 / a.RO; o_first = q * o_cnt; }
+  else { asm volatile("bar.sync 2, 128;" ::: "memory"); o_cnt = (q == 0) ? a.KS : 0; o_first = 0; }
+  if (lane < o_cnt && !dead) {
+    const uint32_t o = (uint32_t)(o_first + lane);
+    const uint32_t src = stage0 + rs * a.red_slot_bytes + o * blk_bytes;
+    const uint32_t dst = mapa_u32(smem_u32(smem + a.off_red) + rs * a.red_slot_bytes + (uint32_t)s * blk_bytes, o);
+    const uint32_t bar = mapa_u32(smem_u32(&bars->red_full[rs]), o);
+    dsmem_bulk_copy(dst, src, blk_bytes, bar);
+  }
 }
 
 // Latency-mode consumer (warps 1 and 3, see ll_tag): warp `ci` serves the positions p = ci, ci + 2, ... of every step.
@@ -188,7 +234,7 @@ __device__ __forceinline__ uint32_t sched_at(const RecSched& sc, int i, int n, i
 // the "hi" tiles, their tf32 remainders to the "lo" tiles, both in the 128B-swizzle layout of the MMA descriptors.  With
 // NB = 16 the loads of the warp's next position are issued before the current one is stored (two register sets).
 template <int NB>
-__device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sch, RecBars* bars, uint8_t* smem, int ci, int s,
+__device__ __forceinline__ void ll_consumer(const RecArgs& a, SchedTab sch, RecBars* bars, uint8_t* smem, int ci, int s,
                                             int lane, bool dbg_on, bool dbg_w, int dbg_wi) {
   constexpr int NLD = NB / 2;                    // float4 per lane and sub-chunk
   constexpr bool PREFETCH = (NB == 16);
@@ -302,15 +348,17 @@ __device__ __forceinline__ void ll_consumer(const RecArgs& a, const RecSched& sc
     }
 }
 
-template <int NB, bool BWD, int CB, bool SYM>
+template <int NB, bool BWD, int CB, bool SYM, bool SPLIT = false>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW64,
-               const __grid_constant__ RecSched sch, const RecArgs a_in) {
+               const __grid_constant__ RecSched sch_in, const RecArgs a_in) {
   // Batch groups: utterances are independent, so grid.z groups of (KS x MT) CTAs each run the whole chain on their own
   // contiguous range of batch tiles (disjoint SMs, own flags, no interaction).  Everything indexed by the utterance is
   // re-based once here; below, tile i / utterance b are group-local.
   RecArgs a = a_in;
+  // (the last group may hold fewer tiles: its schedule classes differ)
+  SchedTab sch = (gridDim.z > 1 && blockIdx.z == gridDim.z - 1) ? sch_in.e_last : sch_in.e;
   const int tile0 = blockIdx.z * a_in.n_tiles;
   const int boff = tile0 * NB;
   if (gridDim.z > 1) {
@@ -359,7 +407,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     for (int i = 0; i < RT_MAXW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_free[i], 4); }
     for (int i = 0; i < RT_MAXH; ++i) { mbar_init(&bars->h_full[i], 1); mbar_init(&bars->h_empty[i], 1); }
     for (int i = 0; i < RT_AST; ++i) { mbar_init(&bars->t_full[i], 1); mbar_init(&bars->t_empty[i], 4); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&bars->red_full[i], 1); mbar_init(&bars->red_free[i], 4 * a.KS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bars->red_full[i], 1); mbar_init(&bars->red_free[i], (SPLIT ? 8 : 4) * a.KS); }
     for (int i = 0; i < RT_PST; ++i) { mbar_init(&bars->pub_full[i], 4); mbar_init(&bars->pub_empty[i], 1); }
     bars->abort = 0;
     if (a.dbg) {
@@ -553,7 +601,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         rot += a.rot; rot = rot >= RT_WB ? rot - RT_WB : rot;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 8 && !SPLIT) {
     // ================= pushers: TMEM accumulator -> staging smem -> bulk DSMEM copy into every owner's slot =========
     // Thread rho holds accumulator row rho.  Rows are staged row-major with the 16-byte chunks of a row XOR-swizzled
     // by (row & 7) (conflict-free STS.128 here and LDS.128 in the owner); rows [o*RO, (o+1)*RO) are one contiguous
@@ -638,12 +686,24 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         j = jend;
       }
     }
-  } else if (warp >= 8 && warp < 12 && !BWD) {
+  } else if (!BWD && ((warp >= 8 && warp < 12) || (SPLIT && warp >= 4 && warp < 8))) {
     // ================= owners: reduce the KS partials of rows [o*RO, (o+1)*RO), epilogue, publish =================
-    const int otid = threadIdx.x - 256;              // 0..127
-    const int RO = a.RO;
-    const int row0 = m * 128 + s * RO;               // first global output row this CTA owns
-    const int cta_lin = m * a.KS + s, n_cta = a.MT * a.KS;
+    // Split epilogue (a.split: K-split 2 with 64 batch columns, 4096 outputs per item): the exchange of such an item is
+    // a third of the K-split-4 one per flop, which leaves the owners as the bottleneck - so two groups of four warps own
+    // half of the CTA's rows each.  Group 1 = warps 4-7, which first push the item (they are the only warps that can read
+    // all 128 TMEM lanes besides the loaders), group 0 = warps 8-11.  Each group has its own leak / staging scratch, its
+    // own named barrier and publishes as a CTA of its own (psum slot, 4 flag increments).
+    constexpr int nparts_o = SPLIT ? 2 : 1;
+    const int part_o = (SPLIT && warp < 8) ? 1 : 0;
+    const int otid = threadIdx.x & 127;              // 0..127 inside the group
+    const int RO = a.RO / nparts_o;                  // rows of this group
+    const int rpart0 = part_o * RO;                  // their offset inside the CTA's block of the reduction slot
+    const int row0 = m * 128 + s * a.RO + rpart0;    // first global output row of the group
+    const int cta_lin = (m * a.KS + s) * nparts_o + part_o, n_cta = a.MT * a.KS * nparts_o;
+    const int bar_id = part_o ? 3 : 1;
+    float* leak_g = leak_s + part_o * (n_tiles * NB);
+    float* out_g = out_s + part_o * (NB * (RO + 1));
+    RtRing ar_push;                                  // accumulator stage of the next item to push (group 1)
     const size_t KRp = (size_t)K * Rp;
     // The RO x NB outputs of a tile are dealt to the 128 threads as ONE block of 4 rows x CB batch columns each
     // (CB = RO*NB/512, chosen by the host; fewer threads work when the tile is smaller).  Partials are read as
@@ -731,28 +791,32 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (t > 0) {
           const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(a.ll ? t : t * K);   // LL: flags only count frames
           if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) rt_fail(a.dev_error, 209);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
           float sacc = 0.f;
           const float* ps = a.psum + (size_t)((t - 1) & 1) * 256 * a.Bp + i * NB + b;
 #pragma unroll 16                                  // independent L2 loads in flight, summed in index order
           for (int c = part; c < n_cta; c += nparts) sacc += __ldcg(ps + (size_t)c * a.Bp);
-          out_s[part * NB + b] = sacc;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          out_g[part * NB + b] = sacc;
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (otid < NB) {
             float tot = 0.f;
-            for (int p = 0; p < nparts; ++p) tot += out_s[p * NB + otid];
-            leak_s[i * NB + otid] = tot;
+            for (int p = 0; p < nparts; ++p) tot += out_g[p * NB + otid];
+            leak_g[i * NB + otid] = tot;
           }
         } else if (otid < NB) {
-          leak_s[i * NB + otid] = h0sum;
+          leak_g[i * NB + otid] = h0sum;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       } else {
         // ---- wait for the KS partial tiles, sum them in rank order ----
         const int rs = rr.idx;
         // (after a failed wait the thread only runs through: re-arming a barrier whose phase never completed traps)
-        if (otid == 0 && !dead) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
+        if (SPLIT && part_o == 1) {                    // split epilogue: this group pushes the item first
+          push_item<NB>(a, bars, smem, tmem_base, ACC_COL0, s, warp - 4, lane, ar_push.idx, ar_push.ph, rs, rr.ph, dead);
+          ar_push.next(RT_AST);
+        }
+        if (otid == 0 && part_o == 0 && !dead) mbar_expect_tx(&bars->red_full[rs], (uint32_t)(128 * NB * 4));
         bool oko = false;
         if (!dead) RT_TIMED(0, oko = mbar_wait_cluster(&bars->red_full[rs], rr.ph, err, RT_WATCHDOG));
         if (!oko) { rt_fail(a.dev_error, 210); dead = true; }
@@ -761,12 +825,12 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (otid == 0) RT_TRACE(5, 1, it);
         // address of (row r, columns CB*cq..) inside a source block: row-major, 16-byte chunk index swizzled by
         // (row & 7); the pusher's row index rho = o*RO + r has the same low 3 bits as r because RO is a multiple of 8.
-        const uint32_t src_stride = (uint32_t)(RO * NB * 4);
+        const uint32_t src_stride = (uint32_t)(a.RO * NB * 4);
         if (mine) {
           uint32_t qaddr[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int r = 4 * my_rq + e, col = CB * my_cq, ch = col >> 2;
+            const int r = rpart0 + 4 * my_rq + e, col = CB * my_cq, ch = col >> 2;
             qaddr[e] = red + (uint32_t)(r * (NB * 4) + ((ch & ~SWZ) | ((ch ^ r) & SWZ)) * 16 + (col & 3) * 4);
           }
 #pragma unroll 4
@@ -802,7 +866,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 #pragma unroll
         for (int bi = 0; bi < CB; ++bi) {
           const int bl = CB * my_cq + bi, b = i * NB + bl;
-          const float lkv = off * leak_s[i * NB + bl];
+          const float lkv = off * leak_g[i * NB + bl];
           const float pv[4] = {pre[bi].x, pre[bi].y, pre[bi].z, pre[bi].w};
           const float xv[4] = {xw[bi].x, xw[bi].y, xw[bi].z, xw[bi].w};
           float sv[4] = {0.f, 0.f, 0.f, 0.f};          // state entering the frame (only for U with d != o beyond layer 0)
@@ -855,7 +919,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           }
           if (last) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) out_s[bl * (RO + 1) + 4 * my_rq + e] = stn[e];
+            for (int e = 0; e < 4; ++e) out_g[bl * (RO + 1) + 4 * my_rq + e] = stn[e];
           }
         }
         if (a.actT_hi) {                               // backward needs every layer's post-relu output
@@ -879,13 +943,13 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       }
       if (last) {
         // partial row sums of the new state over this CTA's RO rows (rank-1 leak of the next frame)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (otid < NB) {
           float ps = 0.f;
-          for (int r = 0; r < RO; ++r) ps += out_s[otid * (RO + 1) + r];
+          for (int r = 0; r < RO; ++r) ps += out_g[otid * (RO + 1) + r];
           __stcg(a.psum + (size_t)(t & 1) * 256 * a.Bp + (size_t)cta_lin * a.Bp + i * NB + otid, ps);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // out_s may be rewritten by the next item
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // out_s may be rewritten by the next item
       }
       if (dbg_on) {   // epilogue time by item kind: frame start (k = 0, incl. the psum flag wait) | last layer | regular
         const long long _n = clock64(), _d = _n - _ts; _ts = _n;
@@ -1294,13 +1358,13 @@ struct RecPlan { int NB, KS, MT, RO, NSC, KSLICE, n_tiles, n_tiles_total, G, WST
 // upwards (results do not depend on the tile an utterance lands in) and the buffers rotate from step to step so that the
 // next step's first sub-chunks are converted while this step still multiplies.  NSC > RT_WB: buffer = sub-chunk mod 3,
 // tiles walk the K-slice in alternating direction and reuse whatever the previous tile left resident.
-static void build_schedule(RecSched& sc, int NSC, int n_tiles, int* rot) {
-  memset(&sc, 0, sizeof(sc));
+static void build_schedule(uint8_t (*sce)[RT_MAXSC], int NSC, int n_tiles, int* rot) {
+  memset(sce, 0, 6 * RT_MAXSC);
   if (NSC <= RT_WB) {
     *rot = NSC % RT_WB;
     for (int cls = 0; cls < 6; ++cls)
       for (int p = 0; p < NSC; ++p)
-        sc.e[cls][p] = (uint8_t)(p | (p << 4) | ((cls % 3 == 0) ? 64 : 0) | ((cls >= 3) ? 128 : 0));
+        sce[cls][p] = (uint8_t)(p | (p << 4) | ((cls % 3 == 0) ? 64 : 0) | ((cls >= 3) ? 128 : 0));
     return;
   }
   *rot = 0;
@@ -1324,12 +1388,12 @@ static void build_schedule(RecSched& sc, int NSC, int n_tiles, int* rot) {
     const int cls = (i == 0 ? 0 : ((i & 1) ? 1 : 2)) + (i == n - 1 ? 3 : 0);
     for (int p = 0; p < NSC; ++p) {
       const Acc& x = acc[i * NSC + p];
-      sc.e[cls][p] = (uint8_t)(x.sc | (x.slot << 4) | (x.fresh ? 64 : 0) | (x.last ? 128 : 0));
+      sce[cls][p] = (uint8_t)(x.sc | (x.slot << 4) | (x.fresh ? 64 : 0) | (x.last ? 128 : 0));
     }
   }
 }
 
-static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int G) {
+static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int G, bool bwd) {
   RecPlan p{};
   p.ok = false;
   const int Rp = h->Rp;
@@ -1348,11 +1412,15 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
     const char* e = getenv("DRNMF_REC_PUB");
     p.a.pub_unit = (e && !strcmp(e, "thread")) ? 1 : 4;
   }
-  if (p.RO * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
-  p.CB = p.RO * p.NB >= 2048 ? 4 : (p.RO * p.NB >= 1024 ? 2 : 1);     // batch columns per owner thread (4 rows x CB)
-  if (((p.RO / 4) * (p.NB / p.CB)) % 32 != 0) { p.why = "owner tile smaller than a warp"; return p; }
+  // 128 owner threads x (4 rows x 4 batch columns) = 2048 outputs; the forward pass takes 4096 with the split epilogue
+  p.a.split = (!bwd && p.NB == 64 && p.RO == 64 && !getenv("DRNMF_REC_NOSPLIT")) ? 1 : 0;
+  const int ro_grp = p.a.split ? p.RO / 2 : p.RO;                      // rows per owner group
+  if (ro_grp * p.NB > 2048 || p.RO % 8 != 0) { p.why = "rows per owner x batch tile exceeds the per-thread output budget"; return p; }
+  if (p.a.split) p.a.pub_unit = 8;                                     // both groups publish: 8 flag increments per (CTA, item)
+  p.CB = ro_grp * p.NB >= 2048 ? 4 : (ro_grp * p.NB >= 1024 ? 2 : 1);  // batch columns per owner thread (4 rows x CB)
+  if (((ro_grp / 4) * (p.NB / p.CB)) % 32 != 0) { p.why = "owner tile smaller than a warp"; return p; }
   const int h_stage = 4 * p.NB * 128, red_slot = 128 * p.NB * 4;      // 64 atoms (hi, lo) x NB ; KS blocks of RO x NB fp32
-  const int leak_b = round_up(2 * p.n_tiles * p.NB * 4, 128), out_b = round_up(max(p.NB * (p.RO + 1), 128) * 4, 128);
+  const int leak_b = round_up(2 * p.n_tiles * p.NB * 4, 128), out_b = round_up(max(p.NB * (p.RO + 2), 128) * 4, 128);
   const int fixed = leak_b + out_b + (int)sizeof(RecBars) + 256;
   const int budget = 232448 - 1024 - fixed;
   // every reduction slot has a twin staging slot on the pusher side (same index), hence 2 * red_slot per depth.
@@ -1401,11 +1469,12 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
   p.a.MT = p.MT; p.a.KS = p.KS; p.a.RO = p.RO; p.a.KSLICE = p.KSLICE; p.a.n_tiles = p.n_tiles; p.a.NSC = p.NSC;
   p.a.n_tiles_total = p.n_tiles_total;
   p.a.WST = p.WST; p.a.HST = p.HST; p.a.RST = p.RST;
-  build_schedule(p.sch, p.NSC, p.n_tiles, &p.a.rot);
+  build_schedule(p.sch.e, p.NSC, p.n_tiles, &p.a.rot);
+  build_schedule(p.sch.e_last, p.NSC, p.n_tiles_total - (p.G - 1) * p.n_tiles, &p.a.rot);
   // scalar alph: S_k is symmetric -> mirrored fetches below the diagonal (64-aligned sub-chunks).  Latency regime only:
   // there they keep the weights L2-resident (1.6 GB instead of 16.5 GB of DRAM traffic per launch, 3 % faster); with
   // several tiles / groups the weights are reused anyway and the transposed loader costs 4 - 10 %.
-  p.a.sym = (h->alph_dim == 1 && p.KSLICE % 64 == 0 && p.n_tiles * p.G <= 2 && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
+  p.a.sym = (h->alph_dim == 1 && p.KSLICE % 64 == 0 && p.n_tiles * p.G <= 2 && !p.a.split && !getenv("DRNMF_REC_NOSYM")) ? 1 : 0;
   p.ok = true;
   return p;
 }
@@ -1420,6 +1489,7 @@ static RecKernel rec_kernel_nb(bool bwd, int CB) {
   return CB == 4 ? k_recurrent_tc<NB, false, 4, SYM> : (CB == 2 ? k_recurrent_tc<NB, false, 2, SYM> : k_recurrent_tc<NB, false, 1, SYM>);
 }
 static RecKernel rec_kernel(const RecPlan& p, bool bwd) {
+  if (p.a.split) return k_recurrent_tc<64, false, 4, false, true>;     // the only shape with a split epilogue (see plan_recurrent)
   if (p.a.sym)
     return p.NB == 16 ? rec_kernel_nb<16, true>(bwd, p.CB) : (p.NB == 32 ? rec_kernel_nb<32, true>(bwd, p.CB) : rec_kernel_nb<64, true>(bwd, p.CB));
   return p.NB == 16 ? rec_kernel_nb<16, false>(bwd, p.CB) : (p.NB == 32 ? rec_kernel_nb<32, false>(bwd, p.CB) : rec_kernel_nb<64, false>(bwd, p.CB));
@@ -1495,12 +1565,15 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
   const char* env_g = getenv("DRNMF_REC_G");
   const bool verbose = getenv("DRNMF_REC_VERBOSE") != nullptr;
   const bool latency = B <= 64;
-  static const int ks_lat[5] = {8, 4, 2, 1, 16}, ks_thr[5] = {4, 8, 2, 1, 16};
+  // Forward pass with >= 12 tiles of 64 utterances: K-split 2 (a third of the split-K exchange per flop, split epilogue,
+  // see the owners) - measured 108 against 85 TF/s useful at B = 2048, equal at B = 512 where a group holds one tile.
+  static const int ks_lat[5] = {8, 4, 2, 1, 16}, ks_thr[5] = {4, 8, 2, 1, 16}, ks_big[5] = {2, 4, 8, 1, 16};
+  const bool big = !latency && !bwd && (B + 63) / 64 >= 12 && !getenv("DRNMF_REC_NOSPLIT");
   for (int kq = 0; kq < 5 && !p.ok; ++kq) {
-    const int KS = latency ? ks_lat[kq] : ks_thr[kq];
+    const int KS = latency ? ks_lat[kq] : (big ? ks_big[kq] : ks_thr[kq]);
     if (env_ks && atoi(env_ks) != KS) continue;
     // co-resident clusters for this cluster size (probe with the smallest tile: shared memory is at the limit anyway)
-    RecPlan probe = plan_recurrent(h, B, KS, 16, 1);
+    RecPlan probe = plan_recurrent(h, B, KS, 16, 1, bwd);
     if (!probe.ok) { p.why = probe.why; continue; }
     int mc = 0;
     rec_max_clusters(probe, bwd, &mc);
@@ -1514,7 +1587,7 @@ static RecPlan choose_plan(const drnmf_handle* h, int B, bool bwd) {
       if (!env_nb && !latency && NB == 16) continue;
       if (!env_nb && !latency && NB > 32 && (B + NB - 1) / NB < g_max) continue;
       for (int G = g_max; G >= 1 && !p.ok; --G) {
-        RecPlan c = plan_recurrent(h, B, KS, NB, G);
+        RecPlan c = plan_recurrent(h, B, KS, NB, G, bwd);
         if (!c.ok) { p.why = c.why; continue; }
         if (c.G != G && G != g_max) continue;       // this group count was already tried
         int mc2 = 0;

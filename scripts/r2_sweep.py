@@ -109,8 +109,14 @@ if which in ("b32dbg",):
         sys.stderr.write("\n## B=32 T=%d %s\n" % (Tn, kw)); sys.stderr.flush()
         run(32, Tn, reps=1, **kw)
 if which in ("ab",):
-    for B, Tn in ((64, T), (32, T), (16, T), (512, 48), (2048, 12)):
+    for B, Tn in ((64, T), (32, T), (16, T), (512, 48), (768, 32), (1024, 24), (2048, 12), (4096, 6)):
         run(B, Tn)
+if which in ("ks2",):
+    sweep(2048, 12, [dict(), dict(KS=2, NB=64, VERBOSE=1), dict(KS=2, NB=64, G=8), dict(KS=2, NB=64, G=4), dict(KS=2, NB=32)])
+    sweep(512, 48, [dict(), dict(KS=2, NB=64), dict(KS=2, NB=64, G=8), dict(KS=2, NB=64, G=4), dict(KS=2, NB=32)])
+    sweep(1024, 24, [dict(), dict(KS=2, NB=64)])
+    sys.stderr.write("\n## B=2048 KS=2\n"); sys.stderr.flush()
+    run(2048, 6, reps=1, DEBUG=1, KS=2, NB=64)
 if which in ("crash",):
     run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
 if which in ("trace2",):

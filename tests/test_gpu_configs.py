@@ -80,6 +80,41 @@ def test_throughput_mode_forward_vs_fp64_oracle(B):
     assert max(rel_err(irm.cpu().numpy(), irmo)) < TOL, (rel_err(irm.cpu().numpy(), irmo), cfg)
 
 
+def test_ragged_last_group_forward_vs_fp64_oracle():
+    """5 tiles of 64 over 3 batch groups (2, 2, 1): the last group walks the K-slice with its own schedule classes
+    (4 sub-chunks per K-slice > 3 TMEM weight buffers, so the tiles of a step reuse what their predecessor left)."""
+    F, R, K, T, B = 513, 1000, 6, 3, 320
+    p = synth.model_params(F, R, K)
+    x, lens = _synthetic_batch(B, T, F, 321)
+    eng = engine.DrnmfEngine(F, R, K)
+    eng.set_params(p)
+    H, irm = eng.forward(torch.as_tensor(x, device="cuda"))
+    cfg = eng.recurrent_config()
+    assert cfg["impl"] == "tcgen05" and cfg["NB"] == 64 and cfg["n_tiles"] == 2 and cfg["groups"] == 3, cfg
+    Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+    assert max(rel_err(H.cpu().numpy(), Ho)) < TOL, (rel_err(H.cpu().numpy(), Ho), cfg)
+
+
+def test_split_epilogue_forward_vs_fp64_oracle():
+    """>= 12 tiles of 64 utterances: K-split 2 plan, 4096 outputs per item, warps 4-7 push and own half of the rows
+    (recurrent_tc.cu, split epilogue).  Ragged last tile, masked frames, vector alph off / on."""
+    F, R, K, T, B = 513, 1000, 5, 3, 800
+    for vec in (False, True):
+        p = synth.model_params(F, R, K)
+        if vec:
+            rng = np.random.default_rng(77)
+            p["log_alph"] = (p["log_alph"][:, None] + 0.1 * rng.standard_normal((K, R))).astype(np.float32)
+        x, lens = _synthetic_batch(B, T, F, 900 + int(vec))
+        eng = engine.DrnmfEngine(F, R, K)
+        eng.set_params(p)
+        H, irm = eng.forward(torch.as_tensor(x, device="cuda"))
+        cfg = eng.recurrent_config()
+        assert cfg["impl"] == "tcgen05" and cfg["KS"] == 2 and cfg["NB"] == 64, cfg
+        Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+        assert max(rel_err(H.cpu().numpy(), Ho)) < TOL, (vec, rel_err(H.cpu().numpy(), Ho), cfg)
+        assert max(rel_err(irm.cpu().numpy(), irmo)) < TOL, (vec, rel_err(irm.cpu().numpy(), irmo), cfg)
+
+
 GRAD_CASES = [
     # north-star model: Rp=1024 -> MT=8 x KS=8 clusters, mirrored-block weight loads (scalar alph)
     dict(F=513, R=1000, K=25, B=4, T=6, tied=False, vec=False, alph=None, lead=False),
