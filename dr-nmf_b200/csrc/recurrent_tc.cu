@@ -1445,6 +1445,9 @@ static RecPlan plan_recurrent(const drnmf_handle* h, int B, int KS, int NB, int 
     // loads that are on the critical path (measured 6.15 -> 6.00 us/step with 2 instead of 4 pieces in flight)
     grow(p.RST, 2 * red_slot, 2);
     grow(p.HST, h_stage, min(2 * p.NSC, RT_MAXH));
+  } else if (p.a.split) {
+    // K-split 2 x 64 columns: the loaders bound the item and every byte prefetched ahead competes with them for the
+    // shared-memory port - the minimal rings are the fastest (measured: H2 W2 115 TF/s, H3 W2 112, H2 W4 113)
   } else {
     grow(p.RST, 2 * red_slot, 2);
     grow(p.HST, h_stage, 3);

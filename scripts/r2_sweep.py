@@ -18,7 +18,7 @@ fl_rec = 2.0 * R * R * (K - 1)
 
 def setenv(**kw):
     for k in ("DRNMF_REC_NB", "DRNMF_REC_G", "DRNMF_REC_PUB", "DRNMF_REC_DEBUG", "DRNMF_REC_KS", "DRNMF_REC_VERBOSE", "DRNMF_REC_TRACE",
-              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D", "DRNMF_REC_LLT", "DRNMF_REC_LL", "DRNMF_REC_NOSYM", "DRNMF_REC_PUSH", "DRNMF_REC_DEFER"):
+              "DRNMF_REC_HST", "DRNMF_REC_RST", "DRNMF_REC_WST", "DRNMF_REC_H2D", "DRNMF_REC_LLT", "DRNMF_REC_LL", "DRNMF_REC_NOSYM", "DRNMF_REC_NOSPLIT"):
         os.environ.pop(k, None)
     for k, v in kw.items():
         if v is not None:
@@ -88,7 +88,10 @@ if which in ("final",):
     sweep(128, 96, [dict(), dict(KS=8, NB=64, G=1)])
     sweep(256, 96, [dict()])
     sweep(512, 48, [dict(), dict(PUB="thread")])
-    sweep(2048, 12, [dict(), dict(PUB="thread")])
+    sweep(768, 32, [dict()])
+    sweep(1024, 24, [dict(), dict(NOSPLIT=1)])
+    sweep(2048, 12, [dict(), dict(NOSPLIT=1), dict(KS=4, NB=64, PUB="thread")])
+    sweep(4096, 6, [dict()])
 if which in ("b64x",):
     sweep(64, T, [dict(), dict(HST=2, RST=1, WST=2), dict(HST=2, RST=2, WST=2), dict(HST=4, RST=1, WST=2), dict(HST=2, RST=1, WST=4),
                   dict(HST=2, RST=1, WST=3), dict(HST=3, RST=1, WST=2)])
@@ -117,6 +120,18 @@ if which in ("ks2",):
     sweep(1024, 24, [dict(), dict(KS=2, NB=64)])
     sys.stderr.write("\n## B=2048 KS=2\n"); sys.stderr.flush()
     run(2048, 6, reps=1, DEBUG=1, KS=2, NB=64)
+if which in ("rings",):
+    sweep(2048, 12, [dict(), dict(HST=2, WST=4), dict(HST=2, WST=3), dict(HST=3, WST=2, RST=1), dict(HST=2, WST=2)])
+    sweep(1024, 24, [dict(), dict(HST=2, WST=4)])
+if which in ("rings2",):
+    sweep(512, 48, [dict(), dict(HST=2, WST=2), dict(HST=2, WST=3), dict(HST=3, WST=2), dict(HST=2, WST=4)])
+    sweep(256, 96, [dict(), dict(HST=2, WST=2), dict(HST=2, WST=4)])
+    sweep(128, 96, [dict(), dict(HST=2, WST=2), dict(HST=4, WST=2), dict(HST=2, WST=4)])
+    sweep(4096, 6, [dict(), dict(HST=2, WST=2)])
+if which in ("dbg2",):
+    for B, Tn in ((2048, 6), (512, 12)):
+        sys.stderr.write("\n## B=%d (default plan)\n" % B); sys.stderr.flush()
+        run(B, Tn, reps=1, DEBUG=1)
 if which in ("crash",):
     run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
 if which in ("trace2",):
