@@ -61,6 +61,21 @@ __device__ __forceinline__ float epi_gram_value(int m, int n, int R_valid, float
 }
 // DivideAbyAplusB (custom_layers.py:41-45): exp(log(1e-7 + A) - log(1e-7 + A + B)), optional 'square' transform (mode 1).
 // mode 2: the SNMF baseline's ratio mask  A / (1e-9 + A + B)  (enhance.py:848-852).
+// beta-divergence pieces of one element (sparse_nmf_gpu.m:212-276, beta != 2): lam = max(W H, flr), v = V (made
+// positive on entry, :201-205).  P = lam^(beta-1), Q = v lam^(beta-2), d = the element's divergence.
+__device__ __forceinline__ void epi_beta_values(float lam, float v, float beta, float& P, float& Q, float& d) {
+  if (beta == 1.f) {            // KL (:212-216, :269)
+    const float r = v / lam;
+    P = 1.f; Q = r; d = v * logf(r) - v + lam;
+  } else if (beta == 0.f) {     // IS (:222-226 with beta = 0, :273)
+    const float r = v / lam;
+    P = 1.f / lam; Q = r / lam; d = r - logf(r) - 1.f;
+  } else {                      // generic (:222-226, :275-276)
+    P = powf(lam, beta - 1.f); Q = v * powf(lam, beta - 2.f);
+    d = (powf(v, beta) + (beta - 1.f) * powf(lam, beta) - beta * v * P) / (beta * (beta - 1.f));
+  }
+}
+
 __device__ __forceinline__ float epi_irm_value(float s, float n, int mode) {
   if (mode == 2) return s / (1e-9f + s + n);
   if (mode == 1) { s *= s; n *= n; }

@@ -68,7 +68,7 @@ int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const f
 int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st);
 
 // ---- gemm: C = A (M x K, K-major) . B^T (N x K, K-major) with a fused epilogue --------------------
-enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2, EPI_LAMBDA = 3 };
+enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2, EPI_LAMBDA = 3, EPI_LAMBDA_B = 4 };
 struct GemmArgs {
   const float *A_hi, *A_lo; int lda;     // M x Kd
   const float *B_hi, *B_lo; int ldb;     // N x Kd
@@ -87,6 +87,11 @@ struct GemmArgs {
   const float* Vref; int ldv;
   double* div_partials;
   float flr;
+  // EPI_LAMBDA_B (beta-divergence, beta != 2; sparse_nmf_gpu.m:212-276): with L = max(acc, flr) the epilogue writes
+  // P = L^(beta-1) to C/C_lo/CT/CT_lo (the operand that takes Lambda's place in the updates) and Q = Vref . L^(beta-2)
+  // to Q/Q_lo/QT/QT_lo (the operand that takes V's place), and sums the beta-divergence into div_partials.
+  float beta;
+  float *Q, *Q_lo, *QT, *QT_lo;
 };
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
@@ -105,8 +110,8 @@ int launch_mask_istft(const float* stack, const float* mask, const int64_t* fidx
                       int max_frames, int N, int hop, int64_t total_frames, float* frames_tmp, float* out_audio,
                       cudaStream_t st);
 // ---- snmf.cu ---------------------------------------------------------------------------------------
-size_t snmf_workspace_bytes(int F, int n, int R);
-int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
+size_t snmf_workspace_bytes(int F, int n, int R, float beta = 2.f);
+int snmf_mu_ed(int F, int n, int R, float beta, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
                int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
                double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st,
                drnmf_allreduce_fn allreduce, void* user);

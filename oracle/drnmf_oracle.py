@@ -208,8 +208,10 @@ def ista_ed(x, W, H, lam1, alph, K):
 # --------------------------------------------------------------------------------------------
 # A.3  sparse NMF, Euclidean branch (sparseNMF/sparse_nmf_gpu.m) + chunk driver (snmf.py)
 # --------------------------------------------------------------------------------------------
-def sparse_nmf_ed(V, params, dtype=np.float64, rng=None):
-    """sparse_nmf_gpu.m:72-304 restricted to cf='ed' (beta=2; every shipped config, enhance.py:568,590).
+def sparse_nmf_ed(V, params, dtype=np.float64, rng=None, beta=2.0):
+    """sparse_nmf_gpu.m:72-304.  beta = 2 is cf='ed' (every shipped config, enhance.py:568,590); beta = 1 ('kl', the
+    solver's own default, :100-115) and beta = 0 ('is') and any other beta follow the generic branches (:212-226,
+    :232-260, :266-276) - see sparse_nmf_beta below.
 
     params keys as in the .m: sparsity, max_iter, conv_eps, r, init_w, init_h ('ones' or array), w_update_ind,
     h_update_ind.  MATLAB's legacy rand('seed') stream (:119,:126,:132,:139) cannot be reproduced: missing
@@ -250,28 +252,50 @@ def sparse_nmf_ed(V, params, dtype=np.float64, rng=None):
     h = h * wn[:, None]
     flr = dtype(1e-9)
     lam = np.maximum(w @ h, flr)
+    if beta != 2.0 and np.any(V == 0):                                    # :201-205
+        V = V.copy()
+        V[V == 0] = V[V > 0].min()
     last_cost = np.inf
     divs, costs = [], []
     update_h, update_w = h_ind.sum() > 0, w_ind.sum() > 0
     for it in range(1, max_iter + 1):
         if update_h:                                                      # :217-221, :228
-            dph = w[:, h_ind].T @ lam + sp[h_ind]
+            if beta == 2.0:
+                P, Q = lam, V
+            elif beta == 1.0:                                             # :212-216 (W^T 1 = column sums of W)
+                P, Q = np.ones_like(lam), V / lam
+            else:                                                         # :222-226
+                P, Q = lam ** (beta - 1), V * lam ** (beta - 2)
+            dph = w[:, h_ind].T @ P + sp[h_ind]
             dph = np.maximum(dph, flr)
-            dmh = w[:, h_ind].T @ V
+            dmh = w[:, h_ind].T @ Q
             h[h_ind] = h[h_ind] * dmh / dph
             lam = np.maximum(w @ h, flr)
         if update_w:                                                      # :243-249, :262-263
             hw = h[w_ind]
             ww = w[:, w_ind]
-            VH = V @ hw.T
-            LH = lam @ hw.T
+            if beta == 2.0:
+                P, Q = lam, V
+            elif beta == 1.0:                                             # :232-241 (1 H^T = row sums of H)
+                P, Q = np.ones_like(lam), V / lam
+            else:                                                         # :250-259
+                P, Q = lam ** (beta - 1), V * lam ** (beta - 2)
+            VH = Q @ hw.T
+            LH = P @ hw.T
             dpw = LH + np.sum(VH * ww, axis=0, keepdims=True) * ww
             dpw = np.maximum(dpw, flr)
             dmw = VH + np.sum(LH * ww, axis=0, keepdims=True) * ww
             w[:, w_ind] = ww * dmw / dpw
             w = w / np.sqrt(np.sum(w ** 2, axis=0))
             lam = np.maximum(w @ h, flr)
-        div = np.sum((V - lam) ** 2)                                      # :271  (no 1/2)
+        if beta == 2.0:
+            div = np.sum((V - lam) ** 2)                                  # :271  (no 1/2)
+        elif beta == 1.0:
+            div = np.sum(V * np.log(V / lam) - V + lam)                   # :269
+        elif beta == 0.0:
+            div = np.sum(V / lam - np.log(V / lam) - 1)                   # :273
+        else:
+            div = np.sum(V ** beta + (beta - 1) * lam ** beta - beta * V * lam ** (beta - 1)) / (beta * (beta - 1))
         cost = div + np.sum(sp * h)                                       # :278
         divs.append(float(div)), costs.append(float(cost))
         if it > 1 and conv_eps > 0:                                       # :288-296
@@ -280,6 +304,13 @@ def sparse_nmf_ed(V, params, dtype=np.float64, rng=None):
                 break
         last_cost = cost
     return w, h, {"div": np.array(divs), "cost": np.array(costs)}
+
+
+def sparse_nmf_beta(V, params, dtype=np.float64, rng=None):
+    """sparse_nmf_gpu.m:100-115: cf in {'is', 'kl', 'ed'} selects beta = 0 / 1 / 2, otherwise params['beta'] (default 1)."""
+    cf = params.get("cf", "kl")
+    beta = {"is": 0.0, "kl": 1.0, "ed": 2.0}.get(cf, float(params.get("beta", 1.0)))
+    return sparse_nmf_ed(V, params, dtype=dtype, rng=rng, beta=beta)
 
 
 def sparse_nmf_chunked(V, params, frame_batch_size=None, save_H=True, dtype=np.float64, rng=None):
