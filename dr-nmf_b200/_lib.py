@@ -71,6 +71,9 @@ def load():
         "drnmf_snmf_workspace_bytes": (sz, [i32, i32, i32]),
         "drnmf_snmf_mu_ed_dist": (i32, [i32, i32, i32, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, C.POINTER(i32), i32, vp, sz, vp,
                                         ALLREDUCE_FN, vp]),
+        "drnmf_snmf_mu_beta": (i32, [i32, i32, i32, f32, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, C.POINTER(i32), i32, vp, sz,
+                                     vp, ALLREDUCE_FN, vp]),
+        "drnmf_snmf_beta_workspace_bytes": (sz, [i32, i32, i32, f32]),
         "drnmf_snmf_irm": (i32, [i32, i32, i32, i32, vp, vp, vp, i32, vp, sz, vp]),
         "drnmf_snmf_irm_workspace_bytes": (sz, [i32, i32, i32]),
         "drnmf_ista_ed": (i32, [i32, i32, i32, vp, vp, vp, f32, f32, i32, i32, vp, sz, vp]),

@@ -325,9 +325,11 @@ int drnmf_mask_istft(const float* stack, const float* mask, const int64_t* fidx,
                            (cudaStream_t)stream);
 }
 
-size_t drnmf_snmf_workspace_bytes(int F, int n, int R) {
+size_t drnmf_snmf_workspace_bytes(int F, int n, int R) { return drnmf_snmf_beta_workspace_bytes(F, n, R, 2.f); }
+
+size_t drnmf_snmf_beta_workspace_bytes(int F, int n, int R, float beta) {
   if (F < 1 || n < 1 || R < 1) return 0;
-  return snmf_workspace_bytes(F, n, R) + 2 * al((size_t)R);
+  return snmf_workspace_bytes(F, n, R, beta) + 2 * al((size_t)R);
 }
 
 int drnmf_snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update_host,
@@ -341,8 +343,17 @@ int drnmf_snmf_mu_ed_dist(int F, int n, int R, const float* V, float* W, float* 
                           const uint8_t* h_update_host, float sparsity, int max_iter, float conv_eps, double* cost_host,
                           double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream,
                           drnmf_allreduce_fn allreduce, void* user) {
+  return drnmf_snmf_mu_beta(F, n, R, 2.f, V, W, H, w_update_host, h_update_host, sparsity, max_iter, conv_eps, cost_host,
+                            div_host, iters_host, flags, ws, ws_bytes, stream, allreduce, user);
+}
+
+int drnmf_snmf_mu_beta(int F, int n, int R, float beta, const float* V, float* W, float* H, const uint8_t* w_update_host,
+                       const uint8_t* h_update_host, float sparsity, int max_iter, float conv_eps, double* cost_host,
+                       double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream,
+                       drnmf_allreduce_fn allreduce, void* user) {
   int rc = check_device(nullptr);
   if (rc) return rc;
+  DRNMF_CHECK(beta == beta, "drnmf_snmf_mu_beta: beta is NaN");
   DRNMF_CHECK(V && W && H && cost_host && div_host && iters_host && ws, "drnmf_snmf_mu_ed: NULL argument");
   DRNMF_CHECK(F >= 1 && n >= 1 && R >= 1 && max_iter >= 1, "drnmf_snmf_mu_ed: bad sizes");
   DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
@@ -350,14 +361,14 @@ int drnmf_snmf_mu_ed_dist(int F, int n, int R, const float* V, float* W, float* 
   // update masks arrive as host bytes (they are tiny and decide which GEMMs run); device copies live in the workspace tail
   int any_w = 0, any_h = 0;
   for (int r = 0; r < R; ++r) { any_w |= (!w_update_host || w_update_host[r]); any_h |= (!h_update_host || h_update_host[r]); }
-  const size_t core = snmf_workspace_bytes(F, n, R);
+  const size_t core = snmf_workspace_bytes(F, n, R, beta);
   const size_t need = core + 2 * al((size_t)R);
   if (ws_bytes < need) { set_error("snmf workspace too small: need %zu bytes, got %zu", need, ws_bytes); return DRNMF_ERR_WORKSPACE; }
   uint8_t* wmask = nullptr; uint8_t* hmask = nullptr;
   if (w_update_host) { wmask = (uint8_t*)ws + core; DRNMF_CUDA(cudaMemcpyAsync(wmask, w_update_host, R, cudaMemcpyHostToDevice, st)); }
   if (h_update_host) { hmask = (uint8_t*)ws + core + al((size_t)R); DRNMF_CUDA(cudaMemcpyAsync(hmask, h_update_host, R, cudaMemcpyHostToDevice, st)); }
   const bool simt = pick_impl(flags) == DRNMF_IMPL_SIMT;
-  rc = snmf_mu_ed(F, n, R, V, W, H, wmask, hmask, any_w, any_h, sparsity, max_iter, conv_eps, cost_host, div_host, iters_host,
+  rc = snmf_mu_ed(F, n, R, beta, V, W, H, wmask, hmask, any_w, any_h, sparsity, max_iter, conv_eps, cost_host, div_host, iters_host,
                   ws, core, simt, st, allreduce, user);
   if (rc) return rc;
   int g = gemm_device_error(st);

@@ -44,16 +44,24 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
       } else if (EPI == EPI_RECON) {
         a.C[(size_t)m * a.ldc + n] = epi_irm_value(acc[i][j], acc2[i][j], a.square);
         if (a.C_S) { a.C_S[(size_t)m * a.ldc + n] = acc[i][j]; a.C_N[(size_t)m * a.ldc + n] = acc2[i][j]; }
-      } else {
+      } else if (EPI == EPI_LAMBDA) {
         const float v = fmaxf(acc[i][j], a.flr);
         a.C[(size_t)m * a.ldc + n] = v; a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(v);
         a.CT[(size_t)n * a.ldct + m] = v; a.CT_lo[(size_t)n * a.ldct + m] = tf32_lo(v);
         const float d = a.Vref[(size_t)m * a.ldv + n] - v;
         dsum = fmaf(d, d, dsum);
+      } else {
+        float P, Q, d;
+        epi_beta_values(fmaxf(acc[i][j], a.flr), a.Vref[(size_t)m * a.ldv + n], a.beta, P, Q, d);
+        a.C[(size_t)m * a.ldc + n] = P; a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(P);
+        a.CT[(size_t)n * a.ldct + m] = P; a.CT_lo[(size_t)n * a.ldct + m] = tf32_lo(P);
+        a.Q[(size_t)m * a.ldc + n] = Q; a.Q_lo[(size_t)m * a.ldc + n] = tf32_lo(Q);
+        a.QT[(size_t)n * a.ldct + m] = Q; a.QT_lo[(size_t)n * a.ldct + m] = tf32_lo(Q);
+        dsum += d;
       }
     }
   }
-  if (EPI == EPI_LAMBDA) {
+  if (EPI == EPI_LAMBDA || EPI == EPI_LAMBDA_B) {
     __shared__ float red[SIMT_THREADS / 32];
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dsum;
@@ -73,6 +81,7 @@ int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
     case EPI_GRAM:  k_gemm_simt<EPI_GRAM><<<grid, SIMT_THREADS, 0, st>>>(a); break;
     case EPI_RECON: k_gemm_simt<EPI_RECON><<<grid, SIMT_THREADS, 0, st>>>(a); break;
     case EPI_LAMBDA: k_gemm_simt<EPI_LAMBDA><<<grid, SIMT_THREADS, 0, st>>>(a); break;
+    case EPI_LAMBDA_B: k_gemm_simt<EPI_LAMBDA_B><<<grid, SIMT_THREADS, 0, st>>>(a); break;
   }
   count_launch();
   DRNMF_CUDA(cudaGetLastError());
@@ -279,12 +288,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
               const float4* vp = reinterpret_cast<const float4*>(a.Vref + (size_t)m * a.ldv + n);
 #pragma unroll
               for (int i = 0; i < 4; ++i) { const float4 t4 = __ldg(vp + i); vr[4 * i] = t4.x; vr[4 * i + 1] = t4.y; vr[4 * i + 2] = t4.z; vr[4 * i + 3] = t4.w; }
+              float qv[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const bool in = (n + i < a.N_valid);
                 hi[i] = in ? fmaxf(v[i], a.flr) : 0.f;
+                if (EPI == EPI_LAMBDA_B) {         // beta != 2: P = L^(beta-1) replaces Lambda, Q = V L^(beta-2) replaces V
+                  float P = 0.f, Q = 0.f, d = 0.f;
+                  if (in) epi_beta_values(hi[i], vr[i], a.beta, P, Q, d);
+                  hi[i] = P; qv[i] = Q; dsum += d;
+                } else if (in) { const float d = vr[i] - hi[i]; dsum = fmaf(d, d, dsum); }
                 lo[i] = tf32_lo(hi[i]);
-                if (in) { const float d = vr[i] - hi[i]; dsum = fmaf(d, d, dsum); }
               }
               float4* d1 = reinterpret_cast<float4*>(a.C + (size_t)m * a.ldc + n);
               float4* d2 = reinterpret_cast<float4*>(a.C_lo + (size_t)m * a.ldc + n);
@@ -296,12 +310,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 16; ++i)
                 if (n + i < a.N_valid) { a.CT[(size_t)(n + i) * a.ldct + m] = hi[i]; a.CT_lo[(size_t)(n + i) * a.ldct + m] = lo[i]; }
+              if (EPI == EPI_LAMBDA_B) {
+                float4* q1 = reinterpret_cast<float4*>(a.Q + (size_t)m * a.ldc + n);
+                float4* q2 = reinterpret_cast<float4*>(a.Q_lo + (size_t)m * a.ldc + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  q1[i] = make_float4(qv[4 * i], qv[4 * i + 1], qv[4 * i + 2], qv[4 * i + 3]);
+                  q2[i] = make_float4(tf32_lo(qv[4 * i]), tf32_lo(qv[4 * i + 1]), tf32_lo(qv[4 * i + 2]), tf32_lo(qv[4 * i + 3]));
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (n + i < a.N_valid) { a.QT[(size_t)(n + i) * a.ldct + m] = qv[i]; a.QT_lo[(size_t)(n + i) * a.ldct + m] = tf32_lo(qv[i]); }
+              }
             }
           }
         }
       }
     }
-    if (EPI == EPI_LAMBDA) {
+    if (EPI == EPI_LAMBDA || EPI == EPI_LAMBDA_B) {
       float* red = reinterpret_cast<float*>(tmem_slot + 2);
       for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
       if (lane_id() == 0) red[q] = dsum;
@@ -363,7 +389,7 @@ static int gemm_error_word(int** out) {
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
   DRNMF_CHECK(a.lda % 4 == 0 && a.ldb % 4 == 0, "tcgen05 GEMM needs row strides that are multiples of 4 floats");
   if (epi == EPI_STORE || epi == EPI_GRAM) DRNMF_CHECK(a.ldc % 4 == 0 && a.N_valid % 16 == 0, "tcgen05 GEMM store needs ldc%%4==0, N%%16==0");
-  if (epi == EPI_LAMBDA) DRNMF_CHECK(a.ldc % 4 == 0 && a.ldv % 4 == 0, "EPI_LAMBDA needs ldc%%4==0 and ldv%%4==0");
+  if (epi == EPI_LAMBDA || epi == EPI_LAMBDA_B) DRNMF_CHECK(a.ldc % 4 == 0 && a.ldv % 4 == 0, "EPI_LAMBDA needs ldc%%4==0 and ldv%%4==0");
   int* errw = nullptr;
   int rc = gemm_error_word(&errw);
   if (rc) return rc;
@@ -377,6 +403,7 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
     case EPI_GRAM:  return wide ? launch_tc_impl<EPI_GRAM, 256>(a, st, errw) : launch_tc_impl<EPI_GRAM, 128>(a, st, errw);
     case EPI_RECON: return launch_tc_impl<EPI_RECON, 128>(a, st, errw);
     case EPI_LAMBDA: return wide ? launch_tc_impl<EPI_LAMBDA, 256>(a, st, errw) : launch_tc_impl<EPI_LAMBDA, 128>(a, st, errw);
+    case EPI_LAMBDA_B: return wide ? launch_tc_impl<EPI_LAMBDA_B, 256>(a, st, errw) : launch_tc_impl<EPI_LAMBDA_B, 128>(a, st, errw);
   }
   return DRNMF_ERR_INVALID;
 }

@@ -6,6 +6,10 @@
 //                                                                       two split-K (F x n).(n x R) GEMMs + k_mu_w
 //   W <- W ./ colnorm(W) ; L <- max(W H, flr)           (:262-263)
 //   div = |V - L|_F^2 (no 1/2) ; cost = div + mu * sum(H)   (:271,278) ; stop when |d cost| / cost_prev < conv_eps (:288-296)
+// beta != 2 (KL, IS, generic beta-divergence; :212-216, :222-226, :232-241, :250-259, :266-276): the same iteration with
+// P = L^(beta-1) in the place of L and Q = V .* L^(beta-2) in the place of V - the lambda GEMM's epilogue
+// (EPI_LAMBDA_B) writes P and Q in all layouts and sums the divergence, everything else is shared.  (For beta = 1 the
+// .m file writes W^T 1 and 1 H^T as column / row sums; P = 1 gives the same numbers through the GEMM.)
 // Both operand layouts of every matrix are kept (frame-major for the contractions over F and R, feature-major for the
 // contractions over frames) together with their tf32 remainders; the epilogues write all of them.
 #include "internal.h"
@@ -25,6 +29,9 @@ struct SnmfWs {
   float *Vm_hi, *Vm_lo;   // F x nk      V
   float *Lt_hi, *Lt_lo;   // nk x Fk     L^T
   float *Lm_hi, *Lm_lo;   // F x nk      L
+  float *Qt_hi, *Qt_lo;   // nk x Fk     (V .* L^(beta-2))^T    beta != 2 only (L* then hold P = L^(beta-1))
+  float *Qm_hi, *Qm_lo;   // F x nk      V .* L^(beta-2)
+  float* vmin;            // smallest positive entry of V (:201-205)
   float *dph, *dmh;       // nk x Rk     (W^T L)^T , (W^T V)^T
   float *VHp, *LHp;       // splits x F x Rk   split-K partials of V H^T, L H^T
   double *div_part, *hsum_part, *scal;   // per-CTA partial sums; scal[0] = div, scal[1] = mu * sum(H)
@@ -35,7 +42,7 @@ struct SnmfWs {
 
 static size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
-static SnmfWs carve_snmf(int F, int n, int R, void* base) {
+static SnmfWs carve_snmf(int F, int n, int R, void* base, float beta = 2.f) {
   SnmfWs w;
   w.Fk = round_up(F, 32); w.Rk = round_up(R, 32); w.nk = round_up(n, 128);
   int total_kb = w.nk / 32;
@@ -56,6 +63,12 @@ static SnmfWs carve_snmf(int F, int n, int R, void* base) {
   w.Vm_hi = (float*)take(F_ * nk * 4); w.Vm_lo = (float*)take(F_ * nk * 4);
   w.Lt_hi = (float*)take(nk * Fk * 4); w.Lt_lo = (float*)take(nk * Fk * 4);
   w.Lm_hi = (float*)take(F_ * nk * 4); w.Lm_lo = (float*)take(F_ * nk * 4);
+  w.Qt_hi = w.Qt_lo = w.Qm_hi = w.Qm_lo = nullptr;
+  if (beta != 2.f) {
+    w.Qt_hi = (float*)take(nk * Fk * 4); w.Qt_lo = (float*)take(nk * Fk * 4);
+    w.Qm_hi = (float*)take(F_ * nk * 4); w.Qm_lo = (float*)take(F_ * nk * 4);
+  }
+  w.vmin = (float*)take(256);
   w.dph = (float*)take(nk * Rk * 4); w.dmh = (float*)take(nk * Rk * 4);
   w.VHp = (float*)take((size_t)w.splits * F_ * Rk * 4); w.LHp = (float*)take((size_t)w.splits * F_ * Rk * 4);
   w.n_div_part = (int)((nk / 64) * ((Fk + 63) / 64 + 1));            // upper bound over both GEMM tilings
@@ -73,7 +86,8 @@ static SnmfWs carve_snmf(int F, int n, int R, void* base) {
 __global__ void k_split_both(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ rm_hi,
                              float* __restrict__ rm_lo, int rm_rows, int ld_rm, float* __restrict__ tr_hi,
                              float* __restrict__ tr_lo, int tr_rows, int ld_tr, const float* __restrict__ row_scale,
-                             const float* __restrict__ col_scale, int scale_is_div) {
+                             const float* __restrict__ col_scale, int scale_is_div,
+                             const float* __restrict__ zero_fill = nullptr) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int y = threadIdx.y; y < 32; y += 8) {
@@ -83,6 +97,7 @@ __global__ void k_split_both(const float* __restrict__ src, int rows, int cols, 
       v = src[(size_t)r * ld_src + c];
       if (row_scale) v = scale_is_div ? v / row_scale[r] : v * row_scale[r];
       if (col_scale) v = scale_is_div ? v / col_scale[c] : v * col_scale[c];
+      if (zero_fill && v == 0.f) v = *zero_fill;          // sparse_nmf_gpu.m:201-205
     }
     tile[y][threadIdx.x] = v;
     if (rm_hi && r < rm_rows && c < ld_rm) { rm_hi[(size_t)r * ld_rm + c] = v; rm_lo[(size_t)r * ld_rm + c] = tf32_lo(v); }
@@ -95,6 +110,17 @@ __global__ void k_split_both(const float* __restrict__ src, int rows, int cols, 
       tr_hi[(size_t)c * ld_tr + r] = v; tr_lo[(size_t)c * ld_tr + r] = tf32_lo(v);
     }
   }
+}
+
+// smallest positive entry (positive floats order like their bit patterns): *out starts at +inf
+__global__ void k_min_positive(const float* __restrict__ src, size_t n, unsigned* __restrict__ out) {
+  unsigned m = 0x7f800000u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    if (v > 0.f) m = min(m, __float_as_uint(v));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(out, m);
 }
 
 // column l2 norms of a row-major (rows x cols) matrix: grid ceil(cols/32), block (32, 8)
@@ -245,7 +271,7 @@ static int run_gemm_impl(bool simt, GemmEpi epi, const GemmArgs& a, cudaStream_t
   return simt ? launch_gemm_simt(epi, a, st) : launch_gemm_tc(epi, a, st);
 }
 
-size_t snmf_workspace_bytes(int F, int n, int R) { return carve_snmf(F, n, R, nullptr).bytes; }
+size_t snmf_workspace_bytes(int F, int n, int R, float beta) { return carve_snmf(F, n, R, nullptr, beta).bytes; }
 
 // sum the split-K partials into split 0 (fixed order), so that one buffer per matrix can be all-reduced across ranks
 __global__ void k_reduce_splits(float* __restrict__ part, int splits, size_t n) {
@@ -256,11 +282,12 @@ __global__ void k_reduce_splits(float* __restrict__ part, int splits, size_t n) 
   part[i] = v;
 }
 
-int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
+int snmf_mu_ed(int F, int n, int R, float beta, const float* V, float* W, float* H, const uint8_t* w_update, const uint8_t* h_update,
                int any_w_update, int any_h_update, float sparsity, int max_iter, float conv_eps, double* cost_host,
                double* div_host, int* iters_host, void* ws, size_t ws_bytes, bool simt, cudaStream_t st,
                drnmf_allreduce_fn allreduce, void* user) {
-  SnmfWs w = carve_snmf(F, n, R, ws);
+  SnmfWs w = carve_snmf(F, n, R, ws, beta);
+  const bool ed = (beta == 2.f);
   if (ws_bytes < w.bytes) { set_error("snmf workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
   const int Fk = w.Fk, Rk = w.Rk, nk = w.nk;
   const float flr = 1e-9f;
@@ -273,8 +300,15 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
                                                                   nullptr, w.wnorm, 1);
   k_split_both<<<dim3((n + 31) / 32, (R + 31) / 32), tb, 0, st>>>(H, R, n, n, w.Hm_hi, w.Hm_lo, R, nk, w.Ht_hi, w.Ht_lo, nk, Rk,
                                                                   w.wnorm, nullptr, 0);
+  if (!ed) {   // :201-205  v(v==0) = min(v(v>0)); with sharded frames the minimum is over all ranks (dtype 2 = float32 MIN)
+    const unsigned inf_bits = 0x7f800000u;
+    DRNMF_CUDA(cudaMemcpyAsync(w.vmin, &inf_bits, 4, cudaMemcpyHostToDevice, st));
+    k_min_positive<<<148 * 4, 256, 0, st>>>(V, (size_t)F * n, reinterpret_cast<unsigned*>(w.vmin));
+    count_launch();
+    if (allreduce && allreduce(user, w.vmin, 1, 2, st)) { set_error("all-reduce callback failed"); return DRNMF_ERR_CUDA; }
+  }
   k_split_both<<<dim3((n + 31) / 32, (F + 31) / 32), tb, 0, st>>>(V, F, n, n, w.Vm_hi, w.Vm_lo, F, nk, w.Vt_hi, w.Vt_lo, nk, Fk,
-                                                                  nullptr, nullptr, 0);
+                                                                  nullptr, nullptr, 0, ed ? nullptr : w.vmin);
   count_launch(4);
   DRNMF_CUDA(cudaGetLastError());
 
@@ -285,7 +319,8 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
     a.M = n; a.N = F; a.Kd = Rk; a.M_valid = n; a.N_valid = F;
     a.C = w.Lt_hi; a.C_lo = w.Lt_lo; a.ldc = Fk; a.CT = w.Lm_hi; a.CT_lo = w.Lm_lo; a.ldct = nk;
     a.Vref = w.Vt_hi; a.ldv = Fk; a.div_partials = w.div_part; a.flr = flr;
-    return run_gemm_impl(simt, EPI_LAMBDA, a, st);
+    a.beta = beta; a.Q = w.Qt_hi; a.Q_lo = w.Qt_lo; a.QT = w.Qm_hi; a.QT_lo = w.Qm_lo;
+    return run_gemm_impl(simt, ed ? EPI_LAMBDA : EPI_LAMBDA_B, a, st);
   };
   auto proj_gemm = [&](const float* A_hi, const float* A_lo, float* out) {   // (n x F).(R x F)^T -> n x Rk
     GemmArgs a{};
@@ -311,13 +346,17 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
 
   int rc;
   if ((rc = lambda_gemm())) return rc;
-  if (!any_w_update && any_h_update) { if ((rc = proj_gemm(w.Vt_hi, w.Vt_lo, w.dmh))) return rc; }   // W^T V is constant
+  // the operands that stand where V stands in the Euclidean updates
+  const float *Xt_hi = ed ? w.Vt_hi : w.Qt_hi, *Xt_lo = ed ? w.Vt_lo : w.Qt_lo;
+  const float *Xm_hi = ed ? w.Vm_hi : w.Qm_hi, *Xm_lo = ed ? w.Vm_lo : w.Qm_lo;
+  const bool dmh_constant = ed && !any_w_update && any_h_update;                                       // W^T V is constant
+  if (dmh_constant) { if ((rc = proj_gemm(w.Vt_hi, w.Vt_lo, w.dmh))) return rc; }
   double last_cost = INFINITY;
   int it = 0;
   for (it = 1; it <= max_iter; ++it) {
     if (any_h_update) {
       if ((rc = proj_gemm(w.Lt_hi, w.Lt_lo, w.dph))) return rc;
-      if (any_w_update) { if ((rc = proj_gemm(w.Vt_hi, w.Vt_lo, w.dmh))) return rc; }
+      if (!dmh_constant) { if ((rc = proj_gemm(Xt_hi, Xt_lo, w.dmh))) return rc; }
       k_mu_h<<<gh, tb, 0, st>>>(w.Ht_hi, w.Ht_lo, w.Hm_hi, w.Hm_lo, w.dph, w.dmh, n, R, Rk, nk, sparsity, flr, h_update, 1, w.hsum_part);
       count_launch();
       if ((rc = lambda_gemm())) return rc;
@@ -326,7 +365,7 @@ int snmf_mu_ed(int F, int n, int R, const float* V, float* W, float* H, const ui
       count_launch();
     }
     if (any_w_update) {
-      if ((rc = corr_gemm(w.Vm_hi, w.Vm_lo, w.VHp))) return rc;
+      if ((rc = corr_gemm(Xm_hi, Xm_lo, w.VHp))) return rc;
       if ((rc = corr_gemm(w.Lm_hi, w.Lm_lo, w.LHp))) return rc;
       // split-K partials -> split 0 with one thread per element (fixed split order): the update kernel below has only
       // ceil(R/32) CTAs, and summing the partials there made it the largest item of an iteration (830 us of 2.2 ms)

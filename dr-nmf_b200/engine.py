@@ -345,10 +345,11 @@ def mask_istft(stack, mask, fidx, N, hop):
 
 # ---- sparse NMF multiplicative updates -------------------------------------------------------------
 def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_update=None, impl=None, group=None,
-               distributed=False):
+               distributed=False, beta=2.0):
     """V (F,n), W (F,R), H (R,n): float32 CUDA tensors (W and H are updated IN PLACE).  w_update / h_update: boolean
     arrays of length R (None = all).  Returns (cost, div) numpy arrays truncated at convergence
-    (sparse_nmf_gpu.m:288-296).  Replaces the MATLAB subprocess of snmf.py:88-113."""
+    (sparse_nmf_gpu.m:288-296).  Replaces the MATLAB subprocess of snmf.py:88-113.  beta selects the divergence
+    (sparse_nmf_gpu.m:100-115): 2 = 'ed' (every shipped config), 1 = 'kl', 0 = 'is', else the generic branch."""
     _require_cuda()
     lib = _lib.load()
     for t in (V, W, H):
@@ -373,7 +374,8 @@ def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_updat
 
     wm, wp = mask(w_update)
     hm, hp = mask(h_update)
-    nb = lib.drnmf_snmf_workspace_bytes(F, n, R)
+    beta = float(beta)
+    nb = lib.drnmf_snmf_beta_workspace_bytes(F, n, R, beta)
     ws = torch.empty(nb + 256, dtype=torch.uint8, device=V.device)
     off = (-ws.data_ptr()) % 256
     flags = _lib.IMPL_SIMT if impl == "simt" else 0
@@ -389,19 +391,19 @@ def snmf_mu_ed(V, W, H, sparsity, max_iter, conv_eps=0.0, w_update=None, h_updat
 
         def _allreduce(user, ptr, count, dtype, stream):
             try:
-                item, tdt = (4, torch.float32) if dtype == 0 else (8, torch.float64)
+                item, tdt = (8, torch.float64) if dtype == 1 else (4, torch.float32)
                 o = int(ptr) - base
                 view = ws[o:o + count * item].view(tdt)
-                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(view, op=dist.ReduceOp.MIN if dtype == 2 else dist.ReduceOp.SUM, group=group)
                 return 0
             except Exception as e:      # an exception must not unwind through the C frames
                 import sys
                 print("[drnmf] all-reduce callback failed: %r" % (e,), file=sys.stderr)
                 return 1
         cb = _lib.ALLREDUCE_FN(_allreduce)
-    _lib.check(lib.drnmf_snmf_mu_ed_dist(F, n, R, _ptr(V), _ptr(W), _ptr(H), wp, hp, float(sparsity), max_iter,
-                                         float(conv_eps), C.c_void_p(cost.ctypes.data), C.c_void_p(div.ctypes.data),
-                                         C.byref(iters), flags, C.c_void_p(ws.data_ptr() + off), nb, _stream(), cb, None))
+    _lib.check(lib.drnmf_snmf_mu_beta(F, n, R, beta, _ptr(V), _ptr(W), _ptr(H), wp, hp, float(sparsity), max_iter,
+                                      float(conv_eps), C.c_void_p(cost.ctypes.data), C.c_void_p(div.ctypes.data),
+                                      C.byref(iters), flags, C.c_void_p(ws.data_ptr() + off), nb, _stream(), cb, None))
     k = iters.value
     return cost[:k].copy(), div[:k].copy()
 

@@ -1,8 +1,9 @@
 """Host-side mirror of the reference's snmf.py: sparse_nmf_matlab (the chunk driver, snmf.py:9-85) and
 sparse_nmf_matlab_on_chunk (snmf.py:88-113), with the MATLAB subprocess + .mat file IPC replaced by the in-process
-CUDA solver behind drnmf_snmf_mu_ed (sparseNMF/sparse_nmf_gpu.m, Euclidean branch).
+CUDA solver behind drnmf_snmf_mu_beta (sparseNMF/sparse_nmf_gpu.m: cf = 'ed' - every shipped config, enhance.py:568,590 -
+'kl', 'is' or a numeric beta).
 
-Differences that are deliberate: only cf='ed' (beta = 2; every shipped config, enhance.py:568,590) is built; errors are
+Differences that are deliberate: errors are
 raised instead of constructed-and-dropped (snmf.py:105-106); missing initialisers are drawn from numpy's
 default_rng(random_seed) because MATLAB's legacy rand('seed') stream (sparse_nmf_gpu.m:119) cannot be reproduced;
 an array init_h is sliced per chunk (the reference would hand MATLAB a mis-sized matrix)."""
@@ -62,9 +63,8 @@ def sparse_nmf_matlab_on_chunk(V, params, verbose=True, useGPU=True, gpuIndex=1,
     """snmf.py:88-113 without MATLAB: parameter handling of sparse_nmf_gpu.m:72-161, solver on the GPU."""
     if not useGPU:
         raise NotImplementedError("there is no CPU solver: the sparse-NMF path runs on the B200 only")
-    cf = params.get("cf", "kl")
-    if cf != "ed" and float(params.get("beta", 1)) != 2:
-        raise NotImplementedError("only the Euclidean branch (cf='ed') is on the DR-NMF path (enhance.py:568,590)")
+    cf = params.get("cf", "kl")                                               # sparse_nmf_gpu.m:100-115
+    beta = {"is": 0.0, "kl": 1.0, "ed": 2.0}.get(cf, float(params.get("beta", 1.0)))
     V = np.asarray(V)
     m, n = V.shape
     rng = np.random.default_rng(int(params.get("random_seed", 1)))
@@ -92,7 +92,7 @@ def sparse_nmf_matlab_on_chunk(V, params, verbose=True, useGPU=True, gpuIndex=1,
     Hd = torch.as_tensor(np.ascontiguousarray(h, dtype=np.float32), device=dev)
     cost, div = _engine.snmf_mu_ed(Vd, Wd, Hd, float(sp.reshape(())), int(params.get("max_iter", 100)),
                                    float(params.get("conv_eps", 0.0)), params.get("w_update_ind", None),
-                                   params.get("h_update_ind", None), impl=impl)
+                                   params.get("h_update_ind", None), impl=impl, beta=beta)
     W = Wd.cpu().numpy().astype(V.dtype)
     H = Hd.cpu().numpy().astype(V.dtype)
     return W, H, {"cost": cost, "div": div}

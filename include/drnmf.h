@@ -148,6 +148,17 @@ DRNMF_API int drnmf_snmf_mu_ed_dist(int F, int n, int R, const float* V, float* 
                           double* div_host, int* iters_host, int flags, void* ws, size_t ws_bytes, void* stream,
                           drnmf_allreduce_fn allreduce, void* user);
 
+/* ---- sparse NMF multiplicative updates for any beta-divergence (sparseNMF/sparse_nmf_gpu.m:100-115 cf/beta selection,
+ * :201-205 zero entries of V raised to its smallest positive entry, :212-226 H updates, :232-260 W updates, :266-276
+ * divergence): beta = 1 is 'kl' (the solver's default), 0 is 'is', 2 is 'ed' (identical to drnmf_snmf_mu_ed), anything
+ * else the generic branch.  Same arguments and conventions as drnmf_snmf_mu_ed_dist; with a non-NULL `allreduce` and
+ * beta != 2 the callback is additionally called once with dtype 2 = float32 MIN over ranks (1 element: min positive V). */
+DRNMF_API int drnmf_snmf_mu_beta(int F, int n, int R, float beta, const float* V, float* W, float* H,
+                       const uint8_t* w_update_host, const uint8_t* h_update_host, float sparsity, int max_iter,
+                       float conv_eps, double* cost_host, double* div_host, int* iters_host, int flags, void* ws,
+                       size_t ws_bytes, void* stream, drnmf_allreduce_fn allreduce, void* user);
+DRNMF_API size_t drnmf_snmf_beta_workspace_bytes(int F, int n, int R, float beta);
+
 /* ---- SNMF baseline ratio mask (enhance.py:847-852): irm = S^ / (1e-9 + S^ + N^) with S^ = W[:, :r] H[:r],
  * N^ = W[:, r:] H[r:].  W (F,R), H (R,n), irm (F,n) row-major device arrays.  One dual-operand tcgen05 GEMM with the ratio
  * fused into its epilogue (the reference: two np.dot and an elementwise divide on the host). */

@@ -16,7 +16,7 @@ import numpy as np
 
 __all__ = [
     "EPS", "alt_params_init", "layer_weights", "structured_U", "rnn_forward", "output_head",
-    "drnmf_forward", "training_loss", "ista_ed", "sparse_nmf_ed", "sparse_nmf_chunked", "train_snmf",
+    "drnmf_forward", "training_loss", "ista_ed", "sparse_nmf_ed", "sparse_nmf_beta", "sparse_nmf_chunked", "train_snmf",
     "snmf_irm", "sqrt_hann", "stft_mc", "stack_reim", "magnitude", "istft_no_div", "istft_mc",
     "reconstruct_x", "wav_quantize", "sdr_db", "masked_seqs_to_frames", "param_count_notebook",
     "reshape_and_pad_stacks", "clip_x_to_y", "get_mask_value", "data_transform", "snr_db", "snmf_savefile_stem",

@@ -203,6 +203,50 @@ def test_configs3_mu_ed_north_star_dictionary():
     np.testing.assert_allclose(div, obj["div"], rtol=2e-5)
 
 
+@pytest.mark.parametrize("cf,beta", [("kl", 1.0), ("is", 0.0), ("beta", 0.5), ("beta", 1.5)])
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_snmf_beta_divergences_vs_oracle(cf, beta, impl):
+    """KL / IS / generic beta-divergence branches of the MU solver (sparse_nmf_gpu.m:201-205, :212-226, :232-260, :266-276)
+    with zeros in V, a frozen half of the dictionary on the second run, and the solver's cf/beta selection (:100-115)
+    through the Python mirror."""
+    from drnmf_b200 import snmf as S
+    F, n, R, iters = 129, 700, 96, 5
+    rng = np.random.default_rng(77)
+    V = (np.abs(rng.standard_normal((F, n))) * 2).astype(np.float32)
+    V[rng.random((F, n)) < 0.03] = 0.0
+    W0 = (np.abs(rng.standard_normal((F, R))) + 0.1).astype(np.float32)
+    H0 = (np.abs(rng.standard_normal((R, n))) + 0.1).astype(np.float32)
+    for wu in (None, np.arange(R) >= R // 2):
+        prm = {"cf": cf, "beta": beta, "sparsity": 0.4, "max_iter": iters, "conv_eps": 0.0, "r": R, "init_w": W0, "init_h": H0}
+        if wu is not None:
+            prm["w_update_ind"] = wu
+        Wo, Ho, obj = O.sparse_nmf_beta(V, prm, dtype=np.float64)
+        W, H, o = S.sparse_nmf_matlab_on_chunk(V, prm, verbose=False, impl=None if impl == "tc" else "simt")
+        assert len(o["cost"]) == iters
+        assert max(rel_err(W, Wo)) < TOL, (cf, beta, rel_err(W, Wo))
+        assert max(rel_err(H, Ho)) < TOL, (cf, beta, rel_err(H, Ho))
+        np.testing.assert_allclose(o["div"], obj["div"], rtol=5e-5)
+        np.testing.assert_allclose(o["cost"], obj["cost"], rtol=5e-5)
+        np.testing.assert_allclose(np.sqrt((W.astype(np.float64) ** 2).sum(0)), 1.0, rtol=1e-5)
+
+
+def test_snmf_beta2_entry_equals_ed_entry():
+    """drnmf_snmf_mu_beta(beta = 2) IS the Euclidean solver: bitwise the same iterates as drnmf_snmf_mu_ed."""
+    F, n, R = 65, 300, 40
+    rng = np.random.default_rng(3)
+    V = np.abs(rng.standard_normal((F, n))).astype(np.float32)
+    W0 = (np.abs(rng.standard_normal((F, R))) + 0.1).astype(np.float32)
+    H0 = (np.abs(rng.standard_normal((R, n))) + 0.1).astype(np.float32)
+    outs = []
+    for b in (2.0, None):
+        Vd, Wd, Hd = (torch.as_tensor(a, device="cuda") for a in (V, W0.copy(), H0.copy()))
+        kw = {} if b is None else {"beta": b}
+        cost, _ = engine.snmf_mu_ed(Vd, Wd, Hd, 0.3, 6, 0.0, **kw)
+        outs.append((Wd.cpu().numpy(), Hd.cpu().numpy(), cost))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+
+
 def test_device_error_is_not_sticky():
     """a latched device-side error word must not poison later calls on the same handle."""
     F, R, K = 33, 16, 2

@@ -385,8 +385,8 @@ def test_snmf_python_mirror_chunk_driver(golden_dir):
     W, H, obj = snmf.sparse_nmf_matlab(g["V"], prm, verbose=False)
     assert max(rel_err(W, g["W"])) < TOL and max(rel_err(H, g["H"])) < TOL
     np.testing.assert_allclose(obj["cost"], g["cost"], rtol=2e-5)
-    with pytest.raises(NotImplementedError):
-        snmf.sparse_nmf_matlab_on_chunk(g["V"], dict(prm, cf="kl"))
+    with pytest.raises(NotImplementedError):                       # there is no CPU solver to fall back to
+        snmf.sparse_nmf_matlab_on_chunk(g["V"], prm, useGPU=False)
 
 
 # ---- training: loss + hand-written BPTT against torch.autograd on the float64 oracle ---------------------------

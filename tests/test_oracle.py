@@ -122,6 +122,39 @@ def test_snmf_golden_and_properties(golden_dir):
     assert np.all(np.diff(o2["cost"]) <= 1e-9 * o2["cost"][:-1])
 
 
+def test_snmf_beta_divergence_branches_are_consistent():
+    """sparse_nmf_gpu.m has four code paths (beta = 1, 2, 0-divergence, generic).  The MATLAB solver cannot run here
+    [unpinned]; what can be checked is that the restated branches agree with one another where the formulas meet:
+    the generic branch at beta -> 1 equals the KL branch, at beta -> 2 it gives the ED iterates with HALF the ED
+    divergence (:271 has no 1/2, :275-276 divides by beta (beta - 1) = 2), at beta -> 0 the IS divergence; zeros of V
+    are raised to its smallest positive entry for beta != 2 only (:201-205); KL cost is non-increasing."""
+    rng = np.random.default_rng(11)
+    F, n, R = 24, 90, 7
+    V = np.abs(rng.standard_normal((F, n)))
+    V[rng.random((F, n)) < 0.05] = 0.0
+    base = {"sparsity": 0.3, "max_iter": 12, "conv_eps": 0.0, "r": R, "init_w": np.abs(rng.standard_normal((F, R))) + 0.1,
+            "init_h": np.abs(rng.standard_normal((R, n))) + 0.1}
+    eps = 1e-7
+    Wk, Hk, ok = O.sparse_nmf_beta(V, dict(base, cf="kl"))
+    Wg, Hg, og = O.sparse_nmf_beta(V, dict(base, cf="beta", beta=1.0 + eps))
+    np.testing.assert_allclose(Wg, Wk, rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(Hg, Hk, rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(og["div"], ok["div"], rtol=1e-4)
+    assert np.all(np.diff(ok["cost"]) <= 1e-9 * ok["cost"][:-1])
+    Vp = V.copy(); Vp[Vp == 0] = Vp[Vp > 0].min()
+    We, He, oe = O.sparse_nmf_beta(Vp, dict(base, cf="ed"))
+    Wg, Hg, og = O.sparse_nmf_beta(Vp, dict(base, cf="beta", beta=2.0 + eps))
+    np.testing.assert_allclose(Wg, We, rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(og["div"], 0.5 * oe["div"], rtol=1e-4)
+    _, _, oe0 = O.sparse_nmf_beta(V, dict(base, cf="ed"))                 # ED keeps the zeros of V
+    assert abs(oe0["div"][0] - oe["div"][0]) > 0
+    Wi, Hi, oi = O.sparse_nmf_beta(V, dict(base, cf="is"))
+    Wg, Hg, og = O.sparse_nmf_beta(V, dict(base, cf="beta", beta=eps))
+    np.testing.assert_allclose(Wg, Wi, rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(og["div"], oi["div"], rtol=1e-4)
+    assert O.sparse_nmf_beta(V, dict(base))[2]["div"][0] == ok["div"][0]   # cf defaults to 'kl' (:100-102)
+
+
 def test_snmf_chunking_carries_dictionary():
     rng = np.random.default_rng(5)
     V = np.abs(rng.standard_normal((10, 50)))
