@@ -132,6 +132,13 @@ if which in ("dbg2",):
     for B, Tn in ((2048, 6), (512, 12)):
         sys.stderr.write("\n## B=%d (default plan)\n" % B); sys.stderr.flush()
         run(B, Tn, reps=1, DEBUG=1)
+if which in ("re1",):     # re-entry: the latency-regime alternatives once more (their earlier logs were lost with the container)
+    sweep(64, T, [dict(), dict(KS=4, NB=32, G=2, VERBOSE=1), dict(KS=4, NB=32, G=2, WST=2), dict(KS=4, NB=32, G=2, LL=0), dict(KS=4, NB=16, G=4)])
+    sweep(32, T, [dict(), dict(KS=4, NB=32, G=1), dict(KS=4, NB=16, G=2)])
+if which in ("re2",):
+    sweep(64, T, [dict(), dict(KS=8, NB=16, G=1), dict(KS=8, NB=16, G=1, HST=4, RST=2, WST=2), dict(KS=8, NB=16, G=1, HST=8, RST=4, WST=2),
+                  dict(KS=8, NB=16, G=1, HST=4, RST=4, WST=4), dict(KS=8, NB=16, G=1, NOSYM=1), dict(KS=8, NB=16, G=1, LLT=4)])
+    sweep(48, T, [dict(), dict(KS=8, NB=16, G=1)])
 if which in ("crash",):
     run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
 if which in ("trace2",):
