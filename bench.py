@@ -435,8 +435,11 @@ def main():
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained/2 (TF32 dense)" % pk["src"],
                 "algorithmic_flops_per_launch": fl_rec * B * T, "launch_ms": rec_ms,
                 "share_of_step": rec_ms / (ms_dev / args.steps) if ms_dev > 0 else None,
-                "stage_ms": {"mask_pad": float(stage_ms[0]), "projection_gemm": float(stage_ms[1]),
-                             "recurrence": rec_ms, "recon_mask_gemm": float(stage_ms[3])}}
+                "stage_ms": {"mask_pad": float(stage_ms[0]), "projection_gemm_before_recurrence": float(stage_ms[1]),
+                             "recurrence": rec_ms, "recon_mask_gemm": float(stage_ms[3])},
+                "stage_note": "pipelined projection: only the projection of the first T/6 frames precedes the persistent "
+                              "kernel; the rest of that GEMM runs on the SMs the recurrence leaves free and is inside "
+                              "the recurrence interval (DRNMF_FWD_OVERLAP=0 = serial order, same bits)"}
 
     config = {"workload": "configs[1]: DR-NMF forward via enhance.py path, %d layers, R=%d, %d bins, mask + iSTFT, "
                           "batch of %d synthetic 3 s utterances per GPU" % (K, R, F, B),

@@ -2,6 +2,7 @@
 #include "internal.h"
 #include "../../include/drnmf.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -32,6 +33,8 @@ FwdWorkspace carve_forward_ws(const drnmf_handle* h, int B, int T, void* base) {
   w.psum = (float*)take(2 * 256 * (size_t)Bp * 4);
   w.leak = (float*)take((size_t)Bp * 4);
   w.flags = (unsigned int*)take(16384 * 4);
+  w.xw_ready = (unsigned int*)take(256);
+  w.xw_tmajor = 0; w.xw_t0 = 0;
   w.actT_hi = nullptr; w.actT_lo = nullptr;
   w.bytes = off;
   return w;
@@ -56,11 +59,12 @@ static int run_gemm(const drnmf_handle* h, GemmEpi epi, const GemmArgs& a, cudaS
   return h->impl == DRNMF_IMPL_SIMT ? launch_gemm_simt(epi, a, st) : launch_gemm_tc(epi, a, st);
 }
 
-static int check_dev_error(drnmf_handle* h, cudaStream_t st, const char* what) {
+static int check_dev_error(drnmf_handle* h, cudaStream_t st, const char* what, int* first_code = nullptr) {
   int e4[4] = {0, 0, 0, 0};             // [0] first code, [1] mask of all recurrence codes (bit = code - 200), [2] detail
   DRNMF_CUDA(cudaMemcpyAsync(e4, h->dev_error, sizeof(e4), cudaMemcpyDeviceToHost, st));
   DRNMF_CUDA(cudaStreamSynchronize(st));
   const int v = e4[0];
+  if (first_code) *first_code = v;
   int g = gemm_device_error(st);
   if (v != 0 || g != 0) {
     // report once, then clear: a transient failure (e.g. a watchdog expiry under SM contention) must not latch
@@ -140,6 +144,7 @@ int drnmf_destroy(drnmf_handle* h) {
   for (float* p : ptrs) if (p) cudaFree(p);
   if (h->dev_error) cudaFree(h->dev_error);
   if (h->ev_ready) for (auto& e : h->ev) cudaEventDestroy(e);
+  if (h->hi_ready) { cudaStreamDestroy(h->hi); cudaEventDestroy(h->ev_ov[0]); cudaEventDestroy(h->ev_ov[1]); }
   if (h->side_ready) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_side[0]); cudaEventDestroy(h->ev_side[1]); }
   delete h;
   return DRNMF_OK;
@@ -205,28 +210,86 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
     h->ev_ready = true;
   }
   h->ev_valid = false;
-  DRNMF_CUDA(cudaEventRecord(h->ev[0], st));
-  if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st))) return rc;
-  DRNMF_CUDA(cudaEventRecord(h->ev[1], st));
-  {   // input projections for every layer: XW[bt][k*Rp + j] = x~[bt] . W_k[:, j] + b_k[j]
-    GemmArgs a{};
-    a.A_hi = w.xp_hi; a.A_lo = w.xp_lo; a.lda = h->Fp;
-    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = h->Fp;
-    a.M = BT; a.N = h->K * h->Rp; a.Kd = h->Fp;
-    a.C = w.XW; a.ldc = h->K * h->Rp; a.M_valid = BT; a.N_valid = a.N;
-    a.bias = h->bias;            // XW[bt][k*Rp + j] = x~ . W_k[:, j] + b_k[j]
-    if ((rc = run_gemm(h, EPI_STORE, a, st))) return rc;
-  }
-  DRNMF_CUDA(cudaEventRecord(h->ev[2], st));
+  bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
   {
-    bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
     const char* e = getenv("DRNMF_RECURRENT");      // debugging aid: mix tcgen05 GEMMs with the SIMT recurrence
     if (e && !strcmp(e, "simt")) rec_simt = true;
     if (e && !strcmp(e, "tc")) rec_simt = false;
-    rc = rec_simt ? launch_recurrent_simt(h, w, B, T, H, st) : launch_recurrent_tc(h, w, B, T, H, st);
   }
-  if (rc) return rc;
-  DRNMF_CUDA(cudaEventRecord(h->ev[3], st));
+  // Pipelined projection (latency regime): the recurrence walks the frames in order and occupies 64 of the 148 SMs at
+  // the bench batch, so only the projections of the first frames have to exist when it starts.  xp / XW are laid out
+  // time-major, the first T0 frames are projected up front, the persistent kernel starts on a high-priority stream and
+  // the rest of the projection GEMM runs next to it on the caller's stream - held back (cuStreamWaitValue32) until every
+  // CTA of the persistent kernel is resident: clusters placed around a running GEMM end up scattered over the chip and
+  // the whole chain runs 20-30 % slower (measured).  A device flag, set in stream order after that GEMM, is acquired by
+  // the kernel's owners before they touch frame T0.  Results are bitwise those of the serial order.
+  // Off (serial order) when: DRNMF_FWD_OVERLAP=0; the plan uses more than half of the SMs (the GEMM would crawl on the
+  // rest); kernels cannot run concurrently (CUDA_LAUNCH_BLOCKING, an injected profiler / sanitizer serialises launches);
+  // stream memory operations are unavailable; or a previous pipelined call on this handle timed out on the flag.
+  int T0 = T;
+  {
+    const char* e = getenv("DRNMF_FWD_OVERLAP");
+    const bool forced = e && !strcmp(e, "force");
+    bool want = !(e && !strcmp(e, "0")) && !rec_simt && T >= 16 && !h->no_overlap;
+    if (want && !forced) {
+      const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+      if ((lb && atoi(lb) != 0) || getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) want = false;
+    }
+    if (want) {
+      const bool env_plan = getenv("DRNMF_REC_KS") || getenv("DRNMF_REC_G") || getenv("DRNMF_REC_NB") || getenv("DRNMF_REC_NOSPLIT");
+      if (env_plan || h->plan_B != B) { h->plan_ctas = recurrent_plan_ctas(h, B); h->plan_B = B; }
+      if (2 * h->plan_ctas > h->num_sms) want = false;
+    }
+    if (want && stream_wait_geq(nullptr, nullptr, 0) != 0) want = false;      // probe only
+    if (want) { T0 = (T + 5) / 6; if (T0 < 4) T0 = 4; }
+  }
+  const bool overlap = T0 < T;
+  if (overlap && !h->hi_ready) {
+    int least = 0, greatest = 0;
+    DRNMF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    DRNMF_CUDA(cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, greatest));
+    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[0], cudaEventDisableTiming));
+    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[1], cudaEventDisableTiming));
+    h->hi_ready = true;
+  }
+  w.xw_tmajor = overlap ? 1 : 0; w.xw_t0 = overlap ? T0 : 0;
+  if (!overlap) w.xw_ready = nullptr;
+  DRNMF_CUDA(cudaEventRecord(h->ev[0], st));
+  if (overlap) DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 0, 8, st));
+  if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st, overlap ? B : 0))) return rc;
+  DRNMF_CUDA(cudaEventRecord(h->ev[1], st));
+  auto project = [&](size_t row0, size_t rows) {   // XW[row][k*Rp + j] = x~[row] . W_k[:, j] + b_k[j] for a block of rows
+    GemmArgs a{};
+    a.A_hi = w.xp_hi + row0 * h->Fp; a.A_lo = w.xp_lo + row0 * h->Fp; a.lda = h->Fp;
+    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = h->Fp;
+    a.M = (int)rows; a.N = h->K * h->Rp; a.Kd = h->Fp;
+    a.C = w.XW + row0 * (size_t)h->K * h->Rp; a.ldc = h->K * h->Rp; a.M_valid = (int)rows; a.N_valid = a.N;
+    a.bias = h->bias;
+    a.M_plan = BT;
+    return run_gemm(h, EPI_STORE, a, st);
+  };
+  if ((rc = project(0, (size_t)B * T0))) return rc;
+  cudaStream_t rst = st;                             // stream of the recurrence
+  if (overlap) {
+    DRNMF_CUDA(cudaEventRecord(h->ev_ov[0], st));
+    DRNMF_CUDA(cudaStreamWaitEvent(h->hi, h->ev_ov[0], 0));
+    rst = h->hi;
+  }
+  DRNMF_CUDA(cudaEventRecord(h->ev[2], rst));
+  rc = rec_simt ? launch_recurrent_simt(h, w, B, T, H, rst) : launch_recurrent_tc(h, w, B, T, H, rst);
+  if (rc) {
+    if (overlap) cudaStreamSynchronize(h->hi);
+    return rc;
+  }
+  DRNMF_CUDA(cudaEventRecord(h->ev[3], rst));
+  if (overlap) {
+    DRNMF_CUDA(cudaEventRecord(h->ev_ov[1], h->hi));
+    const unsigned int n_cta = (unsigned int)(h->rec_cfg[1] * h->rec_cfg[2] * h->rec_groups);
+    if (stream_wait_geq(st, w.xw_ready + 1, n_cta)) { set_error("cuStreamWaitValue32 failed"); cudaStreamSynchronize(h->hi); return DRNMF_ERR_CUDA; }
+    if ((rc = project((size_t)B * T0, (size_t)B * (T - T0)))) { cudaStreamSynchronize(h->hi); return rc; }
+    DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 1, 4, st));     // 0x01010101, ordered after the GEMM on the caller's stream
+    DRNMF_CUDA(cudaStreamWaitEvent(st, h->ev_ov[1], 0));
+  }
   if (irm) {   // recon + mask: irm = exp(log(eps + H_c E_c) - log(eps + H_c E_c + H_n E_n))
     GemmArgs a{};
     a.A_hi = w.Hp_hi; a.A_lo = w.Hp_lo; a.lda = h->Rp;
@@ -238,7 +301,17 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
   }
   DRNMF_CUDA(cudaEventRecord(h->ev[4], st));
   h->ev_valid = true;
-  if (h->impl != DRNMF_IMPL_SIMT) return check_dev_error(h, st, "drnmf_forward");
+  if (h->impl != DRNMF_IMPL_SIMT) {
+    int code = 0;
+    rc = check_dev_error(h, st, "drnmf_forward", &code);
+    if (rc == DRNMF_ERR_DEVICE && code == 215 && overlap) {
+      // the second projection chunk never ran next to the persistent kernel (launches are being serialised by a tool
+      // this library did not recognise): from now on this handle keeps the serial order; redo the call that way
+      h->no_overlap = true;
+      return drnmf_forward(h, x, B, T, mask_value, H, irm, ws, ws_bytes, stream);
+    }
+    return rc;
+  }
   return DRNMF_OK;
 }
 

@@ -32,6 +32,8 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 // 2-D fp32 row-major tensor map with a (box_cols x box_rows) box and 128B swizzle (box_cols*4 must be 128).
+// cuStreamWaitValue32(st, addr, value, GEQ): holds the stream until *addr >= value (nonzero return = unavailable)
+int stream_wait_geq(cudaStream_t st, const unsigned int* addr, unsigned int value);
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
                  uint32_t box_cols, uint32_t box_rows);
 

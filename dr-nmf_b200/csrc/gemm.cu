@@ -395,7 +395,8 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
   if (rc) return rc;
   // wide tiles when the grid still fills the device (and never for the dual-B epilogue)
   static const int force_bn = getenv("DRNMF_GEMM_BN") ? atoi(getenv("DRNMF_GEMM_BN")) : 0;
-  const long long ctas256 = (long long)((a.M + TC_BM - 1) / TC_BM) * ((a.N + 255) / 256) * (a.splits > 1 ? a.splits : 1);
+  const int m_plan = a.M_plan > 0 ? a.M_plan : a.M;        // a row block of a larger product keeps that product's tile shape
+  const long long ctas256 = (long long)((m_plan + TC_BM - 1) / TC_BM) * ((a.N + 255) / 256) * (a.splits > 1 ? a.splits : 1);
   const bool wide = force_bn ? force_bn == 256 : (a.N >= 256 && ctas256 >= 4 * 148);     // >= 4 waves: no tail effect (measured:
                                                                                            // split-K weight-gradient GEMMs of 256 CTAs lose)
   switch (epi) {

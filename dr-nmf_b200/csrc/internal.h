@@ -28,6 +28,12 @@ struct drnmf_handle {
   int* dev_error;          // device-side error word (watchdogs / protocol violations)
   cudaEvent_t ev[5];       // stage boundaries of the last drnmf_forward (mask | projection | recurrence | recon)
   bool ev_ready, ev_valid;
+  cudaStream_t hi;         // high-priority stream of the persistent recurrence when drnmf_forward pipelines the input
+                           // projection under it (the rest of the projection runs on the caller's stream meanwhile)
+  cudaEvent_t ev_ov[2];    // [0] first projection chunk done (caller stream), [1] recurrence done (hi stream)
+  bool hi_ready;
+  int plan_B, plan_ctas;   // cache: CTAs of the forward plan for batch plan_B (0 = empty)
+  bool no_overlap;         // a pipelined drnmf_forward timed out on the projection flag: keep the serial order
   cudaStream_t side;       // copy stream of drnmf_enhance_host (the complex STFT is only needed after the recurrence)
   cudaEvent_t ev_side[2];  // [0] main stream reached the call, [1] side copy done
   bool side_ready;
@@ -56,6 +62,11 @@ struct FwdWorkspace {
   float* leak;              // Bp          SIMT path: sum_j state[b][j]
   unsigned int* flags;      // device flags for the persistent kernel
   float *actT_hi, *actT_lo; // training only: K x Rp x (T*Bp) post-relu activations, time-major frames (t*Bp + b)
+  // pipelined forward (drnmf_forward): xp / XW rows are TIME-major (t*B + b) so that the projection of the first xw_t0
+  // frames is a contiguous row block; the rest is computed while the recurrence already runs and announced through
+  // *xw_ready (the owners of the persistent kernel acquire it before they touch frame xw_t0).  0 / null = b-major, no wait.
+  int xw_tmajor, xw_t0;
+  unsigned int* xw_ready;   // [0] projections of the second chunk are complete, [1] resident CTAs of the persistent kernel
   size_t bytes;
   int Bp;
 };
@@ -65,7 +76,9 @@ FwdWorkspace carve_forward_ws(const drnmf_handle* h, int B, int T, void* base);
 int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const float* log_alph, int n_log_alph,
                        int alph_dim, const float* log_lam1, int n_log_lam1, const float* log_h0, const float* k_clean,
                        const float* k_noise, cudaStream_t st);
-int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st);
+// B_tmajor > 0: write xp rows time-major (row t*B + b for input row b*T + t, T = BT / B); mvalid stays b-major
+int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st,
+                    int B_tmajor = 0);
 
 // ---- gemm: C = A (M x K, K-major) . B^T (N x K, K-major) with a fused epilogue --------------------
 enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2, EPI_LAMBDA = 3, EPI_LAMBDA_B = 4 };
@@ -92,6 +105,9 @@ struct GemmArgs {
   // to Q/Q_lo/QT/QT_lo (the operand that takes V's place), and sums the beta-divergence into div_partials.
   float beta;
   float *Q, *Q_lo, *QT, *QT_lo;
+  // tile-shape decision: when this launch is a row block of a larger product (pipelined projection), M_plan = that
+  // product's row count, so that every block accumulates in the same order as the single launch would (bitwise equal)
+  int M_plan;
 };
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
@@ -99,6 +115,7 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 // ---- recurrent.cu ----------------------------------------------------------------------------------
 int launch_recurrent_simt(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
+int recurrent_plan_ctas(const drnmf_handle* h, int B);   // CTAs of the forward plan for batch B (INT_MAX-like large value when none)
 int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,
                             float* deltaT_lo, float* G, float* psum2, cudaStream_t st);
 

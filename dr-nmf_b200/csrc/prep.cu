@@ -144,9 +144,11 @@ int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const f
 // Keras Masking(mask_value) (enhance.py:253): m = any_f(x != mask_value), x~ = x * m.  One warp per frame row;
 // writes the zero-padded row (Fp wide) and its tf32 remainder.
 __global__ void k_mask_pad(const float* __restrict__ x, int BT, int F, int Fp, float mask_value,
-                           float* __restrict__ xp_hi, float* __restrict__ xp_lo, float* __restrict__ mvalid) {
+                           float* __restrict__ xp_hi, float* __restrict__ xp_lo, float* __restrict__ mvalid, int B_tm) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= BT) return;
+  size_t orow = row;                                   // output row: b-major like the input, or time-major (t*B + b)
+  if (B_tm > 0) { const int T = BT / B_tm, b = row / T, t = row - b * T; orow = (size_t)t * B_tm + b; }
   const int lane = threadIdx.x & 31;
   const float* src = x + (size_t)row * F;
   bool any = false;
@@ -154,14 +156,15 @@ __global__ void k_mask_pad(const float* __restrict__ x, int BT, int F, int Fp, f
   any = __any_sync(0xffffffffu, any);
   for (int f = lane; f < Fp; f += 32) {
     float v = (f < F && any) ? src[f] : 0.f;
-    xp_hi[(size_t)row * Fp + f] = v;
-    xp_lo[(size_t)row * Fp + f] = tf32_lo(v);
+    xp_hi[orow * Fp + f] = v;
+    xp_lo[orow * Fp + f] = tf32_lo(v);
   }
   if (lane == 0) mvalid[row] = any ? 1.f : 0.f;
 }
 
-int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st) {
-  k_mask_pad<<<(BT + 7) / 8, 256, 0, st>>>(x, BT, h->F, h->Fp, mask_value, w.xp_hi, w.xp_lo, w.mvalid);
+int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st,
+                    int B_tmajor) {
+  k_mask_pad<<<(BT + 7) / 8, 256, 0, st>>>(x, BT, h->F, h->Fp, mask_value, w.xp_hi, w.xp_lo, w.mvalid, B_tmajor);
   count_launch();
   DRNMF_CUDA(cudaGetLastError());
   return DRNMF_OK;

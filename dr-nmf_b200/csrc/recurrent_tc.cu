@@ -73,6 +73,9 @@ struct RecArgs {
   const float* alph_vec;                     // K x Rp step sizes for vector alph (untie_alph) in the backward chain, else null
   float d0mo_b, o0_b, ok_b;
   unsigned int* flags;
+  // pipelined forward: XW rows are time-major (t*Btot + b) and the frames >= xw_t0 are only valid once *xw_ready != 0
+  const unsigned int* xw_ready; int xw_tmajor, xw_t0, Btot;
+  unsigned int* started;                     // optional: every CTA counts itself in once it is resident (after the cluster sync)
   int* dev_error;
   int dbg_m;                                 // M-tile of the observed CTA (K-split 0)
   long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
@@ -126,13 +129,13 @@ __device__ __forceinline__ bool owners_all(bool pred) {
   return r != 0;
 }
 
-__device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int target, volatile int* err) {
+__device__ __forceinline__ bool poll_flag(const unsigned int* f, unsigned int target, volatile int* err, long long budget = RT_WATCHDOG) {
   if (flag_ld_acquire(f) >= target) return true;
   long long t0 = clock64();
   unsigned it = 0;
   while (flag_ld_acquire(f) < target) {
     if ((++it & 0xFF) == 0) {
-      if (clock64() - t0 > RT_WATCHDOG) return false;
+      if (clock64() - t0 > budget) return false;
       if (*err) return false;
     }
   }
@@ -357,6 +360,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
   // contiguous range of batch tiles (disjoint SMs, own flags, no interaction).  Everything indexed by the utterance is
   // re-based once here; below, tile i / utterance b are group-local.
   RecArgs a = a_in;
+  // pipelined forward: a CTA that executes is resident - the host holds the rest of the projection GEMM back until all
+  // CTAs have counted themselves in (before any early return: the stream waits for the full count)
+  if (a_in.started && threadIdx.x == 0) atomicAdd(a_in.started, 1u);
   // (the last group may hold fewer tiles: its schedule classes differ)
   SchedTab sch = (gridDim.z > 1 && blockIdx.z == gridDim.z - 1) ? sch_in.e_last : sch_in.e;
   const int tile0 = blockIdx.z * a_in.n_tiles;
@@ -368,7 +374,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     a.mvalid += bo * a.T; a.flags += (size_t)tile0 * a.MT;
     a.hb_hi += bo * a.Rp; a.hb_lo += bo * a.Rp;
     if (!BWD) {
-      a.XW += bo * a.T * a.K * a.Rp; a.state += bo * a.Rp; a.psum += bo;
+      a.XW += (a.xw_tmajor ? bo : bo * a.T) * a.K * a.Rp; a.state += bo * a.Rp; a.psum += bo;
       a.Hp_hi += bo * a.T * a.Rp; a.Hp_lo += bo * a.T * a.Rp;
       if (a.H_user) a.H_user += bo * a.T * a.R;
     } else {
@@ -732,7 +738,8 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 #pragma unroll
         for (int bi = 0; bi < CB; ++bi) {
           int b = i * NB + CB * my_cq + bi; b = b < a.B ? b : a.B - 1;
-          xa[bi] = ldg_hint4(a.XW + ((size_t)b * T + tc) * KRp + (size_t)k * Rp + rowq, pol_x);
+          const size_t xrow = a.xw_tmajor ? (size_t)tc * a.Btot + b : (size_t)b * T + tc;
+          xa[bi] = ldg_hint4(a.XW + xrow * KRp + (size_t)k * Rp + rowq, pol_x);
         }
       }
     };
@@ -761,6 +768,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
       {
         int i2 = i + 1, k2 = k, t2 = t;
         if (i2 == n_tiles) { i2 = 0; if (++k2 == K) { k2 = 0; ++t2; } }
+        // pipelined forward: the projections of the frames >= xw_t0 are still being computed on other SMs when this
+        // kernel starts; they are acquired once, before the first load that touches them
+        if (a.xw_ready && t2 == a.xw_t0 && k2 == 0 && i2 == 0 && !poll_flag(a.xw_ready, 1u, err, 400000000LL)) rt_fail(a.dev_error, 215);
         fetch_xw(t2, k2, i2, xa_next);
       }
       // Loads that do not depend on this item's product are issued BEFORE the wait and consumed after it:
@@ -1637,6 +1647,7 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   record_cfg(p, h->bwd_cfg, &h->bwd_groups);
   RecArgs& a = p.a;
   a.XW = nullptr; a.mvalid = w.mvalid; a.h0 = h->h0;
+  a.xw_tmajor = 0; a.xw_t0 = 0; a.xw_ready = nullptr; a.Btot = B; a.started = nullptr;
   a.state = nullptr; a.psum = nullptr; a.Hp_hi = nullptr; a.Hp_lo = nullptr; a.H_user = nullptr;
   a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
   a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo;
@@ -1659,6 +1670,11 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   return launch_rec(p, true, tH_hi, tH_lo, tW, tW64, st);
 }
 
+int recurrent_plan_ctas(const drnmf_handle* h, int B) {
+  const RecPlan p = choose_plan(h, B, false);
+  return p.ok ? p.KS * p.MT * p.G : (1 << 30);
+}
+
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
   const int K = h->K, Rp = h->Rp;
   RecPlan p = choose_plan(h, B, false);
@@ -1673,6 +1689,8 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   record_cfg(p, h->rec_cfg, &h->rec_groups);
   RecArgs& a = p.a;
   a.XW = w.XW; a.mvalid = w.mvalid; a.h0 = h->h0;
+  a.xw_tmajor = w.xw_tmajor; a.xw_t0 = w.xw_t0; a.xw_ready = w.xw_tmajor ? w.xw_ready : nullptr; a.Btot = B;
+  a.started = w.xw_tmajor ? w.xw_ready + 1 : nullptr;
   a.state = w.state; a.psum = w.psum; a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;
   a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
   a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo;

@@ -33,6 +33,21 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+int stream_wait_geq(cudaStream_t st, const unsigned int* addr, unsigned int value) {
+  static PFN_cuStreamWaitValue32_v11070 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuStreamWaitValue32_v11070>(p);
+  }
+  if (!fn) return 1;
+  if (!addr) return 0;                                   // availability probe
+  return fn(st, (CUdeviceptr)(uintptr_t)addr, value, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS ? 0 : 1;
+}
+
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
                  uint32_t box_cols, uint32_t box_rows) {
   auto enc = get_encode();

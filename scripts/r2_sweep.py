@@ -139,6 +139,15 @@ if which in ("re2",):
     sweep(64, T, [dict(), dict(KS=8, NB=16, G=1), dict(KS=8, NB=16, G=1, HST=4, RST=2, WST=2), dict(KS=8, NB=16, G=1, HST=8, RST=4, WST=2),
                   dict(KS=8, NB=16, G=1, HST=4, RST=4, WST=4), dict(KS=8, NB=16, G=1, NOSYM=1), dict(KS=8, NB=16, G=1, LLT=4)])
     sweep(48, T, [dict(), dict(KS=8, NB=16, G=1)])
+if which in ("re3",):     # event traces of two consecutive steps (4 items) at B = 64: flags vs self-validating exchange with two tiles
+    for kw in (dict(), dict(LLT=2), dict(PUB="thread")):
+        sys.stderr.write("\n## B=64 %s\n" % kw); sys.stderr.flush()
+        run(64, 40, reps=1, DEBUG=1, TRACE="400:404", **kw)
+    sys.stderr.write("\n## B=32\n"); sys.stderr.flush()
+    run(32, 40, reps=1, DEBUG=1, TRACE="200:202")
+if which in ("re4",):
+    sys.stderr.write("\n## B=64\n"); sys.stderr.flush()
+    run(64, 40, reps=1, DEBUG=1, TRACE="400:402")
 if which in ("crash",):
     run(int(os.environ.get("CRASH_B", "32")), int(os.environ.get("CRASH_T", "193")), reps=2)
 if which in ("trace2",):

@@ -10,6 +10,7 @@ oracle / torch.autograd on the float64 oracle -- no transitive argument through 
 Tolerances: north_star (1e-4 on H and the mask, Frobenius and max-abs/max); gradients 2e-4.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -245,6 +246,43 @@ def test_snmf_beta2_entry_equals_ed_entry():
         outs.append((Wd.cpu().numpy(), Hd.cpu().numpy(), cost))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_pipelined_projection_is_bitwise_the_serial_order(monkeypatch):
+    """drnmf_forward projects the first frames, starts the persistent recurrence and computes the remaining projections
+    next to it (time-major XW, device flag acquired before the first late frame).  Same bits as the serial order, ragged
+    batch with a leading-masked and a fully masked utterance, one- and two-tile latency plans."""
+    F, R, K = 129, 256, 6
+    p = synth.model_params(F, R, K, alph=60.0)
+    eng = engine.DrnmfEngine(F, R, K)
+    eng.set_params(p)
+    for B, T in ((40, 50), (7, 33)):
+        x, _ = _synthetic_batch(B, T, F, seed=B)
+        x[2, 0] = -1.0
+        x[3] = -1.0
+        xd = torch.as_tensor(x, device="cuda")
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("DRNMF_FWD_OVERLAP", mode)
+            H, irm = eng.forward(xd)
+            torch.cuda.synchronize()
+            out[mode] = (H.clone(), irm.clone(), eng.stage_times()[1])
+        assert torch.equal(out["0"][0], out["1"][0]) and torch.equal(out["0"][1], out["1"][1])
+        Ho, irmo = O.drnmf_forward(x, p, dtype=np.float64)
+        assert max(rel_err(out["1"][0].cpu().numpy(), Ho)) < TOL and max(rel_err(out["1"][1].cpu().numpy(), irmo)) < TOL
+
+
+def test_pipelined_projection_falls_back_when_launches_are_serialised():
+    """With CUDA_LAUNCH_BLOCKING=1 the second projection chunk cannot run next to the persistent kernel.  The library
+    keeps the serial order then; when the pipelined order is forced anyway, the kernel's bounded wait on the projection
+    flag expires, the call is redone serially and the handle stays serial (scripts/fwd_overlap_time.py blocking)."""
+    import subprocess
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "fwd_overlap_time.py")
+    for extra in ({"DRNMF_FWD_OVERLAP": "force"}, {}):
+        env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", **extra)
+        r = subprocess.run([sys.executable, script, "blocking"], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "equal to the serial result: True" in r.stdout
 
 
 def test_device_error_is_not_sticky():
