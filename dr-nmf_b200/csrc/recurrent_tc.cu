@@ -1520,7 +1520,10 @@ static void rec_launch_config(const RecPlan& p, cudaLaunchConfig_t& cfg, cudaLau
   // The CTAs spin on flags written by other clusters, so the whole grid must be co-resident.  A cooperative launch
   // makes the driver check that at launch time (SMs taken by another stream / process / NCCL kernel -> the launch
   // fails cleanly with cudaErrorCooperativeLaunchTooLarge instead of running into the device-side watchdog).
-  static const bool coop = !(getenv("DRNMF_REC_COOP") && !strcmp(getenv("DRNMF_REC_COOP"), "0"));
+  // (Nsight Compute cannot replay cooperative launches of this kernel - the driver reports LaunchFailed -, so the
+  //  attribute is dropped when its injection environment is present; DRNMF_REC_COOP=0/1 overrides either way.)
+  static const bool coop = getenv("DRNMF_REC_COOP") ? strcmp(getenv("DRNMF_REC_COOP"), "0") != 0
+                                                    : getenv("NV_NSIGHT_INJECTION_PORT_BASE") == nullptr;
   if (coop) {
     attr[1].id = cudaLaunchAttributeCooperative;
     attr[1].val.cooperative = 1;
