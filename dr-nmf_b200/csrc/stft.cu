@@ -278,9 +278,19 @@ __global__ void k_stft_mag_tiled(const float* __restrict__ audio, const int64_t*
   const float* src = audio + offs[u];
   for (int k = threadIdx.x; k < N / 2; k += blockDim.x) tw[k] = twg[k];
   for (int n = threadIdx.x; n < N; n += blockDim.x) win[n] = wing[n];
-  for (int n = threadIdx.x; n < seg_n; n += blockDim.x) {
-    const int sidx = j0 * hop + n - N;                    // N zeros in front (util.py:189-190)
-    seg[n] = (sidx >= 0 && sidx < len) ? src[sidx] : 0.f;
+  for (int n0 = threadIdx.x; n0 < seg_n; n0 += 8 * blockDim.x) {   // 8 loads in flight per thread (latency-bound otherwise)
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int n = n0 + k * blockDim.x;
+      const int sidx = j0 * hop + n - N;                  // N zeros in front (util.py:189-190)
+      v[k] = (n < seg_n && sidx >= 0 && sidx < len) ? __ldg(src + sidx) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int n = n0 + k * blockDim.x;
+      if (n < seg_n) seg[n] = v[k];
+    }
   }
   __syncthreads();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,6 +421,125 @@ __global__ void k_istft_ola_tiled(const float* __restrict__ stack, const float* 
   }
 }
 
+// The same synthesis without the [Re;Im] staging tile (N = 512 / 1024, natural-order four-step FFT): the raw spectra of
+// a frame pair are parked IN the pair's FFT buffer - frame a's (re, im) of bin f at d[f], frame b's at d[N-f], the
+// purely real edge bins of both frames share d[0] and d[N/2] - by a pass that reads the stack in runs of consecutive
+// frames; the pair's warp then applies the masks (read along f) and folds the four values of (f, N-f) into
+// Z = Xext_a + i Xext_b in place.  Half the shared memory of k_istft_ola_tiled and 8 warps per CTA: two CTAs per SM.
+template <int N2>
+__global__ void __launch_bounds__(256, 2)
+k_istft_ola_inplace(const float* __restrict__ stack, const float* __restrict__ mask, const int64_t* __restrict__ fidx,
+                    const int64_t* __restrict__ out_offs, int hop, int FT, int halo, int64_t total_frames,
+                    const float* __restrict__ wing, const float2* __restrict__ twg, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  constexpr int N = 32 * N2, F = N / 2 + 1, WB = 33 * N2 + 1;
+  constexpr int pairs = 8, nfr = 16;
+  float2* tw = reinterpret_cast<float2*>(smraw);
+  float* win = reinterpret_cast<float*>(tw + N / 2);
+  float2* buf = reinterpret_cast<float2*>(win + N);
+  const int u = blockIdx.y, j0 = blockIdx.x * FT;
+  const int Tu = (int)(fidx[2 * u + 1] - fidx[2 * u]);
+  const int out_len = hop * (Tu - 1) - N;
+  if (out_len <= 0 || j0 * hop >= hop * (Tu - 1)) return;   // no output sample in this tile
+  const int i0 = j0 - halo;                                  // first frame of the window (may be negative)
+  const int64_t gbase = fidx[2 * u];
+  for (int k = threadIdx.x; k < N / 2; k += blockDim.x) tw[k] = twg[k];
+  for (int n = threadIdx.x; n < N; n += blockDim.x) win[n] = wing[n];
+  {
+    // runs of nfr = 16 consecutive frames per bin: thread t serves frame (t & 15) of the bins (t >> 4) + 16 k.  The loads
+    // of UNR bins are issued before any of them is stored (the loop is latency-bound: one round trip per batch, not per bin)
+    constexpr int UNR = 8;
+    const int j = threadIdx.x & (nfr - 1), i = i0 + j;
+    const bool v = i >= 0 && i < Tu;
+    float2* d = buf + (size_t)(j >> 1) * WB;
+    const float* sre = stack + gbase + (v ? i : 0);
+    const float* sim = sre + (size_t)F * total_frames;
+    for (int f0 = threadIdx.x >> 4; f0 < F; f0 += 16 * UNR) {
+      float re[UNR], im[UNR];
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {
+        const int f = f0 + 16 * k;
+        const bool ok = v && f < F;
+        re[k] = ok ? __ldg(sre + (size_t)f * total_frames) : 0.f;
+        im[k] = (ok && f != 0 && f != N / 2) ? __ldg(sim + (size_t)f * total_frames) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {
+        const int f = f0 + 16 * k;
+        if (f >= F) break;
+        if (f == 0 || f == N / 2) {                             // real bins (their imaginary parts never reach the output)
+          float* dd = reinterpret_cast<float*>(d + f);
+          dd[j & 1] = re[k];
+        } else {
+          d[(j & 1) ? N - f : f] = make_float2(re[k], im[k]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int ia = i0 + 2 * w, ib = ia + 1;
+    const bool va = ia >= 0 && ia < Tu, vb = ib >= 0 && ib < Tu;
+    float2* d = buf + (size_t)w * WB;
+    if (va || vb) {
+      // masks of both frames, read along f: all loads of a batch of MU bins in flight before the first use
+      constexpr int MU = 6;
+      const float* mpa = (va && mask) ? mask + (size_t)(gbase + ia) * F : nullptr;
+      const float* mpb = (vb && mask) ? mask + (size_t)(gbase + ib) * F : nullptr;
+      for (int fb = lane; fb <= N / 2; fb += 32 * MU) {
+        float mav[MU], mbv[MU];
+#pragma unroll
+        for (int k = 0; k < MU; ++k) {
+          const int f = fb + 32 * k;
+          mav[k] = (mpa && f <= N / 2) ? __ldg(mpa + f) : 1.f;
+          mbv[k] = (mpb && f <= N / 2) ? __ldg(mpb + f) : 1.f;
+        }
+#pragma unroll
+        for (int k = 0; k < MU; ++k) {
+        const int f = fb + 32 * k;
+        if (f > N / 2) break;
+        const float ma = mav[k], mb = mbv[k];
+        if (f == 0 || f == N / 2) {
+          const float2 r = d[f];
+          d[f] = make_float2(r.x * ma, r.y * mb);             // Z = are + i bre
+        } else {
+          const float2 ra = d[f], rb = d[N - f];
+          const float are = ra.x * ma, aim = ra.y * ma, bre = rb.x * mb, bim = rb.y * mb;
+          // Z = Xext_a + i Xext_b with the Hermitian extension Xext[N-f] = (re, -im)
+          d[f] = make_float2(are - bim, aim + bre);
+          d[N - f] = make_float2(are + bim, -aim + bre);
+        }
+        }
+      }
+      float2 w32[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w32[j] = tw[j * N2];
+      __syncwarp();
+      fft_fourstep<N2>(d, tw, w32, lane);
+    }
+  }
+  __syncthreads();
+  // overlap-add as a gather over the window's frames (ascending), window * 2/(N/hop) / N applied on the fly
+  const float scale = (2.0f / (float)(N / hop)) / (float)N;      // util.py:143 window scaling, 1/N of the ifft
+  float* dst = out + out_offs[u];
+  for (int q = threadIdx.x; q < FT * hop; q += blockDim.x) {
+    const int p = j0 * hop + q;                                  // position in the untrimmed signal
+    const int sidx = p - N;
+    if (sidx < 0 || sidx >= out_len) continue;
+    int i_hi = p / hop; if (i_hi > Tu - 1) i_hi = Tu - 1;
+    int i_lo = (p - N + hop) / hop; if (i_lo < 0) i_lo = 0;      // smallest i with p - i*hop < N
+    float acc = 0.f;
+    for (int i = i_lo; i <= i_hi; ++i) {
+      const int j = i - i0, n = p - i * hop;
+      const float2 y = buf[(size_t)(j >> 1) * WB + n];
+      acc += ((j & 1) ? y.y : y.x) * win[n] * scale;
+    }
+    dst[sidx] = acc;
+  }
+  (void)pairs;
+}
+
 static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 
 int launch_stft_mag(const float* audio, const int64_t* offs, const int32_t* lens, const int64_t* fidx, int n_utt,
@@ -448,7 +577,16 @@ int launch_mask_istft(const float* stack, const float* mask, const int64_t* fidx
   int rc = get_tables(N, st, &t);
   if (rc) return rc;
   const StftTile tl = stft_tile(N, hop);
-  if (tl.ok && !getenv("DRNMF_STFT_SIMPLE")) {
+  if (tl.ok && tl.N2 && tl.halo <= 8 && !getenv("DRNMF_STFT_SIMPLE") && !getenv("DRNMF_ISTFT_STAGED")) {
+    // in-place variant: 8 frame pairs per CTA = FT output hops + halo frames
+    const int FT = 16 - tl.halo;
+    const size_t smem = 16 + sizeof(float2) * (N / 2) + sizeof(float) * N + sizeof(float2) * (size_t)8 * tl.WB;
+    auto kern = tl.N2 == 32 ? k_istft_ola_inplace<32> : k_istft_ola_inplace<16>;
+    DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((max_frames + FT - 1) / FT, n_utt), 256, smem, st>>>(stack, mask, fidx, out_offs, hop, FT, tl.halo, total_frames,
+                                                                    t.win, t.tw, out_audio);
+    count_launch();
+  } else if (tl.ok && !getenv("DRNMF_STFT_SIMPLE")) {
     auto kern = tl.N2 == 32 ? k_istft_ola_tiled<32> : (tl.N2 == 16 ? k_istft_ola_tiled<16> : k_istft_ola_tiled<0>);
     DRNMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_s));
     kern<<<dim3((max_frames + tl.FT - 1) / tl.FT, n_utt), 32 * tl.pairs_s, tl.smem_s, st>>>(

@@ -295,6 +295,9 @@ class EnhancePlan:
 
 
 # ---- STFT / iSTFT ------------------------------------------------------------------------------
+_STFT_TABLES = {}
+
+
 def stft_frames(nsampl, N, hop):
     return _lib.load().drnmf_stft_frames(int(nsampl), int(N), int(hop))
 
@@ -306,13 +309,22 @@ def stft_mag(audio, offs, lens, N, hop, want_stack=True, want_mag=True):
     lib = _lib.load()
     dev = audio.device
     n_utt = len(lens)
-    frames = [lib.drnmf_stft_frames(int(n), N, hop) for n in lens]
-    starts = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
-    total = int(starts[-1])
-    fidx = torch.as_tensor(np.stack([starts[:-1], starts[1:]], axis=1).copy(), device=dev)
+    # the per-utterance index tables only depend on the layout of the batch: built (and uploaded) once per layout
+    key = (str(dev), int(N), int(hop), tuple(int(n) for n in lens), tuple(int(o) for o in offs))
+    hit = _STFT_TABLES.get(key)
+    if hit is None:
+        frames = [lib.drnmf_stft_frames(int(n), N, hop) for n in lens]
+        starts = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+        hit = (int(starts[-1]), max(frames) if frames else 0,
+               torch.as_tensor(np.stack([starts[:-1], starts[1:]], axis=1).copy(), device=dev),
+               torch.as_tensor(np.asarray(offs, dtype=np.int64), device=dev),
+               torch.as_tensor(np.asarray(lens, dtype=np.int32), device=dev))
+        if len(_STFT_TABLES) >= 16:
+            _STFT_TABLES.clear()
+        _STFT_TABLES[key] = hit
+    total, max_fr, fidx, offs_t, lens_t = hit
+    frames = [max_fr]
     F = N // 2 + 1
-    offs_t = torch.as_tensor(np.asarray(offs, dtype=np.int64), device=dev)
-    lens_t = torch.as_tensor(np.asarray(lens, dtype=np.int32), device=dev)
     stack = torch.empty((2 * F, total), dtype=torch.float32, device=dev) if want_stack else None
     mag = torch.empty((total, F), dtype=torch.float32, device=dev) if want_mag else None
     _lib.check(lib.drnmf_stft_mag(_ptr(audio), _ptr(offs_t), _ptr(lens_t), _ptr(fidx), n_utt, max(frames) if frames else 0,
