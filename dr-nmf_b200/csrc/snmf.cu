@@ -312,14 +312,17 @@ int snmf_mu_ed(int F, int n, int R, float beta, const float* V, float* W, float*
   count_launch(4);
   DRNMF_CUDA(cudaGetLastError());
 
-  auto lambda_gemm = [&]() {       // L = max(H^T-rows . W-rows, flr): (n x R).(F x R)^T, all layouts + squared error
+  // L = max(W-rows . H^T-rows, flr): (F x R).(n x R)^T, all layouts + divergence.  The bins are the M dimension: F = 513
+  // costs 5 tiles of 128 rows (640) - as the N dimension of 256-column tiles it cost 3 tiles (768), a third of them for
+  // the one Nyquist bin (2.35 -> 2.0 ms per launch at 513 x 225,000).
+  auto lambda_gemm = [&]() {
     GemmArgs a{};
-    a.A_hi = w.Ht_hi; a.A_lo = w.Ht_lo; a.lda = Rk;
-    a.B_hi = w.Wm_hi; a.B_lo = w.Wm_lo; a.ldb = Rk;
-    a.M = n; a.N = F; a.Kd = Rk; a.M_valid = n; a.N_valid = F;
-    a.C = w.Lt_hi; a.C_lo = w.Lt_lo; a.ldc = Fk; a.CT = w.Lm_hi; a.CT_lo = w.Lm_lo; a.ldct = nk;
-    a.Vref = w.Vt_hi; a.ldv = Fk; a.div_partials = w.div_part; a.flr = flr;
-    a.beta = beta; a.Q = w.Qt_hi; a.Q_lo = w.Qt_lo; a.QT = w.Qm_hi; a.QT_lo = w.Qm_lo;
+    a.A_hi = w.Wm_hi; a.A_lo = w.Wm_lo; a.lda = Rk;
+    a.B_hi = w.Ht_hi; a.B_lo = w.Ht_lo; a.ldb = Rk;
+    a.M = F; a.N = n; a.Kd = Rk; a.M_valid = F; a.N_valid = n;
+    a.C = w.Lm_hi; a.C_lo = w.Lm_lo; a.ldc = nk; a.CT = w.Lt_hi; a.CT_lo = w.Lt_lo; a.ldct = Fk;
+    a.Vref = w.Vm_hi; a.ldv = nk; a.div_partials = w.div_part; a.flr = flr;
+    a.beta = beta; a.Q = w.Qm_hi; a.Q_lo = w.Qm_lo; a.QT = w.Qt_hi; a.QT_lo = w.Qt_lo;
     return run_gemm_impl(simt, ed ? EPI_LAMBDA : EPI_LAMBDA_B, a, st);
   };
   auto proj_gemm = [&](const float* A_hi, const float* A_lo, float* out) {   // (n x F).(R x F)^T -> n x Rk
