@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
   const int kchunk = ((a.Kd + nsplit - 1) / nsplit + SIMT_BK - 1) / SIMT_BK * SIMT_BK;
   const int kbeg = blockIdx.z * kchunk;
   int klen = a.Kd - kbeg; if (klen > kchunk) klen = kchunk; if (klen < 0) klen = 0;
-  simt_tile_mainloop<EPI == EPI_RECON>(a.A_hi + kbeg, a.lda, a.M, a.B_hi + kbeg, EPI == EPI_RECON ? a.B2_hi + kbeg : nullptr,
+  constexpr bool DUAL = (EPI == EPI_RECON || EPI == EPI_MU_H);
+  simt_tile_mainloop<DUAL>(a.A_hi + kbeg, a.lda, a.M, a.B_hi + kbeg, DUAL ? a.B2_hi + kbeg : nullptr,
                                        a.ldb, a.N, klen, m0, n0, acc, acc2);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   float* Cz = a.C + (size_t)blockIdx.z * a.split_stride;
@@ -44,6 +45,12 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
       } else if (EPI == EPI_RECON) {
         a.C[(size_t)m * a.ldc + n] = epi_irm_value(acc[i][j], acc2[i][j], a.square);
         if (a.C_S) { a.C_S[(size_t)m * a.ldc + n] = acc[i][j]; a.C_N[(size_t)m * a.ldc + n] = acc2[i][j]; }
+      } else if (EPI == EPI_MU_H) {
+        float hv = a.C[(size_t)m * a.ldc + n];
+        if (!a.row_update || a.row_update[m]) hv = hv * acc2[i][j] / fmaxf(acc[i][j] + a.mu, a.flr);
+        a.C[(size_t)m * a.ldc + n] = hv; a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(hv);
+        a.CT[(size_t)n * a.ldct + m] = hv; a.CT_lo[(size_t)n * a.ldct + m] = tf32_lo(hv);
+        dsum += hv;
       } else if (EPI == EPI_LAMBDA) {
         const float v = fmaxf(acc[i][j], a.flr);
         a.C[(size_t)m * a.ldc + n] = v; a.C_lo[(size_t)m * a.ldc + n] = tf32_lo(v);
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
       }
     }
   }
-  if (EPI == EPI_LAMBDA || EPI == EPI_LAMBDA_B) {
+  if (EPI == EPI_LAMBDA || EPI == EPI_LAMBDA_B || EPI == EPI_MU_H) {
     __shared__ float red[SIMT_THREADS / 32];
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dsum;
@@ -82,6 +89,7 @@ int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
     case EPI_RECON: k_gemm_simt<EPI_RECON><<<grid, SIMT_THREADS, 0, st>>>(a); break;
     case EPI_LAMBDA: k_gemm_simt<EPI_LAMBDA><<<grid, SIMT_THREADS, 0, st>>>(a); break;
     case EPI_LAMBDA_B: k_gemm_simt<EPI_LAMBDA_B><<<grid, SIMT_THREADS, 0, st>>>(a); break;
+    case EPI_MU_H: k_gemm_simt<EPI_MU_H><<<grid, SIMT_THREADS, 0, st>>>(a); break;
   }
   count_launch();
   DRNMF_CUDA(cudaGetLastError());
@@ -99,7 +107,7 @@ constexpr int TC_THREADS = 192;                              // warp 0 TMA, warp
 // (128 + N) * 32 bytes per N/2 cycles: 128 B/clk at N = 128 (the whole shared-memory port, while TMA refills the ring),
 // 96 B/clk at N = 256 - the wide tile is used whenever the grid still fills the device.
 template <int EPI, int BN> struct TcCfg {
-  static constexpr bool DUAL = (EPI == EPI_RECON);
+  static constexpr bool DUAL = (EPI == EPI_RECON || EPI == EPI_MU_H);
   static_assert(!(DUAL && BN != 128), "the dual-B epilogue needs both accumulators: 128 columns each");
   static constexpr int B_TILE_BYTES = BN * TC_BK * 4;
   static constexpr int STAGES = (DUAL || BN == 256) ? 2 : 3;
@@ -273,6 +281,34 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                 d2[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
               }
             }
+          } else if (EPI == EPI_MU_H) {
+            // fused multiplicative update of H (rows = atoms m, columns = frames): 64 contiguous bytes of H per thread,
+            // transposed copy with lanes = consecutive atoms
+            if (n < a.N_valid) {
+              float hi[16], lo[16];
+              const float4* hp = reinterpret_cast<const float4*>(a.C + (size_t)m * a.ldc + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { const float4 t4 = hp[i]; hi[4 * i] = t4.x; hi[4 * i + 1] = t4.y; hi[4 * i + 2] = t4.z; hi[4 * i + 3] = t4.w; }
+              const bool upd = !a.row_update || a.row_update[m];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool in = (n + i < a.N_valid);
+                if (in && upd) hi[i] = hi[i] * v2[i] / fmaxf(v[i] + a.mu, a.flr);
+                if (!in) hi[i] = 0.f;
+                lo[i] = tf32_lo(hi[i]);
+                dsum += hi[i];
+              }
+              float4* d1 = reinterpret_cast<float4*>(a.C + (size_t)m * a.ldc + n);
+              float4* d2 = reinterpret_cast<float4*>(a.C_lo + (size_t)m * a.ldc + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                d1[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                d2[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n + i < a.N_valid) { a.CT[(size_t)(n + i) * a.ldct + m] = hi[i]; a.CT_lo[(size_t)(n + i) * a.ldct + m] = lo[i]; }
+            }
           } else if (EPI == EPI_RECON) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
@@ -327,7 +363,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         }
       }
     }
-    if (EPI == EPI_LAMBDA || EPI == EPI_LAMBDA_B) {
+    if (EPI == EPI_LAMBDA || EPI == EPI_LAMBDA_B || EPI == EPI_MU_H) {
       float* red = reinterpret_cast<float*>(tmem_slot + 2);
       for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
       if (lane_id() == 0) red[q] = dsum;
@@ -389,6 +425,7 @@ static int gemm_error_word(int** out) {
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
   DRNMF_CHECK(a.lda % 4 == 0 && a.ldb % 4 == 0, "tcgen05 GEMM needs row strides that are multiples of 4 floats");
   if (epi == EPI_STORE || epi == EPI_GRAM) DRNMF_CHECK(a.ldc % 4 == 0 && a.N_valid % 16 == 0, "tcgen05 GEMM store needs ldc%%4==0, N%%16==0");
+  if (epi == EPI_MU_H) DRNMF_CHECK(a.ldc % 4 == 0, "EPI_MU_H needs ldc%%4==0");
   if (epi == EPI_LAMBDA || epi == EPI_LAMBDA_B) DRNMF_CHECK(a.ldc % 4 == 0 && a.ldv % 4 == 0, "EPI_LAMBDA needs ldc%%4==0 and ldv%%4==0");
   int* errw = nullptr;
   int rc = gemm_error_word(&errw);
@@ -403,6 +440,7 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
     case EPI_STORE: return wide ? launch_tc_impl<EPI_STORE, 256>(a, st, errw) : launch_tc_impl<EPI_STORE, 128>(a, st, errw);
     case EPI_GRAM:  return wide ? launch_tc_impl<EPI_GRAM, 256>(a, st, errw) : launch_tc_impl<EPI_GRAM, 128>(a, st, errw);
     case EPI_RECON: return launch_tc_impl<EPI_RECON, 128>(a, st, errw);
+    case EPI_MU_H: return launch_tc_impl<EPI_MU_H, 128>(a, st, errw);
     case EPI_LAMBDA: return wide ? launch_tc_impl<EPI_LAMBDA, 256>(a, st, errw) : launch_tc_impl<EPI_LAMBDA, 128>(a, st, errw);
     case EPI_LAMBDA_B: return wide ? launch_tc_impl<EPI_LAMBDA_B, 256>(a, st, errw) : launch_tc_impl<EPI_LAMBDA_B, 128>(a, st, errw);
   }

@@ -81,7 +81,7 @@ int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_va
                     int B_tmajor = 0);
 
 // ---- gemm: C = A (M x K, K-major) . B^T (N x K, K-major) with a fused epilogue --------------------
-enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2, EPI_LAMBDA = 3, EPI_LAMBDA_B = 4 };
+enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2, EPI_LAMBDA = 3, EPI_LAMBDA_B = 4, EPI_MU_H = 5 };
 struct GemmArgs {
   const float *A_hi, *A_lo; int lda;     // M x Kd
   const float *B_hi, *B_lo; int ldb;     // N x Kd
@@ -108,6 +108,11 @@ struct GemmArgs {
   // tile-shape decision: when this launch is a row block of a larger product (pipelined projection), M_plan = that
   // product's row count, so that every block accumulates in the same order as the single launch would (bitwise equal)
   int M_plan;
+  // EPI_MU_H (dual-B; sparse_nmf_gpu.m:217-228): acc = (W^T P)[r][frame], acc2 = (W^T Q)[r][frame]; the epilogue applies
+  // h <- h .* acc2 ./ max(acc + mu, flr) to the rows with row_update != 0 (null = all) of H = C (R x ldc, in/out), writes
+  // C_lo, the transposed copy CT / CT_lo and the tile's sum of H into div_partials (for cost = div + mu sum H)
+  float mu;
+  const uint8_t* row_update;
 };
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);

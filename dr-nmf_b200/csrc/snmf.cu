@@ -341,11 +341,25 @@ int snmf_mu_ed(int F, int n, int R, float beta, const float* V, float* W, float*
     a.C = out; a.ldc = Rk; a.splits = w.splits; a.split_stride = (size_t)F * Rk;
     return run_gemm_impl(simt, EPI_STORE, a, st);
   };
+  // H update fused into ONE dual-operand GEMM (both W^T P and W^T Q against the same W^T tiles, atoms = M dimension): the
+  // epilogue applies h <- h .* (W^T Q) ./ max(W^T P + mu, flr) to the H tile, writes both layouts + remainders and the
+  // tile's sum of H.  Saves the (n x R) round trip of the two projections and the separate pass of k_mu_h over H
+  // (3.9 -> 3.1 ms of an 11.7 ms iteration at 513 x 225,000).  Used when W moves too (W^T Q is not constant).
+  auto h_update_gemm = [&](const float* P_hi, const float* P_lo, const float* Q_hi, const float* Q_lo) {
+    GemmArgs a{};
+    a.A_hi = w.WT_hi; a.A_lo = w.WT_lo; a.lda = Fk;
+    a.B_hi = P_hi; a.B_lo = P_lo; a.B2_hi = Q_hi; a.B2_lo = Q_lo; a.ldb = Fk;
+    a.M = R; a.N = n; a.Kd = Fk; a.M_valid = R; a.N_valid = n;
+    a.C = w.Hm_hi; a.C_lo = w.Hm_lo; a.ldc = nk; a.CT = w.Ht_hi; a.CT_lo = w.Ht_lo; a.ldct = Rk;
+    a.div_partials = w.hsum_part; a.flr = flr; a.mu = sparsity; a.row_update = h_update;
+    return run_gemm_impl(simt, EPI_MU_H, a, st);
+  };
+  const bool fused_h = !getenv("DRNMF_MU_UNFUSED");
   // number of div partials the lambda GEMM writes depends on the tiling of the implementation in use
   const int tile = simt ? 64 : 128;
   const int n_div = ((n + tile - 1) / tile) * ((F + tile - 1) / tile);
   const dim3 gh(Rk / 32, nk / 32);
-  const int n_h = gh.x * gh.y;
+  int n_h = gh.x * gh.y;                                           // partial sums of H written per iteration
 
   int rc;
   if ((rc = lambda_gemm())) return rc;
@@ -357,7 +371,11 @@ int snmf_mu_ed(int F, int n, int R, float beta, const float* V, float* W, float*
   double last_cost = INFINITY;
   int it = 0;
   for (it = 1; it <= max_iter; ++it) {
-    if (any_h_update) {
+    if (any_h_update && !dmh_constant && fused_h) {
+      if ((rc = h_update_gemm(w.Lt_hi, w.Lt_lo, Xt_hi, Xt_lo))) return rc;
+      n_h = ((R + tile - 1) / tile) * ((n + tile - 1) / tile);
+      if ((rc = lambda_gemm())) return rc;
+    } else if (any_h_update) {
       if ((rc = proj_gemm(w.Lt_hi, w.Lt_lo, w.dph))) return rc;
       if (!dmh_constant) { if ((rc = proj_gemm(Xt_hi, Xt_lo, w.dmh))) return rc; }
       k_mu_h<<<gh, tb, 0, st>>>(w.Ht_hi, w.Ht_lo, w.Hm_hi, w.Hm_lo, w.dph, w.dmh, n, R, Rk, nk, sparsity, flr, h_update, 1, w.hsum_part);
