@@ -75,12 +75,18 @@ DRNMF_API int drnmf_set_params(drnmf_handle* h, const float* log_D, int n_log_D,
 DRNMF_API size_t drnmf_workspace_bytes(const drnmf_handle* h, int B, int T);
 
 /* Replaces model_irm.predict_on_batch (enhance.py:1191-1193): Masking(mask_value) -> SimpleDeepRNN -> recon ->
- * divide_A_by_AplusB.  x (B,T,F) padded with mask_value; H (B,T,R) and irm (B,T,F) outputs (either may be NULL). */
+ * divide_A_by_AplusB.  x (B,T,F) padded with mask_value; H (B,T,R) and irm (B,T,F) outputs (either may be NULL).
+ * The call returns after the work is complete on `stream` (it reads back the device error word).  With at most 64
+ * utterances the projection of all but the first frames is computed NEXT to the persistent recurrence: the library then
+ * also uses a high-priority stream of its own, ordered after and joined back into `stream` (same results, bit for
+ * bit; DRNMF_FWD_OVERLAP=0 keeps everything on `stream`; automatically off under CUDA_LAUNCH_BLOCKING or an injected
+ * profiler / sanitizer, where kernels cannot overlap). */
 DRNMF_API int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H, float* irm, void* ws,
                   size_t ws_bytes, void* stream);
 
 /* Device time (ms, CUDA events on the call's stream) of the four stages of the last drnmf_forward on this handle:
- * [0] Masking + padding, [1] input-projection GEMM, [2] recurrence over (T x K_layers), [3] recon + mask GEMM. */
+ * [0] Masking + padding, [1] input-projection GEMM (only the part in front of the recurrence when the rest is pipelined
+ * under it), [2] recurrence over (T x K_layers), [3] recon + mask GEMM. */
 DRNMF_API int drnmf_stage_times(drnmf_handle* h, float* ms4);
 
 /* How the recurrence of the last drnmf_forward ran: cfg9[0] = 0 persistent tcgen05 kernel / 1 SIMT per-step kernels;
