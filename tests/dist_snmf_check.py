@@ -29,18 +29,25 @@ def main():
     H0 = np.abs(rng.standard_normal((R, n))).astype(np.float32) + 0.01
     sl = slice(rank * n_per, (rank + 1) * n_per)
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
-    Vd, Wd, Hd = dev(V[:, sl]), dev(W0), dev(H0[:, sl])
-    cost, div = eng.snmf_mu_ed(Vd, Wd, Hd, mu, iters, distributed=True)
-    torch.cuda.synchronize()
     ok = True
-    if rank == 0:
-        Vf, Wf, Hf = dev(V), dev(W0), dev(H0)
-        cost1, div1 = eng.snmf_mu_ed(Vf, Wf, Hf, mu, iters)
-        rel = lambda a, b: float((a - b).norm() / b.norm())
-        eW, eH = rel(Wd, Wf), rel(Hd, Hf[:, sl])
-        ec = float(np.max(np.abs(cost - cost1) / np.abs(cost1)))
-        print("dist_snmf world=%d relW=%.2e relH=%.2e relcost=%.2e iters=%d" % (world, eW, eH, ec, len(cost)), flush=True)
-        ok = eW < 1e-4 and eH < 1e-4 and ec < 1e-5 and len(cost) == len(cost1)
+    # beta = 2 (ED) and beta = 1 (KL) with zeros in V whose smallest positive entry lives on the LAST rank only: the
+    # sharded solve must raise the zeros to the GLOBAL minimum (sparse_nmf_gpu.m:201-205; MIN all-reduce)
+    for beta in (2.0, 1.0):
+        Vb = V.copy()
+        if beta != 2.0:
+            Vb[rng.random(Vb.shape) < 0.02] = 0.0
+            Vb[3, n - 5] = 1e-4
+        Vd, Wd, Hd = dev(Vb[:, sl]), dev(W0), dev(H0[:, sl])
+        cost, div = eng.snmf_mu_ed(Vd, Wd, Hd, mu, iters, distributed=True, beta=beta)
+        torch.cuda.synchronize()
+        if rank == 0:
+            Vf, Wf, Hf = dev(Vb), dev(W0), dev(H0)
+            cost1, div1 = eng.snmf_mu_ed(Vf, Wf, Hf, mu, iters, beta=beta)
+            rel = lambda a, b: float((a - b).norm() / b.norm())
+            eW, eH = rel(Wd, Wf), rel(Hd, Hf[:, sl])
+            ec = float(np.max(np.abs(cost - cost1) / np.abs(cost1)))
+            print("dist_snmf world=%d beta=%g relW=%.2e relH=%.2e relcost=%.2e iters=%d" % (world, beta, eW, eH, ec, len(cost)), flush=True)
+            ok = ok and eW < 1e-4 and eH < 1e-4 and ec < 1e-5 and len(cost) == len(cost1)
     # W must be bit-identical on every rank (same reduced sums, same update)
     Wall = [torch.empty_like(Wd) for _ in range(world)]
     dist.all_gather(Wall, Wd)
