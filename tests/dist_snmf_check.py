@@ -19,8 +19,14 @@ import drnmf_b200.engine as eng  # noqa: E402
 
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # DIST_ONE_GPU=1: all ranks share cuda:0 and reduce over gloo (NCCL refuses two ranks on one device) - lets a 1-GPU box
+    # exercise the sharded code path and its callbacks
+    if os.environ.get("DIST_ONE_GPU") == "1":
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F, R, n_per, iters, mu = 257, 100, 700, 12, 3.0
     n = n_per * world
     rng = np.random.default_rng(5)

@@ -524,15 +524,17 @@ def test_snmf_long_contraction_vs_oracle():
 
 @pytest.mark.gpu
 def test_snmf_frame_sharded():
-    """MU-ED with the frames sharded over 2 GPUs (all-reduce of V H^T, Lambda H^T and the cost) equals the
-    single-GPU solve.  Needs two devices; on a 1-GPU box it is skipped (the gloo CPU tests cover the sharding maths)."""
+    """MU (ED, and KL with the MIN all-reduce of sparse_nmf_gpu.m:201-205) with the frames sharded over 2 ranks
+    (all-reduce of V H^T, Lambda H^T and the cost) equals the single-GPU solve.  Two devices: NCCL, one rank per GPU.
+    On a 1-GPU box both ranks share the device and reduce over gloo - the same library path and callbacks."""
     import subprocess
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(here, "dist_snmf_check.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if torch.cuda.device_count() < 2:
+        env["DIST_ONE_GPU"] = "1"
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "replicas identical: True" in p.stdout
 
