@@ -231,6 +231,33 @@ def test_snmf_beta_divergences_vs_oracle(cf, beta, impl):
         np.testing.assert_allclose(np.sqrt((W.astype(np.float64) ** 2).sum(0)), 1.0, rtol=1e-5)
 
 
+@pytest.mark.parametrize("cf", ["ed", "kl"])
+def test_snmf_partial_h_and_w_update_masks(cf, monkeypatch):
+    """h_update_ind / w_update_ind subsets (sparse_nmf_gpu.m:150-155) through the fused H-update GEMM (row mask in the
+    epilogue) and through the two-projection path (DRNMF_MU_UNFUSED=1): same numbers, both equal to the oracle."""
+    from drnmf_b200 import snmf as S
+    F, n, R, iters = 70, 333, 48, 6
+    rng = np.random.default_rng(123)
+    V = (np.abs(rng.standard_normal((F, n))) + 0.05).astype(np.float32)
+    W0 = (np.abs(rng.standard_normal((F, R))) + 0.1).astype(np.float32)
+    H0 = (np.abs(rng.standard_normal((R, n))) + 0.1).astype(np.float32)
+    prm = {"cf": cf, "sparsity": 0.3, "max_iter": iters, "conv_eps": 0.0, "r": R, "init_w": W0, "init_h": H0,
+           "h_update_ind": np.arange(R) % 3 != 0, "w_update_ind": np.arange(R) < R // 2}
+    Wo, Ho, obj = O.sparse_nmf_beta(V, prm, dtype=np.float64)
+    outs = []
+    for unfused in ("0", "1"):
+        if unfused == "1":
+            monkeypatch.setenv("DRNMF_MU_UNFUSED", "1")
+        W, H, o = S.sparse_nmf_matlab_on_chunk(V, prm, verbose=False)
+        assert max(rel_err(W, Wo)) < TOL and max(rel_err(H, Ho)) < TOL, (cf, unfused, rel_err(W, Wo), rel_err(H, Ho))
+        np.testing.assert_allclose(o["cost"], obj["cost"], rtol=5e-5)
+        frozen = ~prm["h_update_ind"]
+        wn = np.sqrt((W0.astype(np.float64) ** 2).sum(0))
+        np.testing.assert_allclose(H[frozen], (H0 * wn[:, None])[frozen], rtol=1e-6)      # frozen rows only see the initial rescale
+        outs.append((W, H))
+    assert max(rel_err(outs[0][1], outs[1][1])) < 1e-5
+
+
 def test_snmf_beta2_entry_equals_ed_entry():
     """drnmf_snmf_mu_beta(beta = 2) IS the Euclidean solver: bitwise the same iterates as drnmf_snmf_mu_ed."""
     F, n, R = 65, 300, 40
