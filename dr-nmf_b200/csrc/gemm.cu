@@ -20,13 +20,14 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
   const int m0 = blockIdx.y * SIMT_BM, n0 = blockIdx.x * SIMT_BN;
   const int nsplit = a.splits > 1 ? a.splits : 1;
   const int kchunk = ((a.Kd + nsplit - 1) / nsplit + SIMT_BK - 1) / SIMT_BK * SIMT_BK;
-  const int kbeg = blockIdx.z * kchunk;
+  const int zsplit = blockIdx.z + a.split_z0;
+  const int kbeg = zsplit * kchunk;
   int klen = a.Kd - kbeg; if (klen > kchunk) klen = kchunk; if (klen < 0) klen = 0;
   constexpr bool DUAL = (EPI == EPI_RECON || EPI == EPI_MU_H);
   simt_tile_mainloop<DUAL>(a.A_hi + kbeg, a.lda, a.M, a.B_hi + kbeg, DUAL ? a.B2_hi + kbeg : nullptr,
                                        a.ldb, a.N, klen, m0, n0, acc, acc2);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float* Cz = a.C + (size_t)blockIdx.z * a.split_stride;
+  float* Cz = a.C + (size_t)zsplit * a.split_stride;
   float dsum = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gemm_simt(GemmArgs a) {
 }
 
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st) {
-  dim3 grid((a.N + SIMT_BN - 1) / SIMT_BN, (a.M + SIMT_BM - 1) / SIMT_BM, a.splits > 1 ? a.splits : 1);
+  dim3 grid((a.N + SIMT_BN - 1) / SIMT_BN, (a.M + SIMT_BM - 1) / SIMT_BM, a.split_nz > 0 ? a.split_nz : (a.splits > 1 ? a.splits : 1));
   switch (epi) {
     case EPI_STORE: k_gemm_simt<EPI_STORE><<<grid, SIMT_THREADS, 0, st>>>(a); break;
     case EPI_GRAM:  k_gemm_simt<EPI_GRAM><<<grid, SIMT_THREADS, 0, st>>>(a); break;
@@ -142,7 +143,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const int total_kb = (a.Kd + TC_BK - 1) / TC_BK;
   const int nsplit = a.splits > 1 ? a.splits : 1;
   const int kb_chunk = (total_kb + nsplit - 1) / nsplit;
-  const int kb0 = blockIdx.z * kb_chunk;
+  const int zsplit = blockIdx.z + a.split_z0;
+  const int kb0 = zsplit * kb_chunk;
   int num_kb = total_kb - kb0; if (num_kb > kb_chunk) num_kb = kb_chunk; if (num_kb < 0) num_kb = 0;
 
   if (warp == 0 && lane_id() == 0) {
@@ -256,7 +258,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         if (m < a.M_valid) {
           if (EPI == EPI_STORE) {
             if (n < a.N_valid) {
-              float4* dst = reinterpret_cast<float4*>(a.C + (size_t)blockIdx.z * a.split_stride + (size_t)m * a.ldc + n);
+              float4* dst = reinterpret_cast<float4*>(a.C + (size_t)zsplit * a.split_stride + (size_t)m * a.ldc + n);
               if (a.bias) {
                 const float4* bb = reinterpret_cast<const float4*>(a.bias + n);
 #pragma unroll
@@ -400,7 +402,7 @@ static int launch_tc_impl(const GemmArgs& a, cudaStream_t st, int* dev_error) {
     DRNMF_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, TC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set[dev] = true;
   }
-  dim3 grid((a.M + TC_BM - 1) / TC_BM, (a.N + TC_BN - 1) / TC_BN, a.splits > 1 ? a.splits : 1);
+  dim3 grid((a.M + TC_BM - 1) / TC_BM, (a.N + TC_BN - 1) / TC_BN, a.split_nz > 0 ? a.split_nz : (a.splits > 1 ? a.splits : 1));
   k_gemm_tc<EPI, TC_BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tB2_hi, tB2_lo, a, dev_error);
   count_launch();
   DRNMF_CUDA(cudaGetLastError());

@@ -113,6 +113,10 @@ struct GemmArgs {
   // C_lo, the transposed copy CT / CT_lo and the tile's sum of H into div_partials (for cost = div + mu sum H)
   float mu;
   const uint8_t* row_update;
+  // split-K sub-range: launch only the blocks [split_z0, split_z0 + split_nz) of the `splits` K-blocks (split_nz = 0: all).
+  // The block boundaries are those of the full product, so a product can be computed in several launches as its
+  // K range (time-major frames in the weight-gradient GEMMs) becomes available.
+  int split_z0, split_nz;
 };
 int launch_gemm_simt(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
@@ -121,8 +125,11 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 int launch_recurrent_simt(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
 int recurrent_plan_ctas(const drnmf_handle* h, int B);   // CTAs of the forward plan for batch B (INT_MAX-like large value when none)
+// progress (optional, device word, zeroed by the caller): the chain stores (release) the number of completely processed
+// frames (t = T-1, T-2, ...) as it goes; only honoured for single-tile, single-group plans (*progress_ok says so)
 int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,
-                            float* deltaT_lo, float* G, float* psum2, cudaStream_t st);
+                            float* deltaT_lo, float* G, float* psum2, cudaStream_t st, unsigned int* progress = nullptr,
+                            bool* progress_ok = nullptr);
 
 // ---- stft.cu -------------------------------------------------------------------------------------
 // fidx: (n_utt, 2) int64 (start, end) frame indices per utterance, the reference's fidx (util.py:335-337)

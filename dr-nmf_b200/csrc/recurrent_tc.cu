@@ -76,6 +76,7 @@ struct RecArgs {
   // pipelined forward: XW rows are time-major (t*Btot + b) and the frames >= xw_t0 are only valid once *xw_ready != 0
   const unsigned int* xw_ready; int xw_tmajor, xw_t0, Btot;
   unsigned int* started;                     // optional: every CTA counts itself in once it is resident (after the cluster sync)
+  unsigned int* progress;                    // optional (backward chain, one tile, one group): completely processed frames
   int* dev_error;
   int dbg_m;                                 // M-tile of the observed CTA (K-split 0)
   long long* dbg;                            // optional per-role wait-time counters of CTA (0,0) (DRNMF_REC_DEBUG=1)
@@ -1096,6 +1097,10 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           const unsigned int target = (unsigned int)(a.pub_unit * a.KS) * (unsigned int)(a.ll ? fi : fi * K);
           if (otid < a.MT && !poll_flag(a.flags + i * a.MT + otid, target, err)) rt_fail(a.dev_error, 219);
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          // every CTA's stores of the frames processed so far (fi of them) have been released and acquired here: tell the
+          // host-side streams that the weight-gradient GEMMs over those frames may start (cumulative release)
+          if (a.progress && otid == 0 && s == 0 && m == 0)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.progress), "r"((unsigned int)fi) : "memory");
           const int b = otid % NB, part = otid / NB, nparts = 128 / NB;
           float s0 = 0.f, s1 = 0.f;
           const float* ps = a.psum2 + (size_t)((fi - 1) & 1) * 256 * 2 * a.Bp + i * NB + b;
@@ -1642,7 +1647,7 @@ static void record_cfg(const RecPlan& p, int* cfg8, int* groups) {
 
 // Backward chain on the persistent kernel.  Returns 1 (error text set) when no tiling covers the shape.
 int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,
-                            float* deltaT_lo, float* G, float* psum2, cudaStream_t st) {
+                            float* deltaT_lo, float* G, float* psum2, cudaStream_t st, unsigned int* progress, bool* progress_ok) {
   const int K = h->K, Rp = h->Rp;
   if (K < 2) return 1;
   RecPlan p = choose_plan(h, B, true);
@@ -1651,6 +1656,9 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   RecArgs& a = p.a;
   a.XW = nullptr; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.xw_tmajor = 0; a.xw_t0 = 0; a.xw_ready = nullptr; a.Btot = B; a.started = nullptr;
+  const bool prog_ok = (p.n_tiles_total == 1 && p.G == 1);
+  a.progress = prog_ok ? progress : nullptr;
+  if (progress_ok) *progress_ok = prog_ok;
   a.state = nullptr; a.psum = nullptr; a.Hp_hi = nullptr; a.Hp_lo = nullptr; a.H_user = nullptr;
   a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
   a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo;
@@ -1694,6 +1702,7 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   a.XW = w.XW; a.mvalid = w.mvalid; a.h0 = h->h0;
   a.xw_tmajor = w.xw_tmajor; a.xw_t0 = w.xw_t0; a.xw_ready = w.xw_tmajor ? w.xw_ready : nullptr; a.Btot = B;
   a.started = w.xw_tmajor ? w.xw_ready + 1 : nullptr;
+  a.progress = nullptr;
   a.state = w.state; a.psum = w.psum; a.Hp_hi = w.Hp_hi; a.Hp_lo = w.Hp_lo; a.H_user = H_user;
   a.hb_hi = w.hb_hi; a.hb_lo = w.hb_lo; a.flags = w.flags; a.dev_error = h->dev_error;
   a.actT_hi = w.actT_hi; a.actT_lo = w.actT_lo;

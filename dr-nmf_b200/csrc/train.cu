@@ -31,6 +31,9 @@ struct TrainWs {
   float *psum2;                // 2 x 256 x 2 x Bp  partial row sums of the persistent backward chain
   float *rs_part;              // K x NC x Bp  partial row sums of delta^k (rank-1 leak gradient), NC = Rp/64 column tiles
   float *part;                 // split-K partials (max over the GEMMs that use them)
+  float *partS_all, *partX_all;// K x splits x Rp x Rp and K x splits x Rp x Fx: per-layer partials of the weight-gradient
+                               // GEMMs when their late-frame blocks are computed under the backward chain
+  unsigned int* progress;      // frames the backward chain has completely processed (device word)
   float *gsym_hi, *gsym_lo;    // Rp x Rp
   float *dDt;                  // Rp x Fp
   float *dEc;                  // 2 x Rp x Fp   H^T dS , H^T dN
@@ -67,6 +70,12 @@ static TrainWs carve_train(const drnmf_handle* h, int B, int T, void* base) {
   w.splits_x = w.splits_w;
   const size_t part_elems = (size_t)w.splits_w * Rp * (Rp > (size_t)w.Fx ? Rp : (size_t)w.Fx);
   w.part = (float*)take(part_elems * 4);
+  w.partS_all = nullptr; w.partX_all = nullptr;
+  if (w.splits_w == 8) {      // the pipelined plan exists for 8 split-K blocks (kb >= 256: every training-sized batch)
+    w.partS_all = (float*)take((size_t)K * w.splits_w * Rp * Rp * 4);
+    w.partX_all = (float*)take((size_t)K * w.splits_x * Rp * (size_t)w.Fx * 4);
+  }
+  w.progress = (unsigned int*)take(256);
   w.gsym_hi = (float*)take(Rp * Rp * 4); w.gsym_lo = (float*)take(Rp * Rp * 4);
   w.dDt = (float*)take(Rp * Fp * 4);
   w.dEc = (float*)take(2 * Rp * Fp * 4);
@@ -547,6 +556,28 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   ba.alph = (h->alph_dim > 1) ? h->alph : nullptr;
   const dim3 gstep(Rp / SIMT_BN, (B + SIMT_BM - 1) / SIMT_BM);
   int bwd_rc = 1;
+  // Weight gradients pipelined under the backward chain.  The chain occupies 64 SMs and walks the frames from the last
+  // to the first; the weight-gradient GEMMs contract over TIME-major frames, so their split-K blocks over the late
+  // frames are complete long before the chain ends.  Blocks 4..7 (of 8) of every layer are launched on a second stream
+  // once the chain reports half of the frames done, blocks 2..3 at three quarters, blocks 0..1 after the chain; the
+  // per-layer kernels then sum the 8 partials in block order as before (same numbers as the serial order).
+  // DRNMF_TRAIN_OVERLAP=0 = serial; off when launches are serialised or stream memory operations are missing.
+  bool want_pipe = false, piped = false;
+  {
+    const char* e = getenv("DRNMF_TRAIN_OVERLAP");
+    const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+    want_pipe = !(e && !strcmp(e, "0")) && h->impl != DRNMF_IMPL_SIMT && K >= 2 && w.partS_all && T >= 32 &&
+                !(lb && atoi(lb) != 0) && !getenv("CUDA_INJECTION64_PATH") && !getenv("NV_NSIGHT_INJECTION_PORT_BASE") &&
+                stream_wait_geq(nullptr, nullptr, 0) == 0;
+    if (want_pipe && !h->hi_ready) {
+      int least = 0, greatest = 0;
+      DRNMF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      DRNMF_CUDA(cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, greatest));
+      DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[0], cudaEventDisableTiming));
+      DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[1], cudaEventDisableTiming));
+      h->hi_ready = true;
+    }
+  }
   h->last_bwd_impl = 1;
   {
     bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
@@ -554,7 +585,14 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
     if (e && !strcmp(e, "simt")) rec_simt = true;
     if (!rec_simt) {
       // K == 1 has no layer-to-layer product at all: the per-frame kernels below are the whole chain
-      bwd_rc = (K < 2) ? 1 : launch_recurrent_bwd_tc(h, w.fwd, B, T, w.dH, w.deltaT_hi, w.deltaT_lo, w.G, w.psum2, st);
+      if (want_pipe) {
+        DRNMF_CUDA(cudaMemsetAsync(w.progress, 0, 4, st));
+        DRNMF_CUDA(cudaEventRecord(h->ev_ov[0], st));           // everything the early GEMMs read besides the deltas is complete
+      }
+      bool prog_ok = false;
+      bwd_rc = (K < 2) ? 1 : launch_recurrent_bwd_tc(h, w.fwd, B, T, w.dH, w.deltaT_hi, w.deltaT_lo, w.G, w.psum2, st,
+                                                     want_pipe ? w.progress : nullptr, &prog_ok);
+      piped = want_pipe && bwd_rc == 0 && prog_ok;
       if (bwd_rc == 1 && K >= 2) return DRNMF_ERR_INVALID;      // no silent CUDA-core fallback (error text set by the planner)
       if (bwd_rc != 0 && bwd_rc != 1) return bwd_rc;
       if (bwd_rc == 0) {
@@ -580,16 +618,52 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   count_launch();
   // ---------------- recurrence-free weight gradients + parameter chain, layer by layer ----------------
   const bool tied_D = (h->n_log_D == 1), tied_a = (h->n_log_alph == 1), tied_l = (h->n_log_lam1 == 1);
+  // split-K blocks [z0, z0 + nz) of layer k's two weight-gradient GEMMs (nz = 0: all blocks, into the shared buffer)
+  auto gemm_dS = [&](int k, float* out, int z0, int nz, cudaStream_t s_) {
+    GemmArgs a{};   // partial dS_k^T[j][i] = sum_frames delta^k[j][frame] act^{k-1}[i][frame]
+    a.A_hi = w.deltaT_hi + (size_t)k * Rp * TB; a.A_lo = w.deltaT_lo + (size_t)k * Rp * TB; a.lda = (int)TB;
+    a.B_hi = w.fwd.actT_hi + (size_t)(k - 1) * Rp * TB; a.B_lo = w.fwd.actT_lo + (size_t)(k - 1) * Rp * TB; a.ldb = (int)TB;
+    a.M = Rp; a.N = Rp; a.Kd = (int)TB; a.C = out; a.ldc = Rp; a.M_valid = Rp; a.N_valid = Rp;
+    a.splits = w.splits_w; a.split_stride = (size_t)Rp * Rp; a.split_z0 = z0; a.split_nz = nz;
+    return gemm(h, EPI_STORE, a, s_);
+  };
+  auto gemm_dX = [&](int k, float* out, int z0, int nz, cudaStream_t s_) {
+    GemmArgs a{};   // partial [dWt_k | db_k][j][f] = sum_frames delta^k[j][frame] [x~ ; 1][f][frame]
+    a.A_hi = w.deltaT_hi + (size_t)k * Rp * TB; a.A_lo = w.deltaT_lo + (size_t)k * Rp * TB; a.lda = (int)TB;
+    a.B_hi = w.xT_hi; a.B_lo = w.xT_lo; a.ldb = (int)TB;
+    a.M = Rp; a.N = w.Fx; a.Kd = (int)TB; a.C = out; a.ldc = w.Fx; a.M_valid = Rp; a.N_valid = w.Fx;
+    a.splits = w.splits_x; a.split_stride = (size_t)Rp * w.Fx; a.split_z0 = z0; a.split_nz = nz;
+    return gemm(h, EPI_STORE, a, s_);
+  };
+  const size_t strideS = (size_t)w.splits_w * Rp * Rp, strideX = (size_t)w.splits_x * Rp * (size_t)w.Fx;
+  int z_late = w.splits_w;                                   // blocks [0, z_late) remain for the serial phase
+  if (piped) {
+    // block z covers the K columns [z * cols, (z + 1) * cols) of the time-major frames, i.e. the frames >= z * cols / Bp;
+    // they are complete once the chain has processed T - floor(z * cols / Bp) frames
+    const int kb_chunk = ((int)(TB / 32) + w.splits_w - 1) / w.splits_w;
+    const long long cols = (long long)kb_chunk * 32;
+    DRNMF_CUDA(cudaStreamWaitEvent(h->hi, h->ev_ov[0], 0));
+    const int phase_z0[2] = {4, 2}, phase_nz[2] = {4, 2};
+    for (int ph = 0; ph < 2; ++ph) {
+      const int t_min = (int)((phase_z0[ph] * cols) / Bp);
+      const unsigned int need = (unsigned int)(T - t_min);
+      if (need >= (unsigned int)T) break;                      // (never for 8 blocks; guards the wait below)
+      if (stream_wait_geq(h->hi, w.progress, need)) { set_error("cuStreamWaitValue32 failed"); return DRNMF_ERR_CUDA; }
+      for (int k = 0; k < K; ++k) {
+        if (k >= 1 && (rc = gemm_dS(k, w.partS_all + (size_t)k * strideS, phase_z0[ph], phase_nz[ph], h->hi))) return rc;
+        if ((rc = gemm_dX(k, w.partX_all + (size_t)k * strideX, phase_z0[ph], phase_nz[ph], h->hi))) return rc;
+      }
+      z_late = phase_z0[ph];
+    }
+    DRNMF_CUDA(cudaEventRecord(h->ev_ov[1], h->hi));
+    DRNMF_CUDA(cudaStreamWaitEvent(st, h->ev_ov[1], 0));        // (st is behind the chain here: the wait costs nothing)
+  }
   for (int k = 0; k < K; ++k) {
     DRNMF_CUDA(cudaMemsetAsync(w.rowacc, 0, (size_t)Rp * 4 * 4, st));
+    float* partS = piped ? w.partS_all + (size_t)k * strideS : w.part;
     if (k >= 1) {
-      GemmArgs a{};   // partial dS_k^T[j][i] = sum_frames delta^k[j][frame] act^{k-1}[i][frame]
-      a.A_hi = w.deltaT_hi + (size_t)k * Rp * TB; a.A_lo = w.deltaT_lo + (size_t)k * Rp * TB; a.lda = (int)TB;
-      a.B_hi = w.fwd.actT_hi + (size_t)(k - 1) * Rp * TB; a.B_lo = w.fwd.actT_lo + (size_t)(k - 1) * Rp * TB; a.ldb = (int)TB;
-      a.M = Rp; a.N = Rp; a.Kd = (int)TB; a.C = w.part; a.ldc = Rp; a.M_valid = Rp; a.N_valid = Rp;
-      a.splits = w.splits_w; a.split_stride = (size_t)Rp * Rp;
-      if ((rc = gemm(h, EPI_STORE, a, st))) return rc;
-      k_gsym<<<dim3(Rp / 32, Rp / 32), tb, 0, st>>>(w.part, w.splits_w, h->ST_hi + (size_t)(k - 1) * Rp * Rp, h->alph + (size_t)k * Rp,
+      if ((rc = piped ? gemm_dS(k, partS, 0, z_late, st) : gemm_dS(k, partS, 0, 0, st))) return rc;
+      k_gsym<<<dim3(Rp / 32, Rp / 32), tb, 0, st>>>(partS, w.splits_w, h->ST_hi + (size_t)(k - 1) * Rp * Rp, h->alph + (size_t)k * Rp,
                                                      R, Rp, w.gsym_hi, w.gsym_lo, w.rowS);
       count_launch();
       GemmArgs g{};   // dDt_S[j][f] = sum_i Gsym[j][i] D^[f][i]
@@ -598,16 +672,10 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
       g.M = Rp; g.N = Fp; g.Kd = Rp; g.C = w.dDt; g.ldc = Fp; g.M_valid = Rp; g.N_valid = Fp;
       if ((rc = gemm(h, EPI_STORE, g, st))) return rc;
     }
-    {
-      GemmArgs a{};   // partial [dWt_k | db_k][j][f] = sum_frames delta^k[j][frame] [x~ ; 1][f][frame]
-      a.A_hi = w.deltaT_hi + (size_t)k * Rp * TB; a.A_lo = w.deltaT_lo + (size_t)k * Rp * TB; a.lda = (int)TB;
-      a.B_hi = w.xT_hi; a.B_lo = w.xT_lo; a.ldb = (int)TB;
-      a.M = Rp; a.N = w.Fx; a.Kd = (int)TB; a.C = w.part; a.ldc = w.Fx; a.M_valid = Rp; a.N_valid = w.Fx;
-      a.splits = w.splits_x; a.split_stride = (size_t)Rp * w.Fx;
-      if ((rc = gemm(h, EPI_STORE, a, st))) return rc;
-    }
+    float* partX = piped ? w.partX_all + (size_t)k * strideX : w.part;
+    if ((rc = piped ? gemm_dX(k, partX, 0, z_late, st) : gemm_dX(k, partX, 0, 0, st))) return rc;
     float* gD = g_log_D + (tied_D ? 0 : (size_t)k * F * R);
-    k_param_chain<<<(R + 7) / 8, 256, 0, st>>>(w.dDt, k >= 1, w.part, w.splits_x, w.Fx, h->Dt_hi + (size_t)k * Rp * Fp,
+    k_param_chain<<<(R + 7) / 8, 256, 0, st>>>(w.dDt, k >= 1, partX, w.splits_x, w.Fx, h->Dt_hi + (size_t)k * Rp * Fp,
                                                 h->Wt_hi + (size_t)k * Rp * Fp, h->bias + (size_t)k * Rp, h->alph + (size_t)k * Rp,
                                                 F, R, Rp, Fp, gD, (tied_D && k > 0) ? 1 : 0, w.rowacc);
     k_scalar_grads<<<1, 256, 0, st>>>(w.rowacc, w.rowS, k >= 1 ? Rp / 32 : 0, R, h->alph_dim, g_log_alph + (tied_a ? 0 : (size_t)k * h->alph_dim), g_log_lam1 + (tied_l ? 0 : k),

@@ -312,6 +312,30 @@ def test_pipelined_projection_falls_back_when_launches_are_serialised():
         assert "equal to the serial result: True" in r.stdout
 
 
+def test_pipelined_weight_gradients_are_bitwise_the_serial_order(monkeypatch):
+    """drnmf_loss_and_grads launches the late-frame split-K blocks of the weight-gradient GEMMs on a second stream while the
+    backward chain still walks the early frames (chain progress word + cuStreamWaitValue32).  Same partial sums, same
+    order: the gradients must be bit-identical to the serial order (which the autograd tests pin), ragged batch."""
+    F, R, K, B, T = 65, 200, 4, 12, 160            # T * ceil64(B) = 10240 columns -> 8 split-K blocks: the pipelined plan
+    p = synth.model_params(F, R, K, alph=60.0)
+    eng = engine.DrnmfEngine(F, R, K)
+    eng.set_params(p)
+    x, _ = _synthetic_batch(B, T, F, seed=5)
+    x[2, 0] = -1.0
+    xd = torch.as_tensor(x, device="cuda")
+    yd = xd * 0.5
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DRNMF_TRAIN_OVERLAP", mode)
+        ls, ms, g = eng.loss_and_grads(xd, yd)
+        torch.cuda.synchronize()
+        out[mode] = (ls, {k: v.clone() for k, v in g.items()})
+    assert out["0"][0] == out["1"][0]
+    for k in out["0"][1]:
+        assert torch.equal(out["0"][1][k], out["1"][1][k]), k
+        assert torch.isfinite(out["1"][1][k]).all()
+
+
 def test_device_error_is_not_sticky():
     """a latched device-side error word must not poison later calls on the same handle."""
     F, R, K = 33, 16, 2
