@@ -193,8 +193,22 @@ size_t drnmf_workspace_bytes(const drnmf_handle* h, int B, int T) {
   return carve_forward_ws(h, B, T, nullptr).bytes;
 }
 
+// x_host != NULL (drnmf_enhance_host): x is the device destination of the input that still sits in host memory; the
+// copy is issued here - in the pipelined order only the first frames in front of the recurrence, the rest under it.
+// after_upload (optional) runs on the host right after the last piece of the input copy has been enqueued on the stream:
+// drnmf_enhance_host queues its second, larger copy (the complex STFT, needed only by the synthesis) behind it.
+typedef int (*upload_hook_fn)(void*);
+static int forward_impl(drnmf_handle* h, const float* x, const float* x_host, int B, int T, float mask_value, float* H,
+                        float* irm, void* ws, size_t ws_bytes, void* stream, upload_hook_fn after_upload = nullptr,
+                        void* hook_arg = nullptr);
+
 int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H, float* irm, void* ws,
                   size_t ws_bytes, void* stream) {
+  return forward_impl(h, x, nullptr, B, T, mask_value, H, irm, ws, ws_bytes, stream);
+}
+
+static int forward_impl(drnmf_handle* h, const float* x, const float* x_host, int B, int T, float mask_value, float* H,
+                        float* irm, void* ws, size_t ws_bytes, void* stream, upload_hook_fn after_upload, void* hook_arg) {
   DRNMF_CHECK(h, "NULL handle");
   int rc = check_device(h);
   if (rc) return rc;
@@ -256,7 +270,16 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
   if (!overlap) w.xw_ready = nullptr;
   DRNMF_CUDA(cudaEventRecord(h->ev[0], st));
   if (overlap) DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 0, 8, st));
-  if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st, overlap ? B : 0))) return rc;
+  const size_t Fh = (size_t)h->F;
+  auto upload = [&](int t0, int nt) {       // frames [t0, t0 + nt) of every utterance: B runs of nt * F floats
+    return cudaMemcpy2DAsync(const_cast<float*>(x) + (size_t)t0 * Fh, (size_t)T * Fh * 4, x_host + (size_t)t0 * Fh, (size_t)T * Fh * 4,
+                             (size_t)nt * Fh * 4, (size_t)B, cudaMemcpyHostToDevice, st);
+  };
+  const bool split_in = overlap && x_host;
+  if (x_host) DRNMF_CUDA(split_in ? upload(0, T0) : cudaMemcpyAsync(const_cast<float*>(x), x_host, (size_t)BT * Fh * 4, cudaMemcpyHostToDevice, st));
+  bool hook_pending = after_upload != nullptr;
+  if (hook_pending && !split_in) { hook_pending = false; if ((rc = after_upload(hook_arg))) return rc; }
+  if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st, overlap ? B : 0, 0, split_in ? T0 : 0))) return rc;
   DRNMF_CUDA(cudaEventRecord(h->ev[1], st));
   auto project = [&](size_t row0, size_t rows) {   // XW[row][k*Rp + j] = x~[row] . W_k[:, j] + b_k[j] for a block of rows
     GemmArgs a{};
@@ -284,8 +307,11 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
   DRNMF_CUDA(cudaEventRecord(h->ev[3], rst));
   if (overlap) {
     DRNMF_CUDA(cudaEventRecord(h->ev_ov[1], h->hi));
+    if (split_in) DRNMF_CUDA(upload(T0, T - T0));            // copy engine only: travels while the kernel is being placed
+    if (hook_pending) { hook_pending = false; if ((rc = after_upload(hook_arg))) { cudaStreamSynchronize(h->hi); return rc; } }
     const unsigned int n_cta = (unsigned int)(h->rec_cfg[1] * h->rec_cfg[2] * h->rec_groups);
     if (stream_wait_geq(st, w.xw_ready + 1, n_cta)) { set_error("cuStreamWaitValue32 failed"); cudaStreamSynchronize(h->hi); return DRNMF_ERR_CUDA; }
+    if (split_in && (rc = launch_mask_pad(h, x, BT, mask_value, w, st, B, T0, T - T0))) { cudaStreamSynchronize(h->hi); return rc; }
     if ((rc = project((size_t)B * T0, (size_t)B * (T - T0)))) { cudaStreamSynchronize(h->hi); return rc; }
     DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 1, 4, st));     // 0x01010101, ordered after the GEMM on the caller's stream
     DRNMF_CUDA(cudaStreamWaitEvent(st, h->ev_ov[1], 0));
@@ -308,7 +334,7 @@ int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_valu
       // the second projection chunk never ran next to the persistent kernel (launches are being serialised by a tool
       // this library did not recognise): from now on this handle keeps the serial order; redo the call that way
       h->no_overlap = true;
-      return drnmf_forward(h, x, B, T, mask_value, H, irm, ws, ws_bytes, stream);
+      return forward_impl(h, x, x_host, B, T, mask_value, H, irm, ws, ws_bytes, stream);      // (the hook has run: not again)
     }
     return rc;
   }
@@ -608,18 +634,24 @@ int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const float* stack_
     DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_side[1], cudaEventDisableTiming));
     h->side_ready = true;
   }
-  DRNMF_CUDA(cudaMemcpyAsync(e.x, x_host, BT * F * 4, cudaMemcpyHostToDevice, st));
   DRNMF_CUDA(cudaMemcpyAsync(e.frames, frames_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   // the [Re;Im] stack (2/3 of the input bytes) is only read by the synthesis: it travels on a side stream under the
-  // network, ordered after whatever used the workspace before this call and before the mask/iSTFT kernels
-  DRNMF_CUDA(cudaEventRecord(h->ev_side[0], st));
-  DRNMF_CUDA(cudaStreamWaitEvent(h->side, h->ev_side[0], 0));
-  DRNMF_CUDA(cudaMemcpyAsync(e.stack, stack_host, 2 * F * BT * 4, cudaMemcpyHostToDevice, h->side));
-  DRNMF_CUDA(cudaEventRecord(h->ev_side[1], h->side));
+  // network, behind the magnitudes on the copy engine (forward_impl calls the hook once their copy is enqueued) and
+  // before the mask/iSTFT kernels
+  struct StackCopy { drnmf_handle* h; cudaStream_t st; float* dst; const float* src; size_t bytes; } sc{h, st, e.stack, stack_host, 2 * F * BT * 4};
+  auto stack_hook = [](void* p) -> int {
+    StackCopy* c = static_cast<StackCopy*>(p);
+    DRNMF_CUDA(cudaEventRecord(c->h->ev_side[0], c->st));
+    DRNMF_CUDA(cudaStreamWaitEvent(c->h->side, c->h->ev_side[0], 0));
+    DRNMF_CUDA(cudaMemcpyAsync(c->dst, c->src, c->bytes, cudaMemcpyHostToDevice, c->h->side));
+    DRNMF_CUDA(cudaEventRecord(c->h->ev_side[1], c->h->side));
+    return DRNMF_OK;
+  };
   k_enh_tables<<<(B + 127) / 128, 128, 0, st>>>(e.frames, B, T, L, e.fidx, e.out_offs);
   count_launch();
   DRNMF_CUDA(cudaMemsetAsync(e.audio, 0, (size_t)B * L * 4, st));
-  if ((rc = drnmf_forward(h, e.x, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream))) {
+  // (the magnitudes are uploaded inside: in the pipelined order only the first frames precede the recurrence)
+  if ((rc = forward_impl(h, e.x, x_host, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream, stack_hook, &sc))) {
     cudaStreamSynchronize(h->side);      // the caller may release the workspace: let the side copy land first
     return rc;
   }

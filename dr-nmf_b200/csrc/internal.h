@@ -77,8 +77,9 @@ int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const f
                        int alph_dim, const float* log_lam1, int n_log_lam1, const float* log_h0, const float* k_clean,
                        const float* k_noise, cudaStream_t st);
 // B_tmajor > 0: write xp rows time-major (row t*B + b for input row b*T + t, T = BT / B); mvalid stays b-major
+// (t_count > 0: only the frames [t_begin, t_begin + t_count) of every utterance)
 int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st,
-                    int B_tmajor = 0);
+                    int B_tmajor = 0, int t_begin = 0, int t_count = 0);
 
 // ---- gemm: C = A (M x K, K-major) . B^T (N x K, K-major) with a fused epilogue --------------------
 enum GemmEpi { EPI_STORE = 0, EPI_GRAM = 1, EPI_RECON = 2, EPI_LAMBDA = 3, EPI_LAMBDA_B = 4, EPI_MU_H = 5 };

@@ -144,11 +144,15 @@ int launch_prep_params(drnmf_handle* h, const float* log_D, int n_log_D, const f
 // Keras Masking(mask_value) (enhance.py:253): m = any_f(x != mask_value), x~ = x * m.  One warp per frame row;
 // writes the zero-padded row (Fp wide) and its tf32 remainder.
 __global__ void k_mask_pad(const float* __restrict__ x, int BT, int F, int Fp, float mask_value,
-                           float* __restrict__ xp_hi, float* __restrict__ xp_lo, float* __restrict__ mvalid, int B_tm) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= BT) return;
+                           float* __restrict__ xp_hi, float* __restrict__ xp_lo, float* __restrict__ mvalid, int B_tm,
+                           int t_begin, int t_count) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   size_t orow = row;                                   // output row: b-major like the input, or time-major (t*B + b)
-  if (B_tm > 0) { const int T = BT / B_tm, b = row / T, t = row - b * T; orow = (size_t)t * B_tm + b; }
+  if (B_tm > 0) {                                      // frames [t_begin, t_begin + t_count) of every utterance
+    if (row >= B_tm * t_count) return;
+    const int T = BT / B_tm, b = row / t_count, t = t_begin + (row - b * t_count);
+    row = b * T + t; orow = (size_t)t * B_tm + b;
+  } else if (row >= BT) return;
   const int lane = threadIdx.x & 31;
   const float* src = x + (size_t)row * F;
   bool any = false;
@@ -163,8 +167,10 @@ __global__ void k_mask_pad(const float* __restrict__ x, int BT, int F, int Fp, f
 }
 
 int launch_mask_pad(const drnmf_handle* h, const float* x, int BT, float mask_value, FwdWorkspace& w, cudaStream_t st,
-                    int B_tmajor) {
-  k_mask_pad<<<(BT + 7) / 8, 256, 0, st>>>(x, BT, h->F, h->Fp, mask_value, w.xp_hi, w.xp_lo, w.mvalid, B_tmajor);
+                    int B_tmajor, int t_begin, int t_count) {
+  const int rows = B_tmajor > 0 ? B_tmajor * (t_count > 0 ? t_count : BT / B_tmajor) : BT;
+  if (B_tmajor > 0 && t_count <= 0) { t_begin = 0; t_count = BT / B_tmajor; }
+  k_mask_pad<<<(rows + 7) / 8, 256, 0, st>>>(x, BT, h->F, h->Fp, mask_value, w.xp_hi, w.xp_lo, w.mvalid, B_tmajor, t_begin, t_count);
   count_launch();
   DRNMF_CUDA(cudaGetLastError());
   return DRNMF_OK;

@@ -793,7 +793,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
           else
             pre[bi] = (t == 0) ? __ldg(reinterpret_cast<const float4*>(a.h0 + rowq))
                                : __ldcg(reinterpret_cast<const float4*>(a.state + (size_t)bc * Rp + rowq));
-          if (last) mvp[bi] = __ldg(a.mvalid + (size_t)bc * T + t);
+          if (last) mvp[bi] = __ldcg(a.mvalid + (size_t)bc * T + t);   // L2: late frames' entries are written while the kernel runs
         }
       }
       if (dbg_on) { long long _n = clock64(); DBG_ADD(2, _n - _ts); _ts = _n; }
