@@ -248,6 +248,9 @@ static int forward_impl(drnmf_handle* h, const float* x, const float* x_host, in
     if (want && !forced) {
       const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
       if ((lb && atoi(lb) != 0) || getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) want = false;
+      // without the cooperative launch nothing guarantees that every CTA becomes resident: the stream would wait for ever
+      const char* cp = getenv("DRNMF_REC_COOP");
+      if (cp && !strcmp(cp, "0")) want = false;
     }
     if (want) {
       const bool env_plan = getenv("DRNMF_REC_KS") || getenv("DRNMF_REC_G") || getenv("DRNMF_REC_NB") || getenv("DRNMF_REC_NOSPLIT");
