@@ -1568,7 +1568,7 @@ static int launch_rec(const RecPlan& p, bool bwd, const CUtensorMap& tH_hi, cons
   return DRNMF_OK;
 }
 
-// Candidate tilings (measured on B200, R = 1000, K = 25; profiles/r2_recurrence_sweep.md):
+// Candidate tilings (measured on B200, R = 1000, K = 25; profiles/r2_recurrence_sweep.txt):
 //   * latency regime (B <= 64 utterances): every step is a chain of ~8 dependent hops (TMA, MMA, commit, DSMEM, reduce,
 //     release, flag, TMA) of 0.5 - 2k cycles each, insensitive to the bytes moved.  K-splits of 8 (cluster of 8, one
 //     batch group: only 15 such clusters are co-resident) keep the per-CTA weight stream and MMA burst shortest:
