@@ -16,7 +16,10 @@ static size_t al(size_t x) { return round_up_sz(x, 256); }
 FwdWorkspace carve_forward_ws(const drnmf_handle* h, int B, int T, void* base) {
   FwdWorkspace w;
   const size_t BT = (size_t)B * T, BTp = round_up_sz(BT, 128);
-  const int Bp = round_up(B, 64);
+  // padded batch = columns per frame of every time-major training buffer (the weight-gradient GEMMs contract over
+  // T * Bp columns): the latency plans (B <= 64) tile the batch in 16 / 32 columns, so 32 is enough there - half the
+  // contraction length (and half the memsets) of the 64 the throughput tiles need, at the reference's batch of 32
+  const int Bp = B <= 64 ? round_up(B, 32) : round_up(B, 64);
   w.Bp = Bp;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;

@@ -1667,6 +1667,7 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
   a.d0mo_b = h->u0_d - h->u0_o; a.o0_b = h->u0_o; a.ok_b = h->uk_o;
   a.dbg = nullptr;
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
+  DRNMF_CHECK(p.n_tiles_total * p.NB <= w.Bp, "batch tiles (%d x %d) exceed the padded batch %d", p.n_tiles_total, p.NB, w.Bp);
   a.u0_dmo = 0.f; a.u0_off = 0.f; a.uk_dmo = 0.f; a.uk_off = 0.f;
   DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
   // latency mode (one batch tile per group, NB <= 32): self-validating exchange; the ping-pong buffer starts zeroed
@@ -1724,6 +1725,7 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
     a.trace_hi = strchr(tr, ':') ? atoi(strchr(tr, ':') + 1) : a.trace_lo + 2;
   }
   a.B = B; a.Bp = w.Bp; a.T = T; a.K = K; a.R = h->R; a.Rp = Rp;
+  DRNMF_CHECK(p.n_tiles_total * p.NB <= w.Bp, "batch tiles (%d x %d) exceed the padded batch %d", p.n_tiles_total, p.NB, w.Bp);
   a.u0_dmo = h->u0_d - h->u0_o; a.u0_off = h->u0_o; a.uk_dmo = h->uk_d - h->uk_o; a.uk_off = h->uk_o;
   DRNMF_CUDA(cudaMemsetAsync(w.flags, 0, sizeof(unsigned int) * p.n_tiles_total * p.MT, st));
   // latency mode (one batch tile per group, NB <= 32): self-validating exchange; the ping-pong buffer starts zeroed

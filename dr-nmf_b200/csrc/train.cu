@@ -71,7 +71,7 @@ static TrainWs carve_train(const drnmf_handle* h, int B, int T, void* base) {
   const size_t part_elems = (size_t)w.splits_w * Rp * (Rp > (size_t)w.Fx ? Rp : (size_t)w.Fx);
   w.part = (float*)take(part_elems * 4);
   w.partS_all = nullptr; w.partX_all = nullptr;
-  if (w.splits_w == 8) {      // the pipelined plan exists for 8 split-K blocks (kb >= 256: every training-sized batch)
+  if (w.splits_w >= 4) {      // the pipelined plan needs >= 4 split-K blocks (kb >= 64: every training-sized batch)
     w.partS_all = (float*)take((size_t)K * w.splits_w * Rp * Rp * 4);
     w.partX_all = (float*)take((size_t)K * w.splits_x * Rp * (size_t)w.Fx * 4);
   }
@@ -558,9 +558,10 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   int bwd_rc = 1;
   // Weight gradients pipelined under the backward chain.  The chain occupies 64 SMs and walks the frames from the last
   // to the first; the weight-gradient GEMMs contract over TIME-major frames, so their split-K blocks over the late
-  // frames are complete long before the chain ends.  Blocks 4..7 (of 8) of every layer are launched on a second stream
-  // once the chain reports half of the frames done, blocks 2..3 at three quarters, blocks 0..1 after the chain; the
-  // per-layer kernels then sum the 8 partials in block order as before (same numbers as the serial order).
+  // frames are complete long before the chain ends.  The upper half of the split-K blocks of every layer is launched
+  // on a second stream once the chain reports half of the frames done, the next quarter at three quarters, the rest
+  // after the chain; the per-layer kernels then sum the partials in block order as before (same numbers as the
+  // serial order).
   // DRNMF_TRAIN_OVERLAP=0 = serial; off when launches are serialised or stream memory operations are missing.
   bool want_pipe = false, piped = false;
   {
@@ -643,7 +644,8 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
     const int kb_chunk = ((int)(TB / 32) + w.splits_w - 1) / w.splits_w;
     const long long cols = (long long)kb_chunk * 32;
     DRNMF_CUDA(cudaStreamWaitEvent(h->hi, h->ev_ov[0], 0));
-    const int phase_z0[2] = {4, 2}, phase_nz[2] = {4, 2};
+    const int S = w.splits_w;                                  // 8 blocks: {4..7}, {2,3}, then {0,1}; 4 blocks: {2,3}, {1}, then {0}
+    const int phase_z0[2] = {S / 2, S / 4}, phase_nz[2] = {S - S / 2, S / 2 - S / 4};
     for (int ph = 0; ph < 2; ++ph) {
       const int t_min = (int)((phase_z0[ph] * cols) / Bp);
       const unsigned int need = (unsigned int)(T - t_min);
