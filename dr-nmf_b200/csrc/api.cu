@@ -79,6 +79,153 @@ static int check_dev_error(drnmf_handle* h, cudaStream_t st, const char* what, i
   return DRNMF_OK;
 }
 
+// The forward pass (see drnmf_forward in drnmf.h).  x_host != NULL (drnmf_enhance_host): x is the device destination of
+// the input that still sits in host memory; the copy is issued here - in the pipelined order only the first frames in
+// front of the recurrence, the rest under it.  after_upload (optional) runs on the host right after the last piece of
+// the input copy has been enqueued: drnmf_enhance_host queues its second, larger copy (the complex STFT, needed only by
+// the synthesis) behind it.  actT_hi / actT_lo (training): time-major stores of every layer's activations.
+// final_check = false: the caller reads the device error word itself at the end of ITS call (no host sync here).
+int forward_core(drnmf_handle* h, const float* x, const float* x_host, int B, int T, float mask_value, float* H,
+                 float* irm, void* ws, size_t ws_bytes, void* stream, upload_hook_fn after_upload, void* hook_arg,
+                 float* actT_hi, float* actT_lo, bool final_check) {
+  DRNMF_CHECK(h, "NULL handle");
+  int rc = check_device(h);
+  if (rc) return rc;
+  DRNMF_CHECK(h->params_set, "drnmf_forward before drnmf_set_params");
+  DRNMF_CHECK(x && ws && B >= 1 && T >= 1, "drnmf_forward: bad arguments (x=%p ws=%p B=%d T=%d)", (const void*)x, ws, B, T);
+  DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  FwdWorkspace w = carve_forward_ws(h, B, T, ws);
+  if (ws_bytes < w.bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
+  w.actT_hi = actT_hi; w.actT_lo = actT_lo;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int BT = B * T;
+  if (!h->ev_ready) {
+    for (auto& e : h->ev) DRNMF_CUDA(cudaEventCreate(&e));
+    h->ev_ready = true;
+  }
+  h->ev_valid = false;
+  bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
+  {
+    const char* e = getenv("DRNMF_RECURRENT");      // debugging aid: mix tcgen05 GEMMs with the SIMT recurrence
+    if (e && !strcmp(e, "simt")) rec_simt = true;
+    if (e && !strcmp(e, "tc")) rec_simt = false;
+  }
+  // Pipelined projection (latency regime): the recurrence walks the frames in order and occupies 64 of the 148 SMs at
+  // the bench batch, so only the projections of the first frames have to exist when it starts.  xp / XW are laid out
+  // time-major, the first T0 frames are projected up front, the persistent kernel starts on a high-priority stream and
+  // the rest of the projection GEMM runs next to it on the caller's stream - held back (cuStreamWaitValue32) until every
+  // CTA of the persistent kernel is resident: clusters placed around a running GEMM end up scattered over the chip and
+  // the whole chain runs 20-30 % slower (measured).  A device flag, set in stream order after that GEMM, is acquired by
+  // the kernel's owners before they touch frame T0.  Results are bitwise those of the serial order.
+  // Off (serial order) when: DRNMF_FWD_OVERLAP=0; the plan uses more than half of the SMs (the GEMM would crawl on the
+  // rest); kernels cannot run concurrently (CUDA_LAUNCH_BLOCKING, an injected profiler / sanitizer serialises launches);
+  // stream memory operations are unavailable; or a previous pipelined call on this handle timed out on the flag.
+  int T0 = T;
+  {
+    const char* e = getenv("DRNMF_FWD_OVERLAP");
+    const bool forced = e && !strcmp(e, "force");
+    bool want = !(e && !strcmp(e, "0")) && !rec_simt && T >= 16 && !h->no_overlap;
+    if (want && !forced) {
+      const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+      if ((lb && atoi(lb) != 0) || getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) want = false;
+      // without the cooperative launch nothing guarantees that every CTA becomes resident: the stream would wait for ever
+      const char* cp = getenv("DRNMF_REC_COOP");
+      if (cp && !strcmp(cp, "0")) want = false;
+    }
+    if (want) {
+      const bool env_plan = getenv("DRNMF_REC_KS") || getenv("DRNMF_REC_G") || getenv("DRNMF_REC_NB") || getenv("DRNMF_REC_NOSPLIT");
+      if (env_plan || h->plan_B != B) { h->plan_ctas = recurrent_plan_ctas(h, B); h->plan_B = B; }
+      if (2 * h->plan_ctas > h->num_sms) want = false;
+    }
+    if (want && stream_wait_geq(nullptr, nullptr, 0) != 0) want = false;      // probe only
+    if (want) { T0 = (T + 5) / 6; if (T0 < 4) T0 = 4; }
+  }
+  const bool overlap = T0 < T;
+  if (overlap && !h->hi_ready) {
+    int least = 0, greatest = 0;
+    DRNMF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    DRNMF_CUDA(cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, greatest));
+    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[0], cudaEventDisableTiming));
+    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[1], cudaEventDisableTiming));
+    h->hi_ready = true;
+  }
+  w.xw_tmajor = overlap ? 1 : 0; w.xw_t0 = overlap ? T0 : 0;
+  h->last_fwd_tmajor = overlap;
+  if (!overlap) w.xw_ready = nullptr;
+  DRNMF_CUDA(cudaEventRecord(h->ev[0], st));
+  if (overlap) DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 0, 8, st));
+  const size_t Fh = (size_t)h->F;
+  auto upload = [&](int t0, int nt) {       // frames [t0, t0 + nt) of every utterance: B runs of nt * F floats
+    return cudaMemcpy2DAsync(const_cast<float*>(x) + (size_t)t0 * Fh, (size_t)T * Fh * 4, x_host + (size_t)t0 * Fh, (size_t)T * Fh * 4,
+                             (size_t)nt * Fh * 4, (size_t)B, cudaMemcpyHostToDevice, st);
+  };
+  const bool split_in = overlap && x_host;
+  if (x_host) DRNMF_CUDA(split_in ? upload(0, T0) : cudaMemcpyAsync(const_cast<float*>(x), x_host, (size_t)BT * Fh * 4, cudaMemcpyHostToDevice, st));
+  bool hook_pending = after_upload != nullptr;
+  if (hook_pending && !split_in) { hook_pending = false; if ((rc = after_upload(hook_arg))) return rc; }
+  if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st, overlap ? B : 0, 0, split_in ? T0 : 0))) return rc;
+  DRNMF_CUDA(cudaEventRecord(h->ev[1], st));
+  auto project = [&](size_t row0, size_t rows) {   // XW[row][k*Rp + j] = x~[row] . W_k[:, j] + b_k[j] for a block of rows
+    GemmArgs a{};
+    a.A_hi = w.xp_hi + row0 * h->Fp; a.A_lo = w.xp_lo + row0 * h->Fp; a.lda = h->Fp;
+    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = h->Fp;
+    a.M = (int)rows; a.N = h->K * h->Rp; a.Kd = h->Fp;
+    a.C = w.XW + row0 * (size_t)h->K * h->Rp; a.ldc = h->K * h->Rp; a.M_valid = (int)rows; a.N_valid = a.N;
+    a.bias = h->bias;
+    a.M_plan = BT;
+    return run_gemm(h, EPI_STORE, a, st);
+  };
+  if ((rc = project(0, (size_t)B * T0))) return rc;
+  cudaStream_t rst = st;                             // stream of the recurrence
+  if (overlap) {
+    DRNMF_CUDA(cudaEventRecord(h->ev_ov[0], st));
+    DRNMF_CUDA(cudaStreamWaitEvent(h->hi, h->ev_ov[0], 0));
+    rst = h->hi;
+  }
+  DRNMF_CUDA(cudaEventRecord(h->ev[2], rst));
+  rc = rec_simt ? launch_recurrent_simt(h, w, B, T, H, rst) : launch_recurrent_tc(h, w, B, T, H, rst);
+  if (rc) {
+    if (overlap) cudaStreamSynchronize(h->hi);
+    return rc;
+  }
+  DRNMF_CUDA(cudaEventRecord(h->ev[3], rst));
+  if (overlap) {
+    DRNMF_CUDA(cudaEventRecord(h->ev_ov[1], h->hi));
+    if (split_in) DRNMF_CUDA(upload(T0, T - T0));            // copy engine only: travels while the kernel is being placed
+    if (hook_pending) { hook_pending = false; if ((rc = after_upload(hook_arg))) { cudaStreamSynchronize(h->hi); return rc; } }
+    const unsigned int n_cta = (unsigned int)(h->rec_cfg[1] * h->rec_cfg[2] * h->rec_groups);
+    if (stream_wait_geq(st, w.xw_ready + 1, n_cta)) { set_error("cuStreamWaitValue32 failed"); cudaStreamSynchronize(h->hi); return DRNMF_ERR_CUDA; }
+    if (split_in && (rc = launch_mask_pad(h, x, BT, mask_value, w, st, B, T0, T - T0))) { cudaStreamSynchronize(h->hi); return rc; }
+    if ((rc = project((size_t)B * T0, (size_t)B * (T - T0)))) { cudaStreamSynchronize(h->hi); return rc; }
+    DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 1, 4, st));     // 0x01010101, ordered after the GEMM on the caller's stream
+    DRNMF_CUDA(cudaStreamWaitEvent(st, h->ev_ov[1], 0));
+  }
+  if (irm) {   // recon + mask: irm = exp(log(eps + H_c E_c) - log(eps + H_c E_c + H_n E_n))
+    GemmArgs a{};
+    a.A_hi = w.Hp_hi; a.A_lo = w.Hp_lo; a.lda = h->Rp;
+    a.B_hi = h->EcT_hi; a.B_lo = h->EcT_lo; a.B2_hi = h->EnT_hi; a.B2_lo = h->EnT_lo; a.ldb = h->Rp;
+    a.M = BT; a.N = h->F; a.Kd = h->Rp;
+    a.C = irm; a.ldc = h->F; a.M_valid = BT; a.N_valid = h->F;
+    a.square = (h->flags & DRNMF_FLAG_SQUARE_IRM) ? 1 : 0;
+    if ((rc = run_gemm(h, EPI_RECON, a, st))) return rc;
+  }
+  DRNMF_CUDA(cudaEventRecord(h->ev[4], st));
+  h->ev_valid = true;
+  if (h->impl != DRNMF_IMPL_SIMT && final_check) {
+    int code = 0;
+    rc = check_dev_error(h, st, "drnmf_forward", &code);
+    if (rc == DRNMF_ERR_DEVICE && code == 215 && overlap) {
+      // the second projection chunk never ran next to the persistent kernel (launches are being serialised by a tool
+      // this library did not recognise): from now on this handle keeps the serial order; redo the call that way
+      h->no_overlap = true;
+      return forward_core(h, x, x_host, B, T, mask_value, H, irm, ws, ws_bytes, stream, nullptr, nullptr, actT_hi, actT_lo, true);   // (the hook has run: not again)
+    }
+    return rc;
+  }
+  return DRNMF_OK;
+}
+
+
 }  // namespace drnmf
 
 extern "C" {
@@ -196,155 +343,9 @@ size_t drnmf_workspace_bytes(const drnmf_handle* h, int B, int T) {
   return carve_forward_ws(h, B, T, nullptr).bytes;
 }
 
-// x_host != NULL (drnmf_enhance_host): x is the device destination of the input that still sits in host memory; the
-// copy is issued here - in the pipelined order only the first frames in front of the recurrence, the rest under it.
-// after_upload (optional) runs on the host right after the last piece of the input copy has been enqueued on the stream:
-// drnmf_enhance_host queues its second, larger copy (the complex STFT, needed only by the synthesis) behind it.
-typedef int (*upload_hook_fn)(void*);
-static int forward_impl(drnmf_handle* h, const float* x, const float* x_host, int B, int T, float mask_value, float* H,
-                        float* irm, void* ws, size_t ws_bytes, void* stream, upload_hook_fn after_upload = nullptr,
-                        void* hook_arg = nullptr);
-
 int drnmf_forward(drnmf_handle* h, const float* x, int B, int T, float mask_value, float* H, float* irm, void* ws,
                   size_t ws_bytes, void* stream) {
-  return forward_impl(h, x, nullptr, B, T, mask_value, H, irm, ws, ws_bytes, stream);
-}
-
-static int forward_impl(drnmf_handle* h, const float* x, const float* x_host, int B, int T, float mask_value, float* H,
-                        float* irm, void* ws, size_t ws_bytes, void* stream, upload_hook_fn after_upload, void* hook_arg) {
-  DRNMF_CHECK(h, "NULL handle");
-  int rc = check_device(h);
-  if (rc) return rc;
-  DRNMF_CHECK(h->params_set, "drnmf_forward before drnmf_set_params");
-  DRNMF_CHECK(x && ws && B >= 1 && T >= 1, "drnmf_forward: bad arguments (x=%p ws=%p B=%d T=%d)", (const void*)x, ws, B, T);
-  DRNMF_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
-  FwdWorkspace w = carve_forward_ws(h, B, T, ws);
-  if (ws_bytes < w.bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int BT = B * T;
-  if (!h->ev_ready) {
-    for (auto& e : h->ev) DRNMF_CUDA(cudaEventCreate(&e));
-    h->ev_ready = true;
-  }
-  h->ev_valid = false;
-  bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
-  {
-    const char* e = getenv("DRNMF_RECURRENT");      // debugging aid: mix tcgen05 GEMMs with the SIMT recurrence
-    if (e && !strcmp(e, "simt")) rec_simt = true;
-    if (e && !strcmp(e, "tc")) rec_simt = false;
-  }
-  // Pipelined projection (latency regime): the recurrence walks the frames in order and occupies 64 of the 148 SMs at
-  // the bench batch, so only the projections of the first frames have to exist when it starts.  xp / XW are laid out
-  // time-major, the first T0 frames are projected up front, the persistent kernel starts on a high-priority stream and
-  // the rest of the projection GEMM runs next to it on the caller's stream - held back (cuStreamWaitValue32) until every
-  // CTA of the persistent kernel is resident: clusters placed around a running GEMM end up scattered over the chip and
-  // the whole chain runs 20-30 % slower (measured).  A device flag, set in stream order after that GEMM, is acquired by
-  // the kernel's owners before they touch frame T0.  Results are bitwise those of the serial order.
-  // Off (serial order) when: DRNMF_FWD_OVERLAP=0; the plan uses more than half of the SMs (the GEMM would crawl on the
-  // rest); kernels cannot run concurrently (CUDA_LAUNCH_BLOCKING, an injected profiler / sanitizer serialises launches);
-  // stream memory operations are unavailable; or a previous pipelined call on this handle timed out on the flag.
-  int T0 = T;
-  {
-    const char* e = getenv("DRNMF_FWD_OVERLAP");
-    const bool forced = e && !strcmp(e, "force");
-    bool want = !(e && !strcmp(e, "0")) && !rec_simt && T >= 16 && !h->no_overlap;
-    if (want && !forced) {
-      const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
-      if ((lb && atoi(lb) != 0) || getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) want = false;
-      // without the cooperative launch nothing guarantees that every CTA becomes resident: the stream would wait for ever
-      const char* cp = getenv("DRNMF_REC_COOP");
-      if (cp && !strcmp(cp, "0")) want = false;
-    }
-    if (want) {
-      const bool env_plan = getenv("DRNMF_REC_KS") || getenv("DRNMF_REC_G") || getenv("DRNMF_REC_NB") || getenv("DRNMF_REC_NOSPLIT");
-      if (env_plan || h->plan_B != B) { h->plan_ctas = recurrent_plan_ctas(h, B); h->plan_B = B; }
-      if (2 * h->plan_ctas > h->num_sms) want = false;
-    }
-    if (want && stream_wait_geq(nullptr, nullptr, 0) != 0) want = false;      // probe only
-    if (want) { T0 = (T + 5) / 6; if (T0 < 4) T0 = 4; }
-  }
-  const bool overlap = T0 < T;
-  if (overlap && !h->hi_ready) {
-    int least = 0, greatest = 0;
-    DRNMF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    DRNMF_CUDA(cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, greatest));
-    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[0], cudaEventDisableTiming));
-    DRNMF_CUDA(cudaEventCreateWithFlags(&h->ev_ov[1], cudaEventDisableTiming));
-    h->hi_ready = true;
-  }
-  w.xw_tmajor = overlap ? 1 : 0; w.xw_t0 = overlap ? T0 : 0;
-  if (!overlap) w.xw_ready = nullptr;
-  DRNMF_CUDA(cudaEventRecord(h->ev[0], st));
-  if (overlap) DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 0, 8, st));
-  const size_t Fh = (size_t)h->F;
-  auto upload = [&](int t0, int nt) {       // frames [t0, t0 + nt) of every utterance: B runs of nt * F floats
-    return cudaMemcpy2DAsync(const_cast<float*>(x) + (size_t)t0 * Fh, (size_t)T * Fh * 4, x_host + (size_t)t0 * Fh, (size_t)T * Fh * 4,
-                             (size_t)nt * Fh * 4, (size_t)B, cudaMemcpyHostToDevice, st);
-  };
-  const bool split_in = overlap && x_host;
-  if (x_host) DRNMF_CUDA(split_in ? upload(0, T0) : cudaMemcpyAsync(const_cast<float*>(x), x_host, (size_t)BT * Fh * 4, cudaMemcpyHostToDevice, st));
-  bool hook_pending = after_upload != nullptr;
-  if (hook_pending && !split_in) { hook_pending = false; if ((rc = after_upload(hook_arg))) return rc; }
-  if ((rc = launch_mask_pad(h, x, BT, mask_value, w, st, overlap ? B : 0, 0, split_in ? T0 : 0))) return rc;
-  DRNMF_CUDA(cudaEventRecord(h->ev[1], st));
-  auto project = [&](size_t row0, size_t rows) {   // XW[row][k*Rp + j] = x~[row] . W_k[:, j] + b_k[j] for a block of rows
-    GemmArgs a{};
-    a.A_hi = w.xp_hi + row0 * h->Fp; a.A_lo = w.xp_lo + row0 * h->Fp; a.lda = h->Fp;
-    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = h->Fp;
-    a.M = (int)rows; a.N = h->K * h->Rp; a.Kd = h->Fp;
-    a.C = w.XW + row0 * (size_t)h->K * h->Rp; a.ldc = h->K * h->Rp; a.M_valid = (int)rows; a.N_valid = a.N;
-    a.bias = h->bias;
-    a.M_plan = BT;
-    return run_gemm(h, EPI_STORE, a, st);
-  };
-  if ((rc = project(0, (size_t)B * T0))) return rc;
-  cudaStream_t rst = st;                             // stream of the recurrence
-  if (overlap) {
-    DRNMF_CUDA(cudaEventRecord(h->ev_ov[0], st));
-    DRNMF_CUDA(cudaStreamWaitEvent(h->hi, h->ev_ov[0], 0));
-    rst = h->hi;
-  }
-  DRNMF_CUDA(cudaEventRecord(h->ev[2], rst));
-  rc = rec_simt ? launch_recurrent_simt(h, w, B, T, H, rst) : launch_recurrent_tc(h, w, B, T, H, rst);
-  if (rc) {
-    if (overlap) cudaStreamSynchronize(h->hi);
-    return rc;
-  }
-  DRNMF_CUDA(cudaEventRecord(h->ev[3], rst));
-  if (overlap) {
-    DRNMF_CUDA(cudaEventRecord(h->ev_ov[1], h->hi));
-    if (split_in) DRNMF_CUDA(upload(T0, T - T0));            // copy engine only: travels while the kernel is being placed
-    if (hook_pending) { hook_pending = false; if ((rc = after_upload(hook_arg))) { cudaStreamSynchronize(h->hi); return rc; } }
-    const unsigned int n_cta = (unsigned int)(h->rec_cfg[1] * h->rec_cfg[2] * h->rec_groups);
-    if (stream_wait_geq(st, w.xw_ready + 1, n_cta)) { set_error("cuStreamWaitValue32 failed"); cudaStreamSynchronize(h->hi); return DRNMF_ERR_CUDA; }
-    if (split_in && (rc = launch_mask_pad(h, x, BT, mask_value, w, st, B, T0, T - T0))) { cudaStreamSynchronize(h->hi); return rc; }
-    if ((rc = project((size_t)B * T0, (size_t)B * (T - T0)))) { cudaStreamSynchronize(h->hi); return rc; }
-    DRNMF_CUDA(cudaMemsetAsync(w.xw_ready, 1, 4, st));     // 0x01010101, ordered after the GEMM on the caller's stream
-    DRNMF_CUDA(cudaStreamWaitEvent(st, h->ev_ov[1], 0));
-  }
-  if (irm) {   // recon + mask: irm = exp(log(eps + H_c E_c) - log(eps + H_c E_c + H_n E_n))
-    GemmArgs a{};
-    a.A_hi = w.Hp_hi; a.A_lo = w.Hp_lo; a.lda = h->Rp;
-    a.B_hi = h->EcT_hi; a.B_lo = h->EcT_lo; a.B2_hi = h->EnT_hi; a.B2_lo = h->EnT_lo; a.ldb = h->Rp;
-    a.M = BT; a.N = h->F; a.Kd = h->Rp;
-    a.C = irm; a.ldc = h->F; a.M_valid = BT; a.N_valid = h->F;
-    a.square = (h->flags & DRNMF_FLAG_SQUARE_IRM) ? 1 : 0;
-    if ((rc = run_gemm(h, EPI_RECON, a, st))) return rc;
-  }
-  DRNMF_CUDA(cudaEventRecord(h->ev[4], st));
-  h->ev_valid = true;
-  if (h->impl != DRNMF_IMPL_SIMT) {
-    int code = 0;
-    rc = check_dev_error(h, st, "drnmf_forward", &code);
-    if (rc == DRNMF_ERR_DEVICE && code == 215 && overlap) {
-      // the second projection chunk never ran next to the persistent kernel (launches are being serialised by a tool
-      // this library did not recognise): from now on this handle keeps the serial order; redo the call that way
-      h->no_overlap = true;
-      return forward_impl(h, x, x_host, B, T, mask_value, H, irm, ws, ws_bytes, stream);      // (the hook has run: not again)
-    }
-    return rc;
-  }
-  return DRNMF_OK;
+  return forward_core(h, x, nullptr, B, T, mask_value, H, irm, ws, ws_bytes, stream);
 }
 
 int drnmf_stage_times(drnmf_handle* h, float* ms4) {
@@ -574,7 +575,12 @@ int drnmf_loss_and_grads_cb(drnmf_handle* h, const float* x, const float* y, int
   rc = train_loss_and_grads(h, x, y, B, T, mask_value, g_log_D, g_log_alph, g_log_lam1, g_log_h0, g_k_clean, g_k_noise,
                             loss_host, irm, ws, ws_bytes, st, layer_cb, user);
   if (rc) return rc;
-  return check_dev_error(h, st, "drnmf_loss_and_grads");
+  int code = 0;
+  rc = check_dev_error(h, st, "drnmf_loss_and_grads", &code);
+  // (a pipelined forward that timed out on its projection flag - launches serialised by an unrecognised tool - is not
+  //  redone here: the layer callbacks of this step have already fired; the handle keeps the serial order from now on)
+  if (rc == DRNMF_ERR_DEVICE && code == 215) h->no_overlap = true;
+  return rc;
 }
 
 // ---- end-to-end with host buffers ----------------------------------------------------------------
@@ -642,7 +648,7 @@ int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const float* stack_
   }
   DRNMF_CUDA(cudaMemcpyAsync(e.frames, frames_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   // the [Re;Im] stack (2/3 of the input bytes) is only read by the synthesis: it travels on a side stream under the
-  // network, behind the magnitudes on the copy engine (forward_impl calls the hook once their copy is enqueued) and
+  // network, behind the magnitudes on the copy engine (forward_core calls the hook once their copy is enqueued) and
   // before the mask/iSTFT kernels
   struct StackCopy { drnmf_handle* h; cudaStream_t st; float* dst; const float* src; size_t bytes; } sc{h, st, e.stack, stack_host, 2 * F * BT * 4};
   auto stack_hook = [](void* p) -> int {
@@ -657,7 +663,7 @@ int drnmf_enhance_host(drnmf_handle* h, const float* x_host, const float* stack_
   count_launch();
   DRNMF_CUDA(cudaMemsetAsync(e.audio, 0, (size_t)B * L * 4, st));
   // (the magnitudes are uploaded inside: in the pipelined order only the first frames precede the recurrence)
-  if ((rc = forward_impl(h, e.x, x_host, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream, stack_hook, &sc))) {
+  if ((rc = forward_core(h, e.x, x_host, B, T, mask_value, nullptr, e.irm, e.fwd, e.fwd_bytes, stream, stack_hook, &sc))) {
     cudaStreamSynchronize(h->side);      // the caller may release the workspace: let the side copy land first
     return rc;
   }

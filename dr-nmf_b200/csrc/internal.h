@@ -33,6 +33,7 @@ struct drnmf_handle {
   cudaEvent_t ev_ov[2];    // [0] first projection chunk done (caller stream), [1] recurrence done (hi stream)
   bool hi_ready;
   int plan_B, plan_ctas;   // cache: CTAs of the forward plan for batch plan_B (0 = empty)
+  bool last_fwd_tmajor;    // the last forward_core laid xp / XW out time-major (pipelined order)
   bool no_overlap;         // a pipelined drnmf_forward timed out on the projection flag: keep the serial order
   cudaStream_t side;       // copy stream of drnmf_enhance_host (the complex STFT is only needed after the recurrence)
   cudaEvent_t ev_side[2];  // [0] main stream reached the call, [1] side copy done
@@ -125,6 +126,11 @@ int launch_gemm_tc(GemmEpi epi, const GemmArgs& a, cudaStream_t st);
 // ---- recurrent.cu ----------------------------------------------------------------------------------
 int launch_recurrent_simt(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st);
+// api.cu: the forward pass with its pipelining (drnmf_forward, drnmf_enhance_host, and the forward of the training step)
+typedef int (*upload_hook_fn)(void*);
+int forward_core(drnmf_handle* h, const float* x, const float* x_host, int B, int T, float mask_value, float* H, float* irm,
+                 void* ws, size_t ws_bytes, void* stream, upload_hook_fn after_upload = nullptr, void* hook_arg = nullptr,
+                 float* actT_hi = nullptr, float* actT_lo = nullptr, bool final_check = true);
 int recurrent_plan_ctas(const drnmf_handle* h, int B);   // CTAs of the forward plan for batch B (INT_MAX-like large value when none)
 // progress (optional, device word, zeroed by the caller): the chain stores (release) the number of completely processed
 // frames (t = T-1, T-2, ...) as it goes; only honoured for single-tile, single-group plans (*progress_ok says so)

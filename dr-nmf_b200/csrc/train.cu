@@ -186,7 +186,7 @@ __global__ void k_reduce_pairs(const double* __restrict__ part, int n, double* _
 
 // masked input transposed to time-major frames, plus a row of ones at f == F (bias gradient): grid (TB/32, Fx/32)
 __global__ void k_xT(const float* __restrict__ xp, int B, int T, int Bp, int F, int Fp, int Fx, float* __restrict__ xT_hi,
-                     float* __restrict__ xT_lo) {
+                     float* __restrict__ xT_lo, int xp_tmajor) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, f0 = blockIdx.y * 32;     // c = t*Bp + b
   for (int y = threadIdx.y; y < 32; y += 8) {
@@ -194,7 +194,7 @@ __global__ void k_xT(const float* __restrict__ xp, int B, int T, int Bp, int F, 
     const int t = c / Bp, b = c % Bp;
     float v = 0.f;
     if (b < B && t < T) {
-      if (f < F) v = xp[((size_t)b * T + t) * Fp + f];
+      if (f < F) v = xp[(xp_tmajor ? (size_t)t * B + b : (size_t)b * T + t) * Fp + f];
       else if (f == F) v = 1.f;
     }
     tile[y][threadIdx.x] = v;
@@ -498,21 +498,11 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
   // ---------------- forward with stored activations ----------------
   DRNMF_CUDA(cudaMemsetAsync(w.fwd.actT_hi, 0, (size_t)K * Rp * TB * 4, st));     // padded utterances / rows stay zero
   DRNMF_CUDA(cudaMemsetAsync(w.fwd.actT_lo, 0, (size_t)K * Rp * TB * 4, st));
-  if ((rc = launch_mask_pad(h, x, BT, mask_value, w.fwd, st))) return rc;
-  {
-    GemmArgs a{};
-    a.A_hi = w.fwd.xp_hi; a.A_lo = w.fwd.xp_lo; a.lda = Fp;
-    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = Fp;
-    a.M = BT; a.N = K * Rp; a.Kd = Fp; a.C = w.fwd.XW; a.ldc = K * Rp; a.M_valid = BT; a.N_valid = a.N; a.bias = h->bias;
-    if ((rc = gemm(h, EPI_STORE, a, st))) return rc;
-  }
-  {
-    bool rec_simt = (h->impl == DRNMF_IMPL_SIMT);
-    const char* e = getenv("DRNMF_RECURRENT");
-    if (e && !strcmp(e, "simt")) rec_simt = true;
-    rc = rec_simt ? launch_recurrent_simt(h, w.fwd, B, T, nullptr, st) : launch_recurrent_tc(h, w.fwd, B, T, nullptr, st);
-    if (rc) return rc;
-  }
+  // masking, input projection (pipelined under the recurrence like drnmf_forward) and the recurrence with stored activations;
+  // the forward workspace is the head of this call's workspace; the device error word is read at the end of the step
+  if ((rc = forward_core(h, x, nullptr, B, T, mask_value, nullptr, nullptr, ws, ws_bytes, (void*)st, nullptr, nullptr,
+                         w.fwd.actT_hi, w.fwd.actT_lo, false))) return rc;
+  const int xp_tmajor = h->last_fwd_tmajor ? 1 : 0;          // row order of xp (the transposition below reads it)
   {
     GemmArgs a{};
     a.A_hi = w.fwd.Hp_hi; a.A_lo = w.fwd.Hp_lo; a.lda = Rp;
@@ -542,7 +532,7 @@ int train_loss_and_grads(drnmf_handle* h, const float* x, const float* y, int B,
     k_add_scal<<<1, 1, 0, st>>>(w.scal);
     count_launch(3);
   }
-  k_xT<<<dim3((unsigned)(TB / 32), w.Fx / 32), tb, 0, st>>>(w.fwd.xp_hi, B, T, Bp, F, Fp, w.Fx, w.xT_hi, w.xT_lo);
+  k_xT<<<dim3((unsigned)(TB / 32), w.Fx / 32), tb, 0, st>>>(w.fwd.xp_hi, B, T, Bp, F, Fp, w.Fx, w.xT_hi, w.xT_lo, xp_tmajor);
   count_launch();
   // ---------------- backward chain ----------------
   DRNMF_CUDA(cudaMemsetAsync(w.deltaT_hi, 0, (size_t)K * Rp * TB * 4, st));
@@ -724,21 +714,13 @@ int forward_all_hidden(drnmf_handle* h, const float* x, int B, int T, float mask
                        cudaStream_t st) {
   TrainWs w = carve_train(h, B, T, ws);
   if (ws_bytes < w.bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
-  const int K = h->K, Rp = h->Rp, Fp = h->Fp, BT = B * T;
+  const int K = h->K, Rp = h->Rp, Fp = h->Fp;
   const size_t TB = (size_t)w.TB;
   int rc;
   DRNMF_CUDA(cudaMemsetAsync(w.fwd.actT_hi, 0, (size_t)K * Rp * TB * 4, st));
   DRNMF_CUDA(cudaMemsetAsync(w.fwd.actT_lo, 0, (size_t)K * Rp * TB * 4, st));
-  if ((rc = launch_mask_pad(h, x, BT, mask_value, w.fwd, st))) return rc;
-  {
-    GemmArgs a{};
-    a.A_hi = w.fwd.xp_hi; a.A_lo = w.fwd.xp_lo; a.lda = Fp;
-    a.B_hi = h->Wt_hi; a.B_lo = h->Wt_lo; a.ldb = Fp;
-    a.M = BT; a.N = K * Rp; a.Kd = Fp; a.C = w.fwd.XW; a.ldc = K * Rp; a.M_valid = BT; a.N_valid = a.N; a.bias = h->bias;
-    if ((rc = gemm(h, EPI_STORE, a, st))) return rc;
-  }
-  rc = (h->impl == DRNMF_IMPL_SIMT) ? launch_recurrent_simt(h, w.fwd, B, T, nullptr, st) : launch_recurrent_tc(h, w.fwd, B, T, nullptr, st);
-  if (rc) return rc;
+  if ((rc = forward_core(h, x, nullptr, B, T, mask_value, nullptr, nullptr, ws, ws_bytes, (void*)st, nullptr, nullptr,
+                         w.fwd.actT_hi, w.fwd.actT_lo, false))) return rc;
   const size_t n = (size_t)B * K * h->R;
   k_gather_all_hidden<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.fwd.actT_hi, w.fwd.mvalid, B, T, w.fwd.Bp, K, h->R, Rp, H_all);
   count_launch();
