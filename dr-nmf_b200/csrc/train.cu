@@ -714,7 +714,7 @@ int forward_all_hidden(drnmf_handle* h, const float* x, int B, int T, float mask
                        cudaStream_t st) {
   TrainWs w = carve_train(h, B, T, ws);
   if (ws_bytes < w.bytes) { set_error("workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes); return DRNMF_ERR_WORKSPACE; }
-  const int K = h->K, Rp = h->Rp, Fp = h->Fp;
+  const int K = h->K, Rp = h->Rp;
   const size_t TB = (size_t)w.TB;
   int rc;
   DRNMF_CUDA(cudaMemsetAsync(w.fwd.actT_hi, 0, (size_t)K * Rp * TB * 4, st));
