@@ -131,7 +131,7 @@ typedef int (*upload_hook_fn)(void*);
 int forward_core(drnmf_handle* h, const float* x, const float* x_host, int B, int T, float mask_value, float* H, float* irm,
                  void* ws, size_t ws_bytes, void* stream, upload_hook_fn after_upload = nullptr, void* hook_arg = nullptr,
                  float* actT_hi = nullptr, float* actT_lo = nullptr, bool final_check = true);
-int recurrent_plan_ctas(const drnmf_handle* h, int B);   // CTAs of the forward plan for batch B (INT_MAX-like large value when none)
+int recurrent_plan_ctas(const drnmf_handle* h, int B);   // CTAs of the forward plan for batch B (a huge value when there is none or it cannot be pipelined)
 // progress (optional, device word, zeroed by the caller): the chain stores (release) the number of completely processed
 // frames (t = T-1, T-2, ...) as it goes; only honoured for single-tile, single-group plans (*progress_ok says so)
 int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, const float* dH, float* deltaT_hi,

@@ -363,7 +363,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
   RecArgs a = a_in;
   // pipelined forward: a CTA that executes is resident - the host holds the rest of the projection GEMM back until all
   // CTAs have counted themselves in (before any early return: the stream waits for the full count)
-  if (a_in.started && threadIdx.x == 0) atomicAdd(a_in.started, 1u);
+  if constexpr (NB <= 32) { if (a_in.started && threadIdx.x == 0) atomicAdd(a_in.started, 1u); }   // (latency plans only, see PIPE)
   // (the last group may hold fewer tiles: its schedule classes differ)
   SchedTab sch = (gridDim.z > 1 && blockIdx.z == gridDim.z - 1) ? sch_in.e_last : sch_in.e;
   const int tile0 = blockIdx.z * a_in.n_tiles;
@@ -375,7 +375,7 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
     a.mvalid += bo * a.T; a.flags += (size_t)tile0 * a.MT;
     a.hb_hi += bo * a.Rp; a.hb_lo += bo * a.Rp;
     if (!BWD) {
-      a.XW += (a.xw_tmajor ? bo : bo * a.T) * a.K * a.Rp; a.state += bo * a.Rp; a.psum += bo;
+      a.XW += ((NB <= 32 && a.xw_tmajor) ? bo : bo * a.T) * a.K * a.Rp; a.state += bo * a.Rp; a.psum += bo;
       a.Hp_hi += bo * a.T * a.Rp; a.Hp_lo += bo * a.T * a.Rp;
       if (a.H_user) a.H_user += bo * a.T * a.R;
     } else {
@@ -739,7 +739,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
 #pragma unroll
         for (int bi = 0; bi < CB; ++bi) {
           int b = i * NB + CB * my_cq + bi; b = b < a.B ? b : a.B - 1;
-          const size_t xrow = a.xw_tmajor ? (size_t)tc * a.Btot + b : (size_t)b * T + tc;
+          // (the pipelined, time-major order exists for the latency plans only: the 64-column variants, whose owners
+          //  bound the throughput regime, compile without it)
+          const size_t xrow = (NB <= 32 && a.xw_tmajor) ? (size_t)tc * a.Btot + b : (size_t)b * T + tc;
           xa[bi] = ldg_hint4(a.XW + xrow * KRp + (size_t)k * Rp + rowq, pol_x);
         }
       }
@@ -771,7 +773,9 @@ k_recurrent_tc(const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant
         if (i2 == n_tiles) { i2 = 0; if (++k2 == K) { k2 = 0; ++t2; } }
         // pipelined forward: the projections of the frames >= xw_t0 are still being computed on other SMs when this
         // kernel starts; they are acquired once, before the first load that touches them
-        if (a.xw_ready && t2 == a.xw_t0 && k2 == 0 && i2 == 0 && !poll_flag(a.xw_ready, 1u, err, 400000000LL)) rt_fail(a.dev_error, 215);
+        if constexpr (NB <= 32) {
+          if (a.xw_ready && t2 == a.xw_t0 && k2 == 0 && i2 == 0 && !poll_flag(a.xw_ready, 1u, err, 400000000LL)) rt_fail(a.dev_error, 215);
+        }
         fetch_xw(t2, k2, i2, xa_next);
       }
       // Loads that do not depend on this item's product are issued BEFORE the wait and consumed after it:
@@ -1684,7 +1688,8 @@ int launch_recurrent_bwd_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, cons
 
 int recurrent_plan_ctas(const drnmf_handle* h, int B) {
   const RecPlan p = choose_plan(h, B, false);
-  return p.ok ? p.KS * p.MT * p.G : (1 << 30);
+  // (the pipelined order is compiled into the 16- / 32-column variants only: any other plan counts as "too large")
+  return (p.ok && p.NB <= 32) ? p.KS * p.MT * p.G : (1 << 20);
 }
 
 int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H_user, cudaStream_t st) {
@@ -1701,6 +1706,7 @@ int launch_recurrent_tc(drnmf_handle* h, FwdWorkspace& w, int B, int T, float* H
   record_cfg(p, h->rec_cfg, &h->rec_groups);
   RecArgs& a = p.a;
   a.XW = w.XW; a.mvalid = w.mvalid; a.h0 = h->h0;
+  DRNMF_CHECK(!w.xw_tmajor || p.NB <= 32, "pipelined forward needs a 16- or 32-column plan (got NB=%d)", p.NB);
   a.xw_tmajor = w.xw_tmajor; a.xw_t0 = w.xw_t0; a.xw_ready = w.xw_tmajor ? w.xw_ready : nullptr; a.Btot = B;
   a.started = w.xw_tmajor ? w.xw_ready + 1 : nullptr;
   a.progress = nullptr;
