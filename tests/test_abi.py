@@ -70,3 +70,19 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_every_export_cites_the_reference_interface_it_replaces():
+    """include/drnmf.h: each entry point's comment names the reference file:line it stands in for (the drop-in boundary
+    is defined by those citations); only the instrumentation / test hooks have no counterpart in the reference."""
+    import re
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(here, "include", "drnmf.h")).read()
+    hooks = {"drnmf_version", "drnmf_last_error", "drnmf_launch_count", "drnmf_stage_times", "drnmf_recurrent_config",
+             "drnmf_recurrent_config2", "drnmf_debug_inject_error", "drnmf_get_derived", "drnmf_padded_dims"}
+    uncited = []
+    for m in re.finditer(r"DRNMF_API\s+[\w\s\*]+?\b(drnmf_\w+)\s*\(", text):
+        block = text[text[:m.start()].rfind("/*"):m.start()]
+        if m.group(1) not in hooks and not re.search(r"\.(py|m):\d+", block):
+            uncited.append(m.group(1))
+    assert not uncited, uncited
