@@ -4,7 +4,7 @@ persistent recurrence vs. the serial order, and bitwise equality of the two resu
 serial-retry path: the forced pipelined call times out on the projection flag, the handle falls back to the serial order."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from drnmf_b200 import engine, synth
 
 F, R, K = 513, 1000, 25

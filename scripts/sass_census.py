@@ -1,6 +1,6 @@
 """SASS census of dr-nmf_b200/libdrnmf.so: Blackwell-native instruction counts per kernel (cuobjdump -sass).
 UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG = TMA tensor load, UBLKCP = cp.async.bulk."""
-import collections, os, re, subprocess, sys
+import collections, os, re, subprocess
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "dr-nmf_b200", "libdrnmf.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout

@@ -2,7 +2,7 @@
 DRNMF_TRAIN_OVERLAP=1 against the serial order (=0), at the training batch of the reference (32 utterances)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from drnmf_b200 import engine, synth
 F, R, K = 513, 1000, 25
 p = synth.model_params(F, R, K)
